@@ -1,0 +1,167 @@
+/*
+ * v2e_b200 -- C ABI of the B200-native hot paths of SensorsINI/v2e.
+ *
+ * The reference is pure Python and has no FFI; its boundary for these paths is two
+ * Python classes. This header is the boundary a maintainer binds
+ * (ctypes / cffi) to put the sm_100a kernels behind
+ *   v2ecore/emulator.py:35   class EventEmulator  (generate_events, :619)
+ *   v2ecore/slomo.py:37      class SuperSloMo     (interpolate, :231)
+ *
+ * Conventions: every function returns 0 (V2E_OK) or a negative V2eStatus; no C++
+ * exception crosses the ABI; v2e_last_error() gives a message for the calling
+ * thread. Pointers named *_dev are CUDA device pointers, *_host are host pointers.
+ * All work is enqueued on the cudaStream_t passed as `stream` (a void* here so
+ * that the header needs no CUDA include); functions never synchronise unless their
+ * comment says so. A handle is not thread-safe (like the reference's objects).
+ */
+#ifndef V2E_B200_H
+#define V2E_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum V2eStatus {
+    V2E_OK = 0,
+    V2E_E_INVALID = -1,      /* bad argument */
+    V2E_E_CUDA = -2,         /* CUDA runtime error, see v2e_last_error() */
+    V2E_E_CAPACITY = -3,     /* event buffer too small; state is resumable, see v2e_emu_step */
+    V2E_E_ITER_CAP = -4,     /* a pixel produced more events in one frame than iter_cap */
+    V2E_E_STATE = -5,        /* call order violated (e.g. step before first frame) */
+    V2E_E_UNSUPPORTED = -6
+} V2eStatus;
+
+typedef enum V2eFrameDtype { V2E_U8 = 0, V2E_F32 = 1, V2E_F64 = 2 } V2eFrameDtype;
+
+const char *v2e_last_error(void);
+int v2e_version(void);
+
+/* ------------------------------------------------------------------------- */
+/* DVS pixel model: replaces EventEmulator.generate_events (emulator.py:619-1022)
+ * and the tensor helpers it calls (emulator_utils.py:18-173, 297-351).           */
+/* ------------------------------------------------------------------------- */
+
+typedef struct V2eEmuCfg {
+    int32_t width, height;          /* emulator.py: output_width / output_height */
+    int32_t per_pixel_thres;        /* 1 when sigma_thres > 0 (emulator.py:459-472); else the
+                                       nominal thresholds act as Python floats */
+    int32_t hdr;                    /* emulator.py:110 hdr / log_input */
+    double pos_thres_nominal;       /* emulator.py:88 */
+    double neg_thres_nominal;       /* emulator.py:89 */
+    double cutoff_hz;               /* emulator.py:91 ; >0 (or hdr) makes lp/base float64 */
+    double leak_rate_hz;            /* emulator.py:92 */
+    double leak_jitter_fraction;    /* emulator.py:96 */
+    double refractory_period_s;     /* emulator.py:93 */
+    double shot_noise_rate_hz;      /* emulator.py:94 */
+    double shot_inten_factor;       /* emulator.py:213 SHOT_NOISE_INTEN_FACTOR = 0.25 */
+    int32_t rng_mode;               /* 0 = replay: caller uploads the per-frame random fields the
+                                           reference would draw (bit-exact with torch's CPU generator);
+                                       1 = device: counter-based Philox4x32-10 inside the kernels */
+    int32_t iter_cap;               /* max events per pixel per frame that can be emitted (>=1) */
+    uint64_t seed;                  /* rng_mode 1 only */
+    int32_t csdvs;                  /* 1: centre-surround model enabled (emulator.py:245-265) */
+    int32_t max_frames_per_step;    /* upper bound of T in v2e_emu_step (control-block slots) */
+    double cs_tau_p_s, cs_tau_h_s;  /* emulator.py:1069-1073 (already floored at 1e-9) */
+} V2eEmuCfg;
+
+typedef struct V2eEmu V2eEmu;
+
+/* per-frame record the host reads back after a step (host copy of the device control block) */
+typedef struct V2eFrameInfo {
+    int32_t max_n;                  /* max_num_events_any_pixel, emulator.py:773-775 */
+    int32_t filter_active;          /* refractory_period_s > ts_step, emulator.py:830 */
+    uint32_t n_on, n_off;           /* rows emitted for this frame incl. shot noise */
+    uint32_t n_shot_on, n_shot_off;
+    uint32_t n_events;              /* n_on + n_off */
+    int32_t cs_steps;               /* Euler steps taken by the surround, emulator.py:1123 */
+    uint64_t ev_base;               /* row offset of this frame's first event in events_out */
+} V2eFrameInfo;
+
+int v2e_emu_create(const V2eEmuCfg *cfg, V2eEmu **out);
+int v2e_emu_destroy(V2eEmu *h);
+
+/* Uploads the 256-entry lin_log table for integer-valued input (emulator_utils.py:18-45
+ * evaluated by the caller with the reference expression, so it is exact by construction). */
+int v2e_emu_set_linlog_lut(V2eEmu *h, const float *lut256_host, void *stream);
+
+/* Per-pixel fields drawn at the first frame (emulator.py:439-511). Any pointer may be NULL
+ * when the feature is off. Host pointers, [H*W] float32. Synchronous copy. */
+int v2e_emu_set_fields(V2eEmu *h, const float *pos_thres_host, const float *neg_thres_host,
+                       const float *noise_rate_host);
+
+/* First frame (emulator.py:663-717): seeds lp / base / surround / timestamp_mem. Emits nothing.
+ * t_previous stays unchanged, as in the reference (it returns before emulator.py:1011). */
+int v2e_emu_first_frame(V2eEmu *h, const void *frame_dev, int frame_dtype, double t_frame,
+                        double t_previous, void *stream);
+
+/* T frames after the first. frames_dev: [T][H][W] of frame_dtype. t_frames_host[T]: absolute
+ * times; t_previous: time of the frame before frames[0].
+ * leak_randn_dev / shot_rand_dev: [T][H*W] float32, used in rng_mode 0 when the respective
+ * noise is on (the values torch.randn / torch.rand would return, emulator_utils.py:122-124,
+ * 340-343); NULL otherwise. NOTE: in the reference the shot draw of a frame happens after that
+ * frame's randperm calls; a caller that needs seed parity with noise on therefore steps one
+ * frame at a time with the phase functions below.
+ * events_out_dev: [capacity][4] float32 rows [t, x, y, p] (emulator.py:1020); rows of frame f
+ * start at info[f].ev_base; ev_base_start is the row at which this step starts writing.
+ * Rows within one (iteration, polarity) group are in no particular order (the reference shuffles
+ * them, emulator.py:866-870); groups are iteration-major, ON before OFF, shot noise last.
+ * Enqueues everything on `stream`, no host synchronisation.
+ * If the buffer is too small at frame f, that frame's emission and everything after it is
+ * skipped on the device (sticky abort), state is left as "frame f counted, not emitted";
+ * v2e_emu_collect() then reports V2E_E_CAPACITY with frames_done = f, and the caller resumes
+ * with v2e_emu_step(..., first = f, resume_emit = 1) into a larger buffer. */
+int v2e_emu_step(V2eEmu *h, const void *frames_dev, int frame_dtype, int T,
+                 const double *t_frames_host, double t_previous,
+                 const float *leak_randn_dev, const float *shot_rand_dev,
+                 float *events_out_dev, uint64_t capacity, uint64_t ev_base_start,
+                 int first, int resume_emit, void *stream);
+
+/* Copies the per-frame control blocks of the last step to the host. Synchronises `stream`.
+ * info_host[T]. *frames_done = number of frames fully emitted. Returns V2E_OK,
+ * V2E_E_CAPACITY or V2E_E_ITER_CAP. */
+int v2e_emu_collect(V2eEmu *h, V2eFrameInfo *info_host, int T, int *frames_done,
+                    uint64_t *rows_total, void *stream);
+
+/* ---- single-frame phases (what v2e_emu_step enqueues per frame), exposed so that a host
+ * that must replay torch's CPU generator can interleave its draws (RNG parity) */
+/* phase 1: low-pass, leak, event counts, global max (emulator.py:663-775) and, when the
+ * refractory filter applies, the filtered per-iteration counts. Ends with the emission plan
+ * unless shot_pending. */
+int v2e_emu_phase_count(V2eEmu *h, const void *frame_dev, int frame_dtype, double t_frame,
+                        double t_previous, const float *leak_randn_dev,
+                        const float *shot_rand_dev, int shot_pending, uint64_t capacity,
+                        uint64_t ev_base_start, void *stream);
+/* per-(iteration,polarity) row counts of the frame just counted: counts_host[2*max_n]
+ * (ON, OFF interleaved). Synchronises. Returns max_n in *max_n. */
+int v2e_emu_read_counts(V2eEmu *h, int32_t *max_n, uint32_t *counts_host, int counts_cap,
+                        void *stream);
+/* phase 2 (rng_mode 0, shot noise on): flags from the uploaded uniform field
+ * (emulator_utils.py:326-349), then the emission plan. */
+int v2e_emu_phase_shot(V2eEmu *h, const void *frame_dev, int frame_dtype, double t_frame,
+                       double t_previous, const float *shot_rand_dev, uint64_t capacity,
+                       void *stream);
+/* phase 3: emission + state update (emulator.py:810-870, 906-942). */
+int v2e_emu_phase_emit(V2eEmu *h, double t_frame, double t_previous, float *events_out_dev,
+                       uint64_t capacity, void *stream);
+
+/* Measurement hooks: when enabled, v2e_emu_step brackets each of its kernels with CUDA events on
+ * `stream`. v2e_emu_profile_read synchronises and returns, for the last step, the summed device
+ * time (ms) and launch count of the {update, filter, emit} kernels. */
+int v2e_emu_profile(V2eEmu *h, int enable);
+int v2e_emu_profile_read(V2eEmu *h, float *ms_sum3, int *launches3, void *stream);
+
+/* State access for parity probes (emulator.py:756-764 reads them by name). which:
+ * 0 lp_log_frame, 1 base_log_frame, 2 pos_thres, 3 neg_thres, 4 noise_rate_array,
+ * 5 timestamp_mem, 6 cs_surround_frame. dst_host must hold H*W elements of the state's
+ * dtype (*elem_size returns 4 or 8). Synchronous. */
+int v2e_emu_get_state(V2eEmu *h, int which, void *dst_host, int *elem_size);
+int v2e_emu_state_is_f64(V2eEmu *h);
+/* device pointer of a state array (same `which`), for zero-copy views */
+void *v2e_emu_state_ptr(V2eEmu *h, int which);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* V2E_B200_H */

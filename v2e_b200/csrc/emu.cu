@@ -1,0 +1,1148 @@
+// DVS pixel model for sm_100a -- hand-written CUDA behind the C ABI in include/v2e_b200.h.
+//
+// Replaces (reference = SensorsINI/v2e, /root/reference):
+//   v2ecore/emulator.py:619-1022  EventEmulator.generate_events
+//   v2ecore/emulator_utils.py:18-173, 297-351  lin_log, rescale_intensity_frame, low_pass_filter,
+//       subtract_leak_current, compute_event_map, generate_shot_noise
+//
+// Per frame the reference launches ~40 eager ops + one D2H sync per emitted-event iteration. Here a
+// frame is at most three streaming kernels, all on the caller's stream, no host sync:
+//   update : frame + per-pixel state -> new state, signed event count per pixel (int16 record),
+//            global max (atomicMax), per-(iteration,polarity) histogram
+//   filter : only when refractory_period_s > 0: replays the refractory filter on active pixels to
+//            get the filtered histogram
+//   emit   : active pixels only: block-aggregated compaction into the packed [N][4] float32 rows,
+//            base / timestamp_mem patch
+// The "plan" (segment offsets of the iteration-major output, running row offset, capacity check)
+// is computed by the last block to finish the last counting kernel of the frame.
+//
+// Arithmetic is bit-compatible with the reference's CPU path: float64 where torch promotes to
+// float64, float32 products where a Python scalar meets a float32 tensor, ATen's floor-division
+// and linspace formulas. This TU must be compiled with -fmad=false; the only fused multiply-adds
+// are the explicit fmaf() in linspace_f32().
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/v2e_b200.h"
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kVec = 4;                 // pixels per thread
+constexpr int kSegSmem = 64;            // (iteration,polarity) segments aggregated in shared memory
+constexpr int kRecShift = 2;            // record = (signed count << 2) | shot_off << 1 | shot_on
+constexpr int kRecMaxCount = 8191;
+
+struct FrameCtrl {                      // one per frame slot, device memory, zeroed per step
+    int32_t max_n;
+    int32_t filter_active;
+    uint32_t done[3];                   // last-block tickets: update, filter, shot
+    uint32_t n_on, n_off, n_shot_on, n_shot_off, n_events;
+    int32_t cs_steps;
+    int32_t planned;
+    uint64_t ev_base;
+    uint64_t pad;
+};
+static_assert(sizeof(FrameCtrl) == 64, "FrameCtrl layout");
+
+struct EmuDev {                         // passed by value to every kernel
+    int32_t n, W, H, n_pad;
+    int32_t per_pixel_thres, hdr, state_f64, csdvs;
+    int32_t leak_on, lowpass_on, shot_on, refr_on;
+    int32_t rng_mode, iter_cap, seg_stride, max_slots;
+    double pos_nom, neg_nom;
+    float leak_rate_f, leak_jit_f, refr_f, pad0;
+    double refr_d, shot_inten_m1;       // refractory_period_s ; (SHOT_NOISE_INTEN_FACTOR-1)
+    uint64_t seed;
+    void *lp, *base;
+    float *pos_thres, *neg_thres, *noise_rate, *tmem;
+    double *surround;
+    int16_t *rec;
+    const float *lut;                   // [256] lin_log
+    FrameCtrl *ctrl;                    // [max_slots+1]
+    uint32_t *hist_pre, *hist_post, *segoff, *cursor;   // [max_slots][seg_stride]
+    int32_t *abort_flag;                // [2]: status, slot
+};
+
+struct FrameParams {
+    double t_prev, t_frame, dt;
+    double eps_scale;                   // delta_time / tau          (emulator_utils.py:84)
+    float dt_f;                         // float32(delta_time)       (emulator_utils.py:129)
+    uint32_t frame_index;               // Philox counter word
+    double shot_c;                      // (shot_noise_rate_hz/2)*delta_time (emulator_utils.py:323-324)
+    uint64_t capacity;
+};
+
+// ---------------------------------------------------------------------------------------------
+// ATen restatements
+// ---------------------------------------------------------------------------------------------
+// aten/src/ATen/native/BinaryOps.h div_floor_floating, a >= 0, b > 0
+template <typename S> __device__ __forceinline__ int32_t div_floor_count(S a, S b);
+template <> __device__ __forceinline__ int32_t div_floor_count<double>(double a, double b) {
+    if (a < b) return 0;                // fmod(a,b)=a -> (a-a)/b = 0
+    double mod = fmod(a, b);
+    double div = (a - mod) / b;
+    double fl = floor(div);
+    if (div - fl > 0.5) fl += 1.0;
+    return (int32_t)fl;
+}
+template <> __device__ __forceinline__ int32_t div_floor_count<float>(float a, float b) {
+    if (a < b) return 0;
+    float mod = fmodf(a, b);
+    float div = (a - mod) / b;
+    float fl = floorf(div);
+    if (div - fl > 0.5f) fl += 1.0f;
+    return (int32_t)fl;
+}
+
+struct TsParams {                       // torch.linspace(t_prev+ts_step, t_frame, steps, float32)
+    float start, end, step;
+    int32_t steps;
+    int32_t filter_active;
+};
+__device__ __forceinline__ TsParams make_ts(const FrameParams &p, int32_t max_n, double refr_d) {
+    TsParams t;
+    t.steps = max_n > 0 ? max_n : 1;
+    double ts_step = p.dt / (double)t.steps;             // emulator.py:792
+    t.start = (float)(p.t_prev + ts_step);
+    t.end = (float)p.t_frame;
+    t.step = t.steps > 1 ? (t.end - t.start) / (float)(t.steps - 1) : 0.0f;
+    t.filter_active = refr_d > ts_step;                  // emulator.py:830
+    return t;
+}
+__device__ __forceinline__ float linspace_f32(const TsParams &t, int32_t i) {
+    if (t.steps == 1) return t.start;
+    if (i < t.steps / 2) return fmaf(t.step, (float)i, t.start);
+    return fmaf(-t.step, (float)(t.steps - 1 - i), t.end);
+}
+
+// lin_log for a non-integer value (emulator_utils.py:18-45); integer values use the table
+__device__ __forceinline__ float lin_log_eval(double x) {
+    const double f = (1.0 / 20.0) * 2.995732273553991;   // math.log(20)
+    double y = (x <= 20.0) ? x * f : log(x);
+    y = rint(y * 1e8) / 1e8;
+    return (float)y;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (rng_mode 1)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0;
+        key.y += W1;
+    }
+    return ctr;
+}
+__device__ __forceinline__ float u01_open(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+__device__ __forceinline__ float u01_half(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+
+// ---------------------------------------------------------------------------------------------
+// vector load helpers: 4 consecutive elements starting at i (i % 4 == 0)
+// ---------------------------------------------------------------------------------------------
+template <int FT> __device__ __forceinline__ void load_frame4(const void *frame, int i, int n, double x[4]) {
+    if (FT == V2E_U8) {
+        const uint8_t *f = (const uint8_t *)frame;
+        if (i + 4 <= n && ((((uintptr_t)f) + i) & 3) == 0) {
+            uchar4 v = __ldg((const uchar4 *)(f + i));
+            x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) x[k] = (i + k < n) ? (double)f[i + k] : 0.0;
+        }
+    } else if (FT == V2E_F32) {
+        const float *f = (const float *)frame;
+        if (i + 4 <= n && (((uintptr_t)(f + i)) & 15) == 0) {
+            float4 v = __ldg((const float4 *)(f + i));
+            x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) x[k] = (i + k < n) ? (double)f[i + k] : 0.0;
+        }
+    } else {
+        const double *f = (const double *)frame;
+#pragma unroll
+        for (int k = 0; k < 4; k++) x[k] = (i + k < n) ? f[i + k] : 0.0;
+    }
+}
+__device__ __forceinline__ void load_f32x4_any(const float *p, int i, int n, float v[4]) {
+    if (i + 4 <= n && (((uintptr_t)(p + i)) & 15) == 0) {
+        float4 t = __ldg((const float4 *)(p + i));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) v[k] = (i + k < n) ? p[i + k] : 0.0f;
+    }
+}
+// state arrays are padded to a multiple of 4 and 256-byte aligned: always vector
+__device__ __forceinline__ void ld4(const float *p, int i, float v[4]) {
+    float4 t = *(const float4 *)(p + i);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void ld4(const double *p, int i, double v[4]) {
+    double2 a = *(const double2 *)(p + i), b = *(const double2 *)(p + i + 2);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void st4(float *p, int i, const float v[4]) {
+    *(float4 *)(p + i) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void st4(double *p, int i, const double v[4]) {
+    *(double2 *)(p + i) = make_double2(v[0], v[1]);
+    *(double2 *)(p + i + 2) = make_double2(v[2], v[3]);
+}
+
+// shot-noise flags of one pixel (emulator_utils.py:323-349): bit0 ON, bit1 OFF
+__device__ __forceinline__ int shot_flags(const EmuDev &d, const FrameParams &p, double x, float rnd,
+                                          float thp, float thn) {
+    double inten01 = (x + 20.0) / 275.0;
+    double factor = p.shot_c * (d.shot_inten_m1 * inten01 + 1.0);
+    double pre_on, pre_off;
+    if (d.per_pixel_thres) {
+        pre_on = (double)((float)d.pos_nom / thp);       // emulator.py:475-478, float32 tensor
+        pre_off = (double)((float)d.neg_nom / thn);
+    } else {
+        pre_on = (double)(float)(d.pos_nom / d.pos_nom); // torch.div of two Python floats
+        pre_off = (double)(float)(d.neg_nom / d.neg_nom);
+    }
+    double r = (double)rnd;
+    int on = r > 1.0 - factor * pre_on;
+    int off = r < factor * pre_off;
+    return on | (off << 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// emission plan: run by the last block of the last counting kernel of a frame
+// ---------------------------------------------------------------------------------------------
+__device__ void plan_frame(const EmuDev &d, const FrameParams &p, int slot) {
+    __shared__ uint32_t s_part[kThreads];
+    __shared__ uint32_t s_tot[2];
+    FrameCtrl *c = d.ctrl + slot;
+    const int tid = threadIdx.x;
+    int32_t max_n = *(volatile int32_t *)&c->max_n;
+    if (max_n > d.iter_cap) {
+        if (tid == 0 && atomicCAS(d.abort_flag, 0, V2E_E_ITER_CAP) == 0) d.abort_flag[1] = slot;
+        return;
+    }
+    TsParams ts = make_ts(p, max_n, d.refr_d);
+    const uint32_t *h = (ts.filter_active && d.refr_on) ? d.hist_post + (size_t)slot * d.seg_stride
+                                                         : d.hist_pre + (size_t)slot * d.seg_stride;
+    const uint32_t *hs = d.hist_pre + (size_t)slot * d.seg_stride;     // shot counters live at the end
+    uint32_t *off = d.segoff + (size_t)slot * d.seg_stride;
+    const int nseg = 2 * max_n;
+    const int per = (nseg + kThreads - 1) / kThreads;
+    uint32_t sum = 0, on = 0;
+    for (int k = 0; k < per; k++) {
+        int s = tid * per + k;
+        if (s < nseg) {
+            uint32_t v = h[s];
+            sum += v;
+            if ((s & 1) == 0) on += v;
+        }
+    }
+    s_part[tid] = sum;
+    if (tid < 2) s_tot[tid] = 0;
+    __syncthreads();
+    atomicAdd(&s_tot[0], on);
+    // exclusive scan of the per-thread partial sums (256 entries, serial by warp 0 lane 0 is fine
+    // but a Hillis-Steele pass keeps it short)
+    for (int o = 1; o < kThreads; o <<= 1) {
+        uint32_t v = tid >= o ? s_part[tid - o] : 0;
+        __syncthreads();
+        s_part[tid] += v;
+        __syncthreads();
+    }
+    uint32_t run = s_part[tid] - sum;
+    for (int k = 0; k < per; k++) {
+        int s = tid * per + k;
+        if (s < nseg) {
+            off[s] = run;
+            run += h[s];
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t sig = s_part[kThreads - 1];
+        uint32_t sig_on = s_tot[0];
+        uint32_t shot_on = hs[2 * d.iter_cap], shot_off = hs[2 * d.iter_cap + 1];
+        off[2 * d.iter_cap] = sig;
+        off[2 * d.iter_cap + 1] = sig + shot_on;
+        uint32_t total = sig + shot_on + shot_off;
+        c->filter_active = ts.filter_active && d.refr_on;
+        c->n_on = sig_on + shot_on;
+        c->n_off = (sig - sig_on) + shot_off;
+        c->n_shot_on = shot_on;
+        c->n_shot_off = shot_off;
+        c->n_events = total;
+        uint64_t base = c->ev_base;
+        if (base + total > p.capacity) {
+            if (atomicCAS(d.abort_flag, 0, V2E_E_CAPACITY) == 0) d.abort_flag[1] = slot;
+        } else {
+            d.ctrl[slot + 1].ev_base = base + total;
+            c->planned = 1;
+        }
+        __threadfence();
+    }
+}
+
+__device__ __forceinline__ bool last_block(uint32_t *ticket) {
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (s_last) __threadfence();
+    return s_last;
+}
+
+// ---------------------------------------------------------------------------------------------
+// first frame (emulator.py:663-717)
+// ---------------------------------------------------------------------------------------------
+template <typename S, int FT>
+__global__ void __launch_bounds__(kThreads) emu_first_frame_kernel(EmuDev d, FrameParams p, const void *frame) {
+    __shared__ float s_lut[256];
+    s_lut[threadIdx.x] = d.lut[threadIdx.x];
+    __syncthreads();
+    int i0 = (blockIdx.x * kThreads + threadIdx.x) * kVec;
+    if (i0 >= d.n) return;
+    double x[4];
+    load_frame4<FT>(frame, i0, d.n, x);
+    S lp[4], base[4];
+    float tm[4];
+    double su[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        double xv = x[k];
+        float lnf = 0.f;
+        if (!d.hdr) lnf = (FT == V2E_U8 || (xv >= 0.0 && xv <= 255.0 && xv == floor(xv))) ? s_lut[(int)xv] : lin_log_eval(xv);
+        if (sizeof(S) == 8) {
+            double ln = d.hdr ? xv : (double)lnf;
+            double v = ln;
+            if (d.lowpass_on) {
+                double eps = ((xv + 20.0) / 275.0) * p.eps_scale;
+                if (eps > 1.0) eps = 1.0;
+                v = (1.0 - eps) * ln + eps * ln;      // lp seeded with log_new, still filtered once
+            }
+            lp[k] = (S)v;
+            su[k] = v;
+            base[k] = (S)(d.csdvs ? v - v : v);      // emulator.py:714
+        } else {
+            lp[k] = (S)lnf;
+            base[k] = (S)lnf;
+            su[k] = 0.0;
+        }
+        tm[k] = 0.0f - d.refr_f;                     // emulator.py:508-511
+    }
+    st4((S *)d.lp, i0, lp);
+    st4((S *)d.base, i0, base);
+    if (d.refr_on) st4(d.tmem, i0, tm);
+    if (d.csdvs) st4(d.surround, i0, su);
+}
+
+// ---------------------------------------------------------------------------------------------
+// update kernel: emulator.py:663-775 for 4 pixels per thread
+// ---------------------------------------------------------------------------------------------
+template <typename S, int FT>
+__global__ void __launch_bounds__(kThreads)
+emu_update_kernel(EmuDev d, FrameParams p, const void *frame, const float *leak_randn,
+                  const float *shot_rand, int slot, int do_plan, int lp_done) {
+    __shared__ float s_lut[256];
+    __shared__ uint32_t s_hist[kSegSmem + 2];
+    __shared__ int s_max;
+    if (*(volatile int32_t *)d.abort_flag) return;
+    const int tid = threadIdx.x;
+    s_lut[tid] = d.lut[tid];
+    if (tid < kSegSmem + 2) s_hist[tid] = 0;
+    if (tid == 0) s_max = 0;
+    __syncthreads();
+    FrameCtrl *c = d.ctrl + slot;
+    uint32_t *hist = d.hist_pre + (size_t)slot * d.seg_stride;
+    const int i0 = (blockIdx.x * kThreads + tid) * kVec;
+    int local_max = 0;
+    if (i0 < d.n) {
+        double x[4];
+        load_frame4<FT>(frame, i0, d.n, x);
+        S lp[4], base[4];
+        float thp[4], thn[4], nr[4], lr[4], sr[4];
+        double su[4];
+        ld4((const S *)d.lp, i0, lp);
+        ld4((const S *)d.base, i0, base);
+        if (d.per_pixel_thres) {
+            ld4(d.pos_thres, i0, thp);
+            ld4(d.neg_thres, i0, thn);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) { thp[k] = (float)d.pos_nom; thn[k] = (float)d.neg_nom; }
+        }
+        if (d.csdvs) ld4(d.surround, i0, su);
+        const bool shot_here = d.shot_on && (d.rng_mode == 1 || shot_rand != nullptr);
+        if (d.leak_on) {
+            ld4(d.noise_rate, i0, nr);
+            if (d.rng_mode == 0) load_f32x4_any(leak_randn, i0, d.n, lr);
+        }
+        if (shot_here && d.rng_mode == 0) load_f32x4_any(shot_rand, i0, d.n, sr);
+        if (d.rng_mode == 1 && (d.leak_on || d.shot_on)) {
+            uint2 key = make_uint2((uint32_t)d.seed, (uint32_t)(d.seed >> 32));
+            if (d.leak_on) {
+                uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 >> 2), p.frame_index, 0u, 0x6c65616bu), key);
+                float a = sqrtf(-2.0f * logf(u01_open(r.x))), b = sqrtf(-2.0f * logf(u01_open(r.z)));
+                float sa, ca, sb, cb;
+                sincosf(6.283185307179586f * u01_half(r.y), &sa, &ca);
+                sincosf(6.283185307179586f * u01_half(r.w), &sb, &cb);
+                lr[0] = a * ca; lr[1] = a * sa; lr[2] = b * cb; lr[3] = b * sb;
+            }
+            if (d.shot_on) {
+                uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 >> 2), p.frame_index, 1u, 0x73686f74u), key);
+                sr[0] = u01_half(r.x); sr[1] = u01_half(r.y); sr[2] = u01_half(r.z); sr[3] = u01_half(r.w);
+            }
+        }
+        short recs[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const double xv = x[k];
+            // photoreceptor low-pass (emulator_utils.py:57-109)
+            if (!lp_done) {
+                float lnf = 0.f;
+                if (!d.hdr)
+                    lnf = (FT == V2E_U8 || (xv >= 0.0 && xv <= 255.0 && xv == floor(xv))) ? s_lut[(int)xv]
+                                                                                          : lin_log_eval(xv);
+                if (sizeof(S) == 8) {
+                    double ln = d.hdr ? xv : (double)lnf;
+                    if (d.lowpass_on) {
+                        double eps = ((xv + 20.0) / 275.0) * p.eps_scale;
+                        if (eps > 1.0) eps = 1.0;
+                        lp[k] = (S)((1.0 - eps) * (double)lp[k] + eps * ln);
+                    } else {
+                        lp[k] = (S)ln;
+                    }
+                } else {
+                    lp[k] = (S)lnf;
+                }
+            }
+            // leak (emulator_utils.py:114-134): float32 products, subtract in S
+            if (d.leak_on) {
+                float rate = (d.leak_rate_f * nr[k]) * (1.0f - d.leak_jit_f * lr[k]);
+                float delta = (p.dt_f * rate) * thp[k];
+                base[k] = base[k] - (S)delta;
+            }
+            // difference and event counts (emulator.py:748-772, emulator_utils.py:137-173)
+            S diff;
+            if (sizeof(S) == 8 && d.csdvs) diff = (S)(((double)lp[k] - su[k]) - (double)base[k]);
+            else diff = lp[k] - base[k];
+            S tp, tn;
+            if (sizeof(S) == 8 && !d.per_pixel_thres) { tp = (S)d.pos_nom; tn = (S)d.neg_nom; }
+            else { tp = (S)thp[k]; tn = (S)thn[k]; }
+            int32_t cnt = 0;
+            if (diff > (S)0) cnt = div_floor_count<S>(diff, tp);
+            else if (diff < (S)0) cnt = -div_floor_count<S>(-diff, tn);
+            int flags = 0;
+            if (shot_here) flags = shot_flags(d, p, xv, sr[k], thp[k], thn[k]);
+            const bool valid = (i0 + k) < d.n;
+            if (!valid) { cnt = 0; flags = 0; }
+            int32_t mag = cnt < 0 ? -cnt : cnt;
+            if (mag > local_max) local_max = mag;
+            if (mag > kRecMaxCount) { cnt = cnt < 0 ? -kRecMaxCount : kRecMaxCount; }
+            recs[k] = (short)((cnt << kRecShift) | flags);
+            if (mag | flags) {
+                const int pol = cnt < 0;
+                const int lim = mag < d.iter_cap ? mag : d.iter_cap;
+                for (int it = 0; it < lim; it++) {
+                    int s = 2 * it + pol;
+                    if (s < kSegSmem) atomicAdd(&s_hist[s], 1u);
+                    else atomicAdd(&hist[s], 1u);
+                }
+                if (flags & 1) atomicAdd(&s_hist[kSegSmem], 1u);
+                if (flags & 2) atomicAdd(&s_hist[kSegSmem + 1], 1u);
+            }
+        }
+        if (!lp_done) st4((S *)d.lp, i0, lp);
+        if (d.leak_on) st4((S *)d.base, i0, base);
+        *(short4 *)(d.rec + i0) = make_short4(recs[0], recs[1], recs[2], recs[3]);
+    }
+    // block max -> one atomicMax per block
+    local_max = warp_reduce_max(local_max);
+    if ((tid & 31) == 0 && local_max > 0) atomicMax(&s_max, local_max);
+    __syncthreads();
+    if (tid == 0 && s_max > 0) atomicMax(&c->max_n, s_max);
+    if (tid < kSegSmem && s_hist[tid]) atomicAdd(&hist[tid], s_hist[tid]);
+    if (tid >= kSegSmem && tid < kSegSmem + 2 && s_hist[tid])
+        atomicAdd(&hist[2 * d.iter_cap + (tid - kSegSmem)], s_hist[tid]);
+    if (do_plan) {
+        if (last_block(&c->done[0])) plan_frame(d, p, slot);
+    }
+}
+
+// walks the emitted iterations of one active pixel; F(it, ts) is called for every event that
+// survives the refractory filter (emulator.py:819-850). Returns the number of surviving events
+// and updates tm (timestamp_mem) when the filter is active.
+template <typename F>
+__device__ __forceinline__ int walk_pixel(int mag, const TsParams &ts, bool filter, float refr_f,
+                                          float &tm, F &&f) {
+    int fin = 0;
+    for (int it = 0; it < mag; it++) {
+        float t = linspace_f32(ts, it);
+        if (filter) {
+            float since = t - tm;
+            if (!(since > refr_f)) continue;
+            tm = t;
+        }
+        f(it, t);
+        fin++;
+    }
+    return fin;
+}
+
+// ---------------------------------------------------------------------------------------------
+// filter-count kernel (only when refractory_period_s > 0): filtered histogram, no state writes
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+emu_filter_kernel(EmuDev d, FrameParams p, int slot, int do_plan) {
+    __shared__ uint32_t s_hist[kSegSmem];
+    if (*(volatile int32_t *)d.abort_flag) return;
+    const int tid = threadIdx.x;
+    FrameCtrl *c = d.ctrl + slot;
+    const int32_t max_n = *(volatile int32_t *)&c->max_n;
+    const TsParams ts = make_ts(p, max_n, d.refr_d);
+    if (ts.filter_active && max_n <= d.iter_cap) {
+        if (tid < kSegSmem) s_hist[tid] = 0;
+        __syncthreads();
+        uint32_t *hist = d.hist_post + (size_t)slot * d.seg_stride;
+        const int i0 = (blockIdx.x * kThreads + tid) * kVec;
+        if (i0 < d.n) {
+            short4 r4 = *(const short4 *)(d.rec + i0);
+            short recs[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                int cnt = recs[k] >> kRecShift;
+                if (cnt == 0) continue;
+                int mag = cnt < 0 ? -cnt : cnt, pol = cnt < 0;
+                float tm = d.tmem[i0 + k];
+                walk_pixel(mag, ts, true, d.refr_f, tm, [&](int it, float) {
+                    int s = 2 * it + pol;
+                    if (s < kSegSmem) atomicAdd(&s_hist[s], 1u);
+                    else atomicAdd(&hist[s], 1u);
+                });
+            }
+        }
+        __syncthreads();
+        if (tid < kSegSmem && s_hist[tid]) atomicAdd(&hist[tid], s_hist[tid]);
+    }
+    if (do_plan) {
+        if (last_block(&c->done[1])) plan_frame(d, p, slot);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// shot-noise flag kernel for rng_mode 0 when the uniform field arrives after the counts
+// ---------------------------------------------------------------------------------------------
+template <int FT>
+__global__ void __launch_bounds__(kThreads)
+emu_shot_kernel(EmuDev d, FrameParams p, const void *frame, const float *shot_rand, int slot) {
+    __shared__ uint32_t s_cnt[2];
+    if (*(volatile int32_t *)d.abort_flag) return;
+    const int tid = threadIdx.x;
+    if (tid < 2) s_cnt[tid] = 0;
+    __syncthreads();
+    FrameCtrl *c = d.ctrl + slot;
+    const int i0 = (blockIdx.x * kThreads + tid) * kVec;
+    if (i0 < d.n) {
+        double x[4];
+        float sr[4], thp[4], thn[4];
+        load_frame4<FT>(frame, i0, d.n, x);
+        load_f32x4_any(shot_rand, i0, d.n, sr);
+        if (d.per_pixel_thres) { ld4(d.pos_thres, i0, thp); ld4(d.neg_thres, i0, thn); }
+        else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) { thp[k] = (float)d.pos_nom; thn[k] = (float)d.neg_nom; }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (i0 + k >= d.n) continue;
+            int flags = shot_flags(d, p, x[k], sr[k], thp[k], thn[k]);
+            if (flags) {
+                d.rec[i0 + k] = (short)(d.rec[i0 + k] | flags);
+                if (flags & 1) atomicAdd(&s_cnt[0], 1u);
+                if (flags & 2) atomicAdd(&s_cnt[1], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    uint32_t *hist = d.hist_pre + (size_t)slot * d.seg_stride;
+    if (tid < 2 && s_cnt[tid]) atomicAdd(&hist[2 * d.iter_cap + tid], s_cnt[tid]);
+    if (last_block(&c->done[2])) plan_frame(d, p, slot);
+}
+
+// ---------------------------------------------------------------------------------------------
+// emit kernel: compaction of the active pixels into packed rows + state patch
+// (emulator.py:810-870, 906-942, 1024-1059)
+// ---------------------------------------------------------------------------------------------
+template <typename S>
+__global__ void __launch_bounds__(kThreads)
+emu_emit_kernel(EmuDev d, FrameParams p, int slot, float4 *events) {
+    __shared__ uint32_t s_cnt[kSegSmem + 2];
+    __shared__ uint32_t s_base[kSegSmem + 2];
+    if (*(volatile int32_t *)d.abort_flag) return;
+    const int tid = threadIdx.x;
+    FrameCtrl *c = d.ctrl + slot;
+    if (!c->planned) return;
+    if (c->n_events == 0) return;
+    const int32_t max_n = c->max_n;
+    const TsParams ts = make_ts(p, max_n, d.refr_d);
+    const bool filter = ts.filter_active && d.refr_on;
+    const float ts_last = linspace_f32(ts, ts.steps - 1);
+    const uint32_t *segoff = d.segoff + (size_t)slot * d.seg_stride;
+    uint32_t *cursor = d.cursor + (size_t)slot * d.seg_stride;
+    const uint64_t ev_base = c->ev_base;
+    if (tid < kSegSmem + 2) s_cnt[tid] = 0;
+    __syncthreads();
+    const int i0 = (blockIdx.x * kThreads + tid) * kVec;
+    short recs[4] = {0, 0, 0, 0};
+    bool any = false;
+    if (i0 < d.n) {
+        short4 r4 = *(const short4 *)(d.rec + i0);
+        recs[0] = r4.x; recs[1] = r4.y; recs[2] = r4.z; recs[3] = r4.w;
+        any = (r4.x | r4.y | r4.z | r4.w) != 0;
+    }
+    // pass 1: block-level counts per segment
+    if (any) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            int r = recs[k];
+            if (r == 0) continue;
+            int cnt = r >> kRecShift, flags = r & 3;
+            int mag = cnt < 0 ? -cnt : cnt, pol = cnt < 0;
+            if (mag) {
+                float tm = filter ? d.tmem[i0 + k] : 0.f;
+                walk_pixel(mag, ts, filter, d.refr_f, tm, [&](int it, float) {
+                    int s = 2 * it + pol;
+                    if (s < kSegSmem) atomicAdd(&s_cnt[s], 1u);
+                });
+            }
+            if (flags & 1) atomicAdd(&s_cnt[kSegSmem], 1u);
+            if (flags & 2) atomicAdd(&s_cnt[kSegSmem + 1], 1u);
+        }
+    }
+    __syncthreads();
+    if (tid < kSegSmem + 2) {
+        uint32_t n = s_cnt[tid];
+        if (n) {
+            int seg = tid < kSegSmem ? tid : 2 * d.iter_cap + (tid - kSegSmem);
+            s_base[tid] = segoff[seg] + atomicAdd(&cursor[seg], n);
+        }
+        s_cnt[tid] = 0;
+    }
+    __syncthreads();
+    // pass 2: write rows, patch state
+    if (any) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            int r = recs[k];
+            if (r == 0) continue;
+            const int idx = i0 + k;
+            int cnt = r >> kRecShift, flags = r & 3;
+            int mag = cnt < 0 ? -cnt : cnt, pol = cnt < 0;
+            const float fx = (float)(idx % d.W), fy = (float)(idx / d.W);
+            int fin = 0;
+            if (mag) {
+                float tm = filter ? d.tmem[idx] : 0.f;
+                const float pv = pol ? -1.0f : 1.0f;
+                fin = walk_pixel(mag, ts, filter, d.refr_f, tm, [&](int it, float t) {
+                    int s = 2 * it + pol;
+                    uint64_t row;
+                    if (s < kSegSmem) row = ev_base + s_base[s] + atomicAdd(&s_cnt[s], 1u);
+                    else row = ev_base + segoff[s] + atomicAdd(&cursor[s], 1u);
+                    events[row] = make_float4(t, fx, fy, pv);
+                });
+                if (filter && fin) d.tmem[idx] = tm;
+            }
+            if (fin || flags) {
+                S *basep = (S *)d.base + idx;
+                S b = *basep;
+                float th = pol ? (d.per_pixel_thres ? d.neg_thres[idx] : (float)d.neg_nom)
+                               : (d.per_pixel_thres ? d.pos_thres[idx] : (float)d.pos_nom);
+                float prod = (float)fin * th;            // int32*float32 -> float32 (emulator.py:936-937)
+                if (pol) b = b - (S)prod; else b = b + (S)prod;
+                if (flags) b = ((const S *)d.lp)[idx];   // emulator.py:940-942
+                *basep = b;
+            }
+            if (flags & 1) {
+                uint64_t row = ev_base + s_base[kSegSmem] + atomicAdd(&s_cnt[kSegSmem], 1u);
+                events[row] = make_float4(ts_last, fx, fy, 1.0f);
+            }
+            if (flags & 2) {
+                uint64_t row = ev_base + s_base[kSegSmem + 1] + atomicAdd(&s_cnt[kSegSmem + 1], 1u);
+                events[row] = make_float4(ts_last, fx, fy, -1.0f);
+            }
+        }
+    }
+}
+
+__global__ void emu_begin_step_kernel(EmuDev d, int slot, uint64_t ev_base) {
+    d.ctrl[slot].ev_base = ev_base;
+}
+
+__global__ void __launch_bounds__(kThreads) emu_plan_kernel(EmuDev d, FrameParams p, int slot) {
+    plan_frame(d, p, slot);
+}
+
+}  // namespace
+
+// =============================================================================================
+// host side
+// =============================================================================================
+struct V2eEmu {
+    V2eEmuCfg cfg;
+    EmuDev d;
+    int first_done;
+    int last_T;
+    uint32_t frame_counter;     // frames counted so far (Philox counter word, rng_mode 1)
+    uint32_t step_base;         // frame_counter at the start of the current step
+    double last_dt;             // delta_time of the last single-frame phase_count
+    int profile;                // 1: bracket every kernel of v2e_emu_step with CUDA events
+    cudaEvent_t *ev;            // [max_slots][3 kinds][2]
+    int prof_frames;
+    unsigned char *prof_used;   // [max_slots][3]
+    float *lut_dev;
+    FrameCtrl *ctrl_host;       // pinned
+    int32_t *abort_host;        // pinned [2]
+    size_t state_elem;
+};
+
+thread_local char g_err[512] = "";
+static int fail(int code, const char *fmt, const char *detail = "") {
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return code;
+}
+#define CU(call)                                                            \
+    do {                                                                    \
+        cudaError_t e_ = (call);                                            \
+        if (e_ != cudaSuccess) return fail(V2E_E_CUDA, #call ": %s", cudaGetErrorString(e_)); \
+    } while (0)
+
+extern "C" const char *v2e_last_error(void) { return g_err; }
+extern "C" int v2e_version(void) { return 100; }
+
+static FrameParams make_params(const V2eEmu *h, double t_frame, double t_prev, uint32_t frame_index,
+                               uint64_t capacity) {
+    FrameParams p;
+    memset(&p, 0, sizeof(p));
+    p.t_prev = t_prev;
+    p.t_frame = t_frame;
+    p.dt = t_frame - t_prev;                                    // emulator.py:656
+    if (h->cfg.cutoff_hz > 0) {
+        double tau = 1.0 / (M_PI * 2 * h->cfg.cutoff_hz);       // emulator_utils.py:80
+        p.eps_scale = p.dt / tau;
+    }
+    p.dt_f = (float)p.dt;
+    p.frame_index = frame_index;
+    p.shot_c = (h->cfg.shot_noise_rate_hz / 2) * p.dt;
+    p.capacity = capacity;
+    return p;
+}
+
+extern "C" int v2e_emu_create(const V2eEmuCfg *cfg, V2eEmu **out) {
+    if (!cfg || !out) return fail(V2E_E_INVALID, "null argument");
+    if (cfg->width <= 0 || cfg->height <= 0) return fail(V2E_E_INVALID, "bad frame size");
+    if ((int64_t)cfg->width * cfg->height > (1ll << 30)) return fail(V2E_E_INVALID, "frame too large");
+    if (cfg->iter_cap < 1 || cfg->iter_cap > kRecMaxCount) return fail(V2E_E_INVALID, "iter_cap out of range");
+    if (cfg->max_frames_per_step < 1) return fail(V2E_E_INVALID, "max_frames_per_step < 1");
+    if (cfg->csdvs && !(cfg->cutoff_hz > 0 || cfg->hdr))
+        return fail(V2E_E_UNSUPPORTED, "csdvs needs a float64 photoreceptor state (cutoff_hz > 0)");
+    V2eEmu *h = new V2eEmu();
+    memset(h, 0, sizeof(*h));
+    h->cfg = *cfg;
+    EmuDev &d = h->d;
+    d.W = cfg->width;
+    d.H = cfg->height;
+    d.n = cfg->width * cfg->height;
+    d.n_pad = (d.n + kVec - 1) / kVec * kVec;
+    d.per_pixel_thres = cfg->per_pixel_thres;
+    d.hdr = cfg->hdr;
+    d.state_f64 = (cfg->cutoff_hz > 0 || cfg->hdr) ? 1 : 0;
+    d.csdvs = cfg->csdvs;
+    d.leak_on = cfg->leak_rate_hz > 0;
+    d.lowpass_on = cfg->cutoff_hz > 0;
+    d.shot_on = cfg->shot_noise_rate_hz > 0;
+    d.refr_on = cfg->refractory_period_s > 0;
+    d.rng_mode = cfg->rng_mode;
+    d.iter_cap = cfg->iter_cap;
+    d.seg_stride = 2 * cfg->iter_cap + 2;
+    d.max_slots = cfg->max_frames_per_step;
+    d.pos_nom = cfg->pos_thres_nominal;
+    d.neg_nom = cfg->neg_thres_nominal;
+    d.leak_rate_f = (float)cfg->leak_rate_hz;
+    d.leak_jit_f = (float)cfg->leak_jitter_fraction;
+    d.refr_f = (float)cfg->refractory_period_s;
+    d.refr_d = cfg->refractory_period_s;
+    d.shot_inten_m1 = cfg->shot_inten_factor - 1;
+    d.seed = cfg->seed;
+    h->state_elem = d.state_f64 ? 8 : 4;
+    size_t np = (size_t)d.n_pad;
+#define ALLOC(ptr, bytes)                                                     \
+    do {                                                                      \
+        cudaError_t e_ = cudaMalloc((void **)&(ptr), (bytes));                \
+        if (e_ == cudaSuccess) e_ = cudaMemset((ptr), 0, (bytes));            \
+        if (e_ != cudaSuccess) { v2e_emu_destroy(h); return fail(V2E_E_CUDA, "cudaMalloc: %s", cudaGetErrorString(e_)); } \
+    } while (0)
+    ALLOC(d.lp, np * h->state_elem);
+    ALLOC(d.base, np * h->state_elem);
+    ALLOC(d.rec, np * sizeof(int16_t));
+    if (d.per_pixel_thres) { ALLOC(d.pos_thres, np * 4); ALLOC(d.neg_thres, np * 4); }
+    if (d.leak_on) ALLOC(d.noise_rate, np * 4);
+    if (d.refr_on) ALLOC(d.tmem, np * 4);
+    if (d.csdvs) ALLOC(d.surround, np * 8);
+    ALLOC(h->lut_dev, 256 * 4);
+    d.lut = h->lut_dev;
+    size_t slots = (size_t)d.max_slots;
+    ALLOC(d.ctrl, (slots + 1) * sizeof(FrameCtrl));
+    ALLOC(d.hist_pre, slots * d.seg_stride * 4);
+    ALLOC(d.hist_post, slots * d.seg_stride * 4);
+    ALLOC(d.segoff, slots * d.seg_stride * 4);
+    ALLOC(d.cursor, slots * d.seg_stride * 4);
+    ALLOC(d.abort_flag, 2 * sizeof(int32_t));
+#undef ALLOC
+    if (cudaMallocHost((void **)&h->ctrl_host, (slots + 1) * sizeof(FrameCtrl)) != cudaSuccess ||
+        cudaMallocHost((void **)&h->abort_host, 2 * sizeof(int32_t)) != cudaSuccess) {
+        v2e_emu_destroy(h);
+        return fail(V2E_E_CUDA, "cudaMallocHost failed");
+    }
+    *out = h;
+    return V2E_OK;
+}
+
+extern "C" int v2e_emu_destroy(V2eEmu *h) {
+    if (!h) return V2E_OK;
+    EmuDev &d = h->d;
+    void *ptrs[] = {d.lp, d.base, d.rec, d.pos_thres, d.neg_thres, d.noise_rate, d.tmem, d.surround,
+                    h->lut_dev, d.ctrl, d.hist_pre, d.hist_post, d.segoff, d.cursor, d.abort_flag};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    if (h->ctrl_host) cudaFreeHost(h->ctrl_host);
+    if (h->abort_host) cudaFreeHost(h->abort_host);
+    if (h->ev) {
+        for (int i = 0; i < d.max_slots * 6; i++) cudaEventDestroy(h->ev[i]);
+        delete[] h->ev;
+        delete[] h->prof_used;
+    }
+    delete h;
+    return V2E_OK;
+}
+
+extern "C" int v2e_emu_set_linlog_lut(V2eEmu *h, const float *lut, void *stream) {
+    if (!h || !lut) return fail(V2E_E_INVALID, "null argument");
+    CU(cudaMemcpyAsync(h->lut_dev, lut, 256 * 4, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    return V2E_OK;
+}
+
+extern "C" int v2e_emu_set_fields(V2eEmu *h, const float *pos, const float *neg, const float *nr) {
+    if (!h) return fail(V2E_E_INVALID, "null handle");
+    size_t bytes = (size_t)h->d.n * 4;
+    if (h->d.per_pixel_thres) {
+        if (!pos || !neg) return fail(V2E_E_INVALID, "per-pixel thresholds required");
+        CU(cudaMemcpy(h->d.pos_thres, pos, bytes, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(h->d.neg_thres, neg, bytes, cudaMemcpyHostToDevice));
+    }
+    if (h->d.leak_on) {
+        if (!nr) return fail(V2E_E_INVALID, "noise_rate field required when leak_rate_hz > 0");
+        CU(cudaMemcpy(h->d.noise_rate, nr, bytes, cudaMemcpyHostToDevice));
+    }
+    return V2E_OK;
+}
+
+static inline int grid_for(const EmuDev &d) { return (d.n_pad / kVec + kThreads - 1) / kThreads; }
+
+template <typename S>
+static int launch_first(V2eEmu *h, const FrameParams &p, const void *frame, int dt, cudaStream_t st) {
+    int g = grid_for(h->d);
+    switch (dt) {
+        case V2E_U8: emu_first_frame_kernel<S, V2E_U8><<<g, kThreads, 0, st>>>(h->d, p, frame); break;
+        case V2E_F32: emu_first_frame_kernel<S, V2E_F32><<<g, kThreads, 0, st>>>(h->d, p, frame); break;
+        case V2E_F64: emu_first_frame_kernel<S, V2E_F64><<<g, kThreads, 0, st>>>(h->d, p, frame); break;
+        default: return fail(V2E_E_INVALID, "bad frame dtype");
+    }
+    return V2E_OK;
+}
+
+extern "C" int v2e_emu_first_frame(V2eEmu *h, const void *frame, int dtype, double t_frame,
+                                   double t_previous, void *stream) {
+    if (!h || !frame) return fail(V2E_E_INVALID, "null argument");
+    FrameParams p = make_params(h, t_frame, t_previous, 0, 0);
+    int rc = h->d.state_f64 ? launch_first<double>(h, p, frame, dtype, (cudaStream_t)stream)
+                            : launch_first<float>(h, p, frame, dtype, (cudaStream_t)stream);
+    if (rc) return rc;
+    CU(cudaGetLastError());
+    h->first_done = 1;
+    return V2E_OK;
+}
+
+template <typename S>
+static int launch_update(V2eEmu *h, const FrameParams &p, const void *frame, int dt, const float *lr,
+                         const float *sr, int slot, int do_plan, int lp_done, cudaStream_t st) {
+    int g = grid_for(h->d);
+    switch (dt) {
+        case V2E_U8: emu_update_kernel<S, V2E_U8><<<g, kThreads, 0, st>>>(h->d, p, frame, lr, sr, slot, do_plan, lp_done); break;
+        case V2E_F32: emu_update_kernel<S, V2E_F32><<<g, kThreads, 0, st>>>(h->d, p, frame, lr, sr, slot, do_plan, lp_done); break;
+        case V2E_F64: emu_update_kernel<S, V2E_F64><<<g, kThreads, 0, st>>>(h->d, p, frame, lr, sr, slot, do_plan, lp_done); break;
+        default: return fail(V2E_E_INVALID, "bad frame dtype");
+    }
+    return V2E_OK;
+}
+
+static int launch_shot(V2eEmu *h, const FrameParams &p, const void *frame, int dt, const float *sr,
+                       int slot, cudaStream_t st) {
+    int g = grid_for(h->d);
+    switch (dt) {
+        case V2E_U8: emu_shot_kernel<V2E_U8><<<g, kThreads, 0, st>>>(h->d, p, frame, sr, slot); break;
+        case V2E_F32: emu_shot_kernel<V2E_F32><<<g, kThreads, 0, st>>>(h->d, p, frame, sr, slot); break;
+        case V2E_F64: emu_shot_kernel<V2E_F64><<<g, kThreads, 0, st>>>(h->d, p, frame, sr, slot); break;
+        default: return fail(V2E_E_INVALID, "bad frame dtype");
+    }
+    return V2E_OK;
+}
+
+struct ProfScope {
+    V2eEmu *h; int slot, kind; cudaStream_t st;
+    ProfScope(V2eEmu *h_, int slot_, int kind_, cudaStream_t st_) : h(h_), slot(slot_), kind(kind_), st(st_) {
+        if (h->profile) { cudaEventRecord(h->ev[(slot * 3 + kind) * 2], st); h->prof_used[slot * 3 + kind] = 1; }
+    }
+    ~ProfScope() { if (h->profile) cudaEventRecord(h->ev[(slot * 3 + kind) * 2 + 1], st); }
+};
+
+static size_t frame_elem(int dt) { return dt == V2E_U8 ? 1 : (dt == V2E_F32 ? 4 : 8); }
+
+// enqueue the counting kernels of one frame into `slot`
+static int enqueue_count(V2eEmu *h, const FrameParams &p, const void *frame, int dtype, const float *lr,
+                         const float *sr, int shot_pending, int slot, cudaStream_t st) {
+    const EmuDev &d = h->d;
+    if (d.rng_mode == 0 && d.leak_on && !lr) return fail(V2E_E_INVALID, "leak_randn field required in replay mode");
+    if (d.csdvs) return fail(V2E_E_UNSUPPORTED, "csdvs path not built yet");
+    const bool shot_in_update = d.shot_on && (d.rng_mode == 1 || sr != nullptr);
+    if (d.shot_on && !shot_in_update && !shot_pending)
+        return fail(V2E_E_INVALID, "shot_rand field required in replay mode (or shot_pending)");
+    const int plan_in_update = !d.refr_on && !shot_pending;
+    int rc;
+    {
+        ProfScope ps(h, slot, 0, st);
+        rc = d.state_f64 ? launch_update<double>(h, p, frame, dtype, lr, sr, slot, plan_in_update, 0, st)
+                         : launch_update<float>(h, p, frame, dtype, lr, sr, slot, plan_in_update, 0, st);
+    }
+    if (rc) return rc;
+    if (d.refr_on) {
+        ProfScope ps(h, slot, 1, st);
+        emu_filter_kernel<<<grid_for(d), kThreads, 0, st>>>(d, p, slot, !shot_pending);
+    }
+    return V2E_OK;
+}
+
+static int enqueue_emit(V2eEmu *h, const FrameParams &p, int slot, float *events, cudaStream_t st) {
+    const EmuDev &d = h->d;
+    ProfScope ps(h, slot, 2, st);
+    if (d.state_f64) emu_emit_kernel<double><<<grid_for(d), kThreads, 0, st>>>(d, p, slot, (float4 *)events);
+    else emu_emit_kernel<float><<<grid_for(d), kThreads, 0, st>>>(d, p, slot, (float4 *)events);
+    return V2E_OK;
+}
+
+static int reset_slots(V2eEmu *h, int first, int count, cudaStream_t st) {
+    EmuDev &d = h->d;
+    size_t off = (size_t)first * d.seg_stride * 4, bytes = (size_t)count * d.seg_stride * 4;
+    CU(cudaMemsetAsync((char *)d.hist_pre + off, 0, bytes, st));
+    CU(cudaMemsetAsync((char *)d.hist_post + off, 0, bytes, st));
+    CU(cudaMemsetAsync((char *)d.cursor + off, 0, bytes, st));
+    CU(cudaMemsetAsync(d.ctrl + first, 0, (size_t)(count + 1) * sizeof(FrameCtrl), st));
+    CU(cudaMemsetAsync(d.abort_flag, 0, 2 * sizeof(int32_t), st));
+    return V2E_OK;
+}
+
+extern "C" int v2e_emu_step(V2eEmu *h, const void *frames, int dtype, int T, const double *t_frames,
+                            double t_previous, const float *leak_randn, const float *shot_rand,
+                            float *events, uint64_t capacity, uint64_t ev_base_start, int first,
+                            int resume_emit, void *stream) {
+    if (!h || !frames || !t_frames || (!events && capacity)) return fail(V2E_E_INVALID, "null argument");
+    if (!h->first_done) return fail(V2E_E_STATE, "v2e_emu_first_frame must run before v2e_emu_step");
+    if (T < 1 || T > h->d.max_slots || first < 0 || first >= T) return fail(V2E_E_INVALID, "bad T / first");
+    if (((uintptr_t)events & 15) != 0) return fail(V2E_E_INVALID, "events_out must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const EmuDev &d = h->d;
+    const size_t fbytes = (size_t)d.n * frame_elem(dtype);
+    int rc;
+    if (resume_emit) {
+        // frame `first` was counted but not emitted (capacity abort): clear the abort and the slots
+        // after it, keep slot `first`'s histograms, re-plan it against the new capacity.
+        if (first + 1 < T && (rc = reset_slots(h, first + 1, T - first - 1, st))) return rc;
+        CU(cudaMemsetAsync(d.abort_flag, 0, 2 * sizeof(int32_t), st));
+    } else {
+        if ((rc = reset_slots(h, first, T - first, st))) return rc;
+    }
+    if (h->profile) { memset(h->prof_used, 0, (size_t)d.max_slots * 3); h->prof_frames = T - first; }
+    if (!resume_emit) {
+        h->step_base = h->frame_counter;
+        h->frame_counter += (uint32_t)T;
+    }
+    emu_begin_step_kernel<<<1, 1, 0, st>>>(d, first, ev_base_start);
+    for (int f = first; f < T; f++) {
+        double tp = f == 0 ? t_previous : t_frames[f - 1];
+        if (t_frames[f] < tp) return fail(V2E_E_INVALID, "frame times must be non-decreasing");
+        FrameParams p = make_params(h, t_frames[f], tp, h->step_base + (uint32_t)f, capacity);
+        const char *frame = (const char *)frames + (size_t)f * fbytes;
+        const float *lr = leak_randn ? leak_randn + (size_t)f * d.n : nullptr;
+        const float *sr = shot_rand ? shot_rand + (size_t)f * d.n : nullptr;
+        if (resume_emit && f == first) {
+            emu_plan_kernel<<<1, kThreads, 0, st>>>(d, p, f);   // only the plan has to be redone
+        } else {
+            if ((rc = enqueue_count(h, p, frame, dtype, lr, sr, 0, f, st))) return rc;
+        }
+        if ((rc = enqueue_emit(h, p, f, events, st))) return rc;
+    }
+    CU(cudaGetLastError());
+    h->last_T = T;
+    return V2E_OK;
+}
+
+extern "C" int v2e_emu_collect(V2eEmu *h, V2eFrameInfo *info, int T, int *frames_done,
+                               uint64_t *rows_total, void *stream) {
+    if (!h || !info || T < 1 || T > h->d.max_slots) return fail(V2E_E_INVALID, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaMemcpyAsync(h->ctrl_host, h->d.ctrl, (size_t)(T + 1) * sizeof(FrameCtrl), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h->abort_host, h->d.abort_flag, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    int status = h->abort_host[0], done = status ? h->abort_host[1] : T;
+    uint64_t rows = 0;
+    for (int f = 0; f < T; f++) {
+        const FrameCtrl &c = h->ctrl_host[f];
+        V2eFrameInfo &o = info[f];
+        o.max_n = c.max_n;
+        o.filter_active = c.filter_active;
+        o.n_on = c.n_on; o.n_off = c.n_off;
+        o.n_shot_on = c.n_shot_on; o.n_shot_off = c.n_shot_off;
+        o.n_events = c.n_events;
+        o.cs_steps = c.cs_steps;
+        o.ev_base = c.ev_base;
+        if (f < done) rows = c.ev_base + c.n_events;
+    }
+    if (frames_done) *frames_done = done;
+    if (rows_total) *rows_total = rows;
+    if (status == V2E_E_CAPACITY) return fail(V2E_E_CAPACITY, "event buffer too small");
+    if (status == V2E_E_ITER_CAP) return fail(V2E_E_ITER_CAP, "a pixel exceeded iter_cap events in one frame");
+    return V2E_OK;
+}
+
+// ---- single-frame phases (slot 0) ---------------------------------------------------------------
+extern "C" int v2e_emu_phase_count(V2eEmu *h, const void *frame, int dtype, double t_frame,
+                                   double t_previous, const float *lr, const float *sr, int shot_pending,
+                                   uint64_t capacity, uint64_t ev_base_start, void *stream) {
+    if (!h || !frame) return fail(V2E_E_INVALID, "null argument");
+    if (!h->first_done) return fail(V2E_E_STATE, "v2e_emu_first_frame must run first");
+    if (t_frame < t_previous) return fail(V2E_E_INVALID, "frame times must be non-decreasing");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if ((rc = reset_slots(h, 0, 1, st))) return rc;
+    emu_begin_step_kernel<<<1, 1, 0, st>>>(h->d, 0, ev_base_start);
+    FrameParams p = make_params(h, t_frame, t_previous, h->frame_counter++, capacity);
+    h->last_dt = p.dt;
+    if ((rc = enqueue_count(h, p, frame, dtype, lr, sr, shot_pending, 0, st))) return rc;
+    CU(cudaGetLastError());
+    h->last_T = 1;
+    return V2E_OK;
+}
+
+extern "C" int v2e_emu_read_counts(V2eEmu *h, int32_t *max_n, uint32_t *counts, int counts_cap, void *stream) {
+    if (!h || !max_n) return fail(V2E_E_INVALID, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaMemcpyAsync(h->ctrl_host, h->d.ctrl, sizeof(FrameCtrl), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    int32_t m = h->ctrl_host[0].max_n;
+    *max_n = m;
+    if (m > h->d.iter_cap) return fail(V2E_E_ITER_CAP, "a pixel exceeded iter_cap events in one frame");
+    if (counts && m > 0) {
+        if (2 * m > counts_cap) return fail(V2E_E_INVALID, "counts buffer too small");
+        // which histogram applies: the refractory filter is active iff
+        // refractory_period_s > delta_time / max_n (emulator.py:792, 830), same doubles as make_ts()
+        const uint32_t *src = h->d.hist_pre;
+        if (h->d.refr_on && h->d.refr_d > h->last_dt / (double)m) src = h->d.hist_post;
+        CU(cudaMemcpy(counts, src, (size_t)2 * m * 4, cudaMemcpyDeviceToHost));
+    }
+    return V2E_OK;
+}
+
+extern "C" int v2e_emu_phase_shot(V2eEmu *h, const void *frame, int dtype, double t_frame, double t_previous,
+                                  const float *sr, uint64_t capacity, void *stream) {
+    if (!h || !frame || !sr) return fail(V2E_E_INVALID, "null argument");
+    FrameParams p = make_params(h, t_frame, t_previous, 0, capacity);
+    int rc = launch_shot(h, p, frame, dtype, sr, 0, (cudaStream_t)stream);
+    if (rc) return rc;
+    CU(cudaGetLastError());
+    return V2E_OK;
+}
+
+extern "C" int v2e_emu_phase_emit(V2eEmu *h, double t_frame, double t_previous, float *events,
+                                  uint64_t capacity, void *stream) {
+    if (!h) return fail(V2E_E_INVALID, "null handle");
+    if (((uintptr_t)events & 15) != 0) return fail(V2E_E_INVALID, "events_out must be 16-byte aligned");
+    FrameParams p = make_params(h, t_frame, t_previous, 0, capacity);
+    int rc = enqueue_emit(h, p, 0, events, (cudaStream_t)stream);
+    if (rc) return rc;
+    CU(cudaGetLastError());
+    return V2E_OK;
+}
+
+extern "C" int v2e_emu_profile(V2eEmu *h, int enable) {
+    if (!h) return fail(V2E_E_INVALID, "null handle");
+    if (enable && !h->ev) {
+        int n = h->d.max_slots * 3 * 2;
+        h->ev = new cudaEvent_t[n];
+        for (int i = 0; i < n; i++) CU(cudaEventCreate(&h->ev[i]));
+        h->prof_used = new unsigned char[h->d.max_slots * 3]();
+    }
+    h->profile = enable ? 1 : 0;
+    return V2E_OK;
+}
+
+extern "C" int v2e_emu_profile_read(V2eEmu *h, float *ms_sum3, int *launches3, void *stream) {
+    if (!h || !h->ev || !ms_sum3 || !launches3) return fail(V2E_E_INVALID, "profiling not enabled");
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    for (int k = 0; k < 3; k++) { ms_sum3[k] = 0.f; launches3[k] = 0; }
+    for (int s = 0; s < h->d.max_slots; s++)
+        for (int k = 0; k < 3; k++)
+            if (h->prof_used[s * 3 + k]) {
+                float ms = 0.f;
+                CU(cudaEventElapsedTime(&ms, h->ev[(s * 3 + k) * 2], h->ev[(s * 3 + k) * 2 + 1]));
+                ms_sum3[k] += ms;
+                launches3[k] += 1;
+            }
+    return V2E_OK;
+}
+
+extern "C" int v2e_emu_state_is_f64(V2eEmu *h) { return h ? h->d.state_f64 : 0; }
+
+extern "C" void *v2e_emu_state_ptr(V2eEmu *h, int which) {
+    if (!h) return nullptr;
+    switch (which) {
+        case 0: return h->d.lp;
+        case 1: return h->d.base;
+        case 2: return h->d.pos_thres;
+        case 3: return h->d.neg_thres;
+        case 4: return h->d.noise_rate;
+        case 5: return h->d.tmem;
+        case 6: return h->d.surround;
+    }
+    return nullptr;
+}
+
+extern "C" int v2e_emu_get_state(V2eEmu *h, int which, void *dst, int *elem_size) {
+    if (!h || !dst) return fail(V2E_E_INVALID, "null argument");
+    void *src = v2e_emu_state_ptr(h, which);
+    if (!src) return fail(V2E_E_STATE, "state array not allocated for this configuration");
+    int es = (which <= 1) ? (int)h->state_elem : (which == 6 ? 8 : 4);
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(dst, src, (size_t)h->d.n * es, cudaMemcpyDeviceToHost));
+    if (elem_size) *elem_size = es;
+    return V2E_OK;
+}

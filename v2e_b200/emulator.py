@@ -1,0 +1,540 @@
+"""EventEmulator -- drop-in for v2ecore/emulator.py:35 backed by the sm_100a kernels.
+
+Same constructor keywords, `generate_events(new_frame, t_frame)` contract, counters and state
+attribute names as the reference (emulator.py:86-117, 619-1022). Host code here is
+plumbing only: it owns no arithmetic of the pixel model. What it does own is the *order of random
+draws*, because parity with a seeded reference run requires the same torch CPU-generator calls
+in the same order (emulator.py:459-505, 868; emulator_utils.py:122-124, 340-343).
+
+Two RNG modes:
+  rng_mode="replay" (default): thresholds / noise-rate / per-frame leak and shot fields are drawn on
+      the host exactly like the reference and uploaded; per-iteration `randperm` calls are replayed
+      so the returned rows are bit-identical *including order* to the reference's CPU output.
+  rng_mode="device": per-frame noise comes from an in-kernel Philox4x32-10 stream; no per-frame
+      host work, frames can be batched (`generate_events_batch`). Counts are bit-exact whenever no
+      per-frame noise is enabled, statistically equivalent otherwise.
+
+Extra keywords (not in the reference): rng_mode, rng (draw source object), iter_cap,
+max_frames_per_step, exact_order.
+"""
+import atexit
+import ctypes
+import logging
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+
+logger = logging.getLogger(__name__)
+
+
+class TorchGlobalRNG:
+    """torch's global CPU generator, the calls the reference makes."""
+
+    def normal(self, mean, std, shape):
+        return torch.normal(mean, std, size=shape, dtype=torch.float32)
+
+    def randn(self, shape):
+        return torch.randn(shape, dtype=torch.float32)
+
+    def rand(self, shape):
+        return torch.rand(shape, dtype=torch.float32)
+
+    def randperm(self, n):
+        return torch.randperm(n)
+
+
+class _DevView:
+    """Minimal __cuda_array_interface__ wrapper so torch can view library-owned device memory."""
+
+    def __init__(self, ptr, shape, typestr, owner):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr,
+                                         "data": (int(ptr), False), "version": 2}
+        self._owner = owner
+
+
+def _linlog_lut():
+    # lin_log(0..255) with the reference's expression (emulator_utils.py:18-45): exact by construction
+    x = torch.arange(256, dtype=torch.float64)
+    f = (1. / 20) * math.log(20)
+    y = torch.where(x <= 20, x * f, torch.log(x))
+    y = torch.round(y * 1e8) / 1e8
+    return y.float().contiguous()
+
+
+_STATE_IDS = {"lp_log_frame": 0, "base_log_frame": 1, "pos_thres": 2, "neg_thres": 3,
+              "noise_rate_array": 4, "timestamp_mem": 5, "cs_surround_frame": 6}
+
+
+class EventEmulator(object):
+    MODEL_STATES = ('new_frame', 'log_new_frame', 'lp_log_frame', 'scidvs_highpass',
+                    'photoreceptor_noise_arr', 'cs_surround_frame', 'c_minus_s_frame',
+                    'base_log_frame', 'diff_frame')
+    MAX_CHANGE_TO_TERMINATE_EULER_SURROUND_STEPPING = 1e-5
+
+    def __init__(
+            self,
+            pos_thres: float = 0.2,
+            neg_thres: float = 0.2,
+            sigma_thres: float = 0.03,
+            cutoff_hz: float = 0.0,
+            leak_rate_hz: float = 0.1,
+            refractory_period_s: float = 0.0,
+            shot_noise_rate_hz: float = 0.0,
+            photoreceptor_noise: bool = False,
+            leak_jitter_fraction: float = 0.1,
+            noise_rate_cov_decades: float = 0.1,
+            seed: int = 0,
+            output_folder: str = None,
+            dvs_h5: str = None,
+            dvs_aedat2: str = None,
+            dvs_aedat4: str = None,
+            dvs_text: str = None,
+            show_dvs_model_state: str = None,
+            save_dvs_model_state: bool = False,
+            output_width: int = None,
+            output_height: int = None,
+            device: str = "cuda",
+            cs_lambda_pixels: float = None,
+            cs_tau_p_ms: float = None,
+            hdr: bool = False,
+            scidvs: bool = False,
+            record_single_pixel_states=None,
+            label_signal_noise=False,
+            # ---- extensions ----
+            rng_mode: str = "replay",
+            rng=None,
+            iter_cap: int = 1024,
+            max_frames_per_step: int = 64,
+            exact_order: bool = True,
+    ):
+        if not str(device).startswith("cuda"):
+            raise RuntimeError("v2e_b200.EventEmulator runs on a CUDA device only (device=%r); "
+                               "there is no CPU fallback" % (device,))
+        if photoreceptor_noise:
+            raise NotImplementedError("photoreceptor_noise (emulator.py:694-703) is not built; its "
+                                      "calibration uses an unseeded numpy generator in the reference")
+        if scidvs:
+            raise NotImplementedError("scidvs (emulator.py:719-725) is not built")
+        if dvs_h5 or dvs_aedat2 or dvs_aedat4 or dvs_text or show_dvs_model_state or \
+                record_single_pixel_states is not None:
+            raise NotImplementedError("file sinks / state display are the caller's job here "
+                                      "(out of scope, SURVEY.md 8f); write the returned rows with "
+                                      "the reference's v2ecore.output classes")
+        if rng_mode not in ("replay", "device"):
+            raise ValueError("rng_mode must be 'replay' or 'device'")
+        logger.info("ON/OFF log_e temporal contrast thresholds: {} / {} +/- {}".format(
+            pos_thres, neg_thres, sigma_thres))
+        self.device = torch.device(device if device != "cuda" else "cuda:0")
+        self.sigma_thres = sigma_thres
+        self.pos_thres_nominal = pos_thres
+        self.neg_thres_nominal = neg_thres
+        self.cutoff_hz = cutoff_hz
+        self.leak_rate_hz = leak_rate_hz
+        self.refractory_period_s = refractory_period_s
+        self.shot_noise_rate_hz = shot_noise_rate_hz
+        self.photoreceptor_noise = photoreceptor_noise
+        self.leak_jitter_fraction = leak_jitter_fraction
+        self.noise_rate_cov_decades = noise_rate_cov_decades
+        self.SHOT_NOISE_INTEN_FACTOR = 0.25
+        self.output_folder = output_folder
+        self.output_width = output_width
+        self.output_height = output_height
+        self.label_signal_noise = label_signal_noise
+        self.log_input = hdr
+        self.scidvs = scidvs
+        self.cs_lambda_pixels = cs_lambda_pixels
+        self.cs_tau_p_ms = cs_tau_p_ms
+        self.csdvs_enabled = cs_lambda_pixels is not None
+        self.cs_steps_taken = []
+        if self.csdvs_enabled:
+            self.cs_tau_h_ms = 0 if (cs_tau_p_ms is None or cs_tau_p_ms == 0) \
+                else cs_tau_p_ms / (cs_lambda_pixels ** 2)
+        self.rng_mode = rng_mode
+        self.rng = rng if rng is not None else TorchGlobalRNG()
+        self.iter_cap = int(iter_cap)
+        self.max_frames_per_step = int(max_frames_per_step)
+        self.exact_order = exact_order
+        self.event_rows_hint = None   # initial event-buffer rows (default: max(2*H*W, 65536))
+        self.seed = seed
+        if seed != 0:  # emulator.py:221-224
+            import random
+            torch.manual_seed(seed)
+            np.random.seed(seed)
+            random.seed(seed)
+        self._lib = _lib.load()
+        self._h = None
+        self._ev_dev = None
+        self._ev_pin = None
+        self.reset()
+        self.t_previous = 0
+        atexit.register(self.cleanup)
+
+    # ------------------------------------------------------------------------------------------
+    def reset(self):
+        """emulator.py:558-578: next frame re-initialises the per-pixel state."""
+        self.num_events_total = 0
+        self.num_events_on = 0
+        self.num_events_off = 0
+        self.frame_counter = 0
+        self._destroy_handle()
+        self._initialized = False
+        self.last_frame_info = None
+
+    def cleanup(self):
+        self._destroy_handle()
+
+    def prepare_storage(self, n_frames, frame_ts):
+        return None  # HDF5 frame storage is a sink (out of scope); kept for call compatibility
+
+    def set_dvs_params(self, model: str):
+        """emulator.py:513-556 presets."""
+        if model == 'clean':
+            self.pos_thres_nominal = self.neg_thres_nominal = 0.2
+            self.sigma_thres = 0.02
+            self.cutoff_hz = 0
+            self.leak_rate_hz = 0
+            self.leak_jitter_fraction = 0
+            self.noise_rate_cov_decades = 0
+            self.shot_noise_rate_hz = 0
+            self.refractory_period_s = 0
+        elif model == 'noisy':
+            self.pos_thres_nominal = self.neg_thres_nominal = 0.2
+            self.sigma_thres = 0.05
+            self.cutoff_hz = 30
+            self.leak_rate_hz = 0.1
+            self.shot_noise_rate_hz = 5.0
+            self.refractory_period_s = 0
+            self.leak_jitter_fraction = 0.1
+            self.noise_rate_cov_decades = 0.1
+        else:
+            logger.warning("dvs_params {} not known: Using commandline assigned options".format(model))
+        if self._initialized:
+            raise RuntimeError("set_dvs_params must be called before the first frame (or after reset())")
+
+    def _destroy_handle(self):
+        if getattr(self, "_h", None):
+            try:
+                self._lib.v2e_emu_destroy(self._h)
+            except Exception:
+                pass
+            self._h = None
+
+    # ------------------------------------------------------------------------------------------
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _to_device_frames(self, frames):
+        """-> (contiguous device tensor, dtype code). Accepts uint8 / float32 / float64 ndarrays or
+        tensors, [H,W] or [T,H,W] (emulator.py:663 copies on entry; so do we)."""
+        if isinstance(frames, np.ndarray):
+            if frames.dtype == np.uint8 or frames.dtype == np.float32:
+                t = torch.from_numpy(np.ascontiguousarray(frames))
+            else:
+                t = torch.from_numpy(np.ascontiguousarray(frames, dtype=np.float64))
+        elif isinstance(frames, torch.Tensor):
+            t = frames
+            if t.dtype not in (torch.uint8, torch.float32, torch.float64):
+                t = t.to(torch.float64)
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(np.asarray(frames), dtype=np.float64))
+        t = t.to(self.device, non_blocking=True).contiguous()
+        code = {torch.uint8: _lib.U8, torch.float32: _lib.F32, torch.float64: _lib.F64}[t.dtype]
+        return t, code
+
+    def _create(self, H, W):
+        cfg = _lib.V2eEmuCfg()
+        cfg.width, cfg.height = W, H
+        cfg.per_pixel_thres = 1 if self.sigma_thres > 0 else 0
+        cfg.hdr = 1 if self.log_input else 0
+        cfg.pos_thres_nominal, cfg.neg_thres_nominal = self.pos_thres_nominal, self.neg_thres_nominal
+        cfg.cutoff_hz = self.cutoff_hz
+        cfg.leak_rate_hz = self.leak_rate_hz
+        cfg.leak_jitter_fraction = self.leak_jitter_fraction
+        cfg.refractory_period_s = self.refractory_period_s
+        cfg.shot_noise_rate_hz = self.shot_noise_rate_hz
+        cfg.shot_inten_factor = self.SHOT_NOISE_INTEN_FACTOR
+        cfg.rng_mode = 0 if self.rng_mode == "replay" else 1
+        cfg.iter_cap = self.iter_cap
+        cfg.seed = int(self.seed) & 0xFFFFFFFFFFFFFFFF
+        cfg.csdvs = 1 if self.csdvs_enabled else 0
+        cfg.max_frames_per_step = self.max_frames_per_step
+        if self.csdvs_enabled:
+            abs_min_tau_p = 1e-9  # emulator.py:1068-1073
+            cfg.cs_tau_p_s = abs_min_tau_p if (self.cs_tau_p_ms is None or self.cs_tau_p_ms == 0) \
+                else self.cs_tau_p_ms * 1e-3
+            cfg.cs_tau_h_s = abs_min_tau_p / (self.cs_lambda_pixels ** 2) \
+                if (self.cs_tau_h_ms is None or self.cs_tau_h_ms == 0) else self.cs_tau_h_ms * 1e-3
+        h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.v2e_emu_create(ctypes.byref(cfg), ctypes.byref(h)))
+            self._h = h
+            lut = _linlog_lut()
+            _lib.check(self._lib.v2e_emu_set_linlog_lut(h, ctypes.c_void_p(lut.data_ptr()), self._stream()))
+        self._H, self._W = H, W
+        self.output_width = W if self.output_width is None else self.output_width
+        self.output_height = H if self.output_height is None else self.output_height
+        self._state_f64 = bool(self._lib.v2e_emu_state_is_f64(h))
+
+    def _init_fields(self, H, W):
+        """emulator.py:439-511 draw order: normal(pos), normal(neg), randn(noise_rate)."""
+        pos = neg = nr = None
+        if self.sigma_thres > 0:
+            pos = torch.clamp(self.rng.normal(self.pos_thres_nominal, self.sigma_thres, (H, W)), min=0.01)
+            neg = torch.clamp(self.rng.normal(self.neg_thres_nominal, self.sigma_thres, (H, W)), min=0.01)
+            pos, neg = pos.contiguous(), neg.contiguous()
+        if self.leak_rate_hz > 0:
+            r = self.rng.randn((H, W))
+            nr = torch.exp(math.log(10) * self.noise_rate_cov_decades * r).contiguous()
+        p = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
+        _lib.check(self._lib.v2e_emu_set_fields(self._h, p(pos), p(neg), p(nr)))
+
+    def _ensure_event_buffers(self, rows):
+        if self._ev_dev is None or self._ev_dev.shape[0] < rows:
+            rows = max(int(rows), 16)
+            self._ev_dev = torch.empty((rows, 4), dtype=torch.float32, device=self.device)
+            self._ev_pin = torch.empty((rows, 4), dtype=torch.float32).pin_memory()
+
+    def _rows_to_host(self, n_rows, base=0):
+        if n_rows == 0:
+            return np.zeros((0, 4), np.float32)
+        self._ev_pin[:n_rows].copy_(self._ev_dev[base:base + n_rows], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self._ev_pin[:n_rows].numpy().copy()
+
+    def _check_time(self, t_frame):
+        if t_frame < self.t_previous:
+            raise ValueError("this frame time={} must be later than previous frame time={}".format(
+                t_frame, self.t_previous))
+
+    def _first_frame(self, fr, code, t_frame):
+        H, W = fr.shape[-2], fr.shape[-1]
+        self._create(H, W)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.v2e_emu_first_frame(self._h, ctypes.c_void_p(fr.data_ptr()), code,
+                                                     float(t_frame), float(self.t_previous), self._stream()))
+            self._init_fields(H, W)
+        self._initialized = True
+        # the reference returns before `self.t_previous = t_frame` (emulator.py:717 vs :1011)
+
+    # ------------------------------------------------------------------------------------------
+    def generate_events(self, new_frame, t_frame):
+        """emulator.py:619: returns float32 [N,4] rows [t, x, y, +-1] or None."""
+        t_frame = float(t_frame)
+        self.frame_counter += 1
+        self._check_time(t_frame)
+        fr, code = self._to_device_frames(new_frame)
+        if fr.dim() != 2:
+            raise ValueError("new_frame must be [height, width]")
+        if not self._initialized:
+            self._first_frame(fr, code, t_frame)
+            return None
+        if fr.shape != (self._H, self._W):
+            raise ValueError("frame size changed")
+        per_frame_rng = (self.leak_rate_hz > 0 or self.shot_noise_rate_hz > 0)
+        if self.rng_mode == "replay" and (per_frame_rng or self.exact_order):
+            ev = self._generate_replay(fr, code, t_frame)
+        else:
+            ev, _ = self._run_step(fr.unsqueeze(0), code, [t_frame])
+        self.t_previous = t_frame
+        if ev is not None and len(ev) > 0:
+            return ev
+        return None
+
+    # replay path: one frame, host draws interleaved exactly like the reference ----------------
+    def _generate_replay(self, fr, code, t_frame):
+        H, W, n = self._H, self._W, self._H * self._W
+        L, h = self._lib, self._h
+        leak_on, shot_on = self.leak_rate_hz > 0, self.shot_noise_rate_hz > 0
+        with torch.cuda.device(self.device):
+            st = self._stream()
+            lr_dev = None
+            if leak_on:
+                lr_dev = self.rng.randn((H, W)).contiguous().to(self.device, non_blocking=False)
+            self._ensure_event_buffers(self.event_rows_hint or max(4 * n, 1 << 16))
+            cap = self._ev_dev.shape[0]
+            tp = float(self.t_previous)
+            fp = ctypes.c_void_p(fr.data_ptr())
+            _lib.check(L.v2e_emu_phase_count(h, fp, code, t_frame, tp,
+                                             None if lr_dev is None else ctypes.c_void_p(lr_dev.data_ptr()),
+                                             None, 1 if shot_on else 0, cap, 0, st))
+            max_n = ctypes.c_int32(0)
+            counts = np.zeros(2 * self.iter_cap, np.uint32)
+            _lib.check(L.v2e_emu_read_counts(h, ctypes.byref(max_n), counts.ctypes.data_as(ctypes.c_void_p),
+                                             counts.size, st))
+            m = max_n.value
+            counts = counts[:2 * m].astype(np.int64)
+            sig_total = int(counts.sum())
+            # replay the per-iteration shuffles now: the shot draw comes after them (emulator.py:868, 897)
+            perms = []
+            for it in range(m):
+                k = int(counts[2 * it] + counts[2 * it + 1])
+                perms.append(self.rng.randperm(k).numpy() if k > 0 else None)
+            if shot_on:
+                sr_dev = self.rng.rand((H, W)).contiguous().to(self.device, non_blocking=False)
+                _lib.check(L.v2e_emu_phase_shot(h, fp, code, t_frame, tp, ctypes.c_void_p(sr_dev.data_ptr()),
+                                                cap, st))
+            _lib.check(L.v2e_emu_phase_emit(h, t_frame, tp, ctypes.c_void_p(self._ev_dev.data_ptr()), cap, st))
+            info = (_lib.V2eFrameInfo * 1)()
+            done, rows = ctypes.c_int(0), ctypes.c_uint64(0)
+            rc = L.v2e_emu_collect(h, info, 1, ctypes.byref(done), ctypes.byref(rows), st)
+            if rc == _lib.V2E_E_CAPACITY:
+                # grow and re-run only the emission of this frame
+                self._ensure_event_buffers(int(info[0].n_events) + 1024)
+                ts = (ctypes.c_double * 1)(t_frame)
+                _lib.check(L.v2e_emu_step(h, fp, code, 1, ts, tp, None, None,
+                                          ctypes.c_void_p(self._ev_dev.data_ptr()), self._ev_dev.shape[0], 0,
+                                          0, 1, st))
+                _lib.check(L.v2e_emu_collect(h, info, 1, ctypes.byref(done), ctypes.byref(rows), st))
+            else:
+                _lib.check(rc)
+            fi = info[0]
+            self.last_frame_info = fi
+            ev = self._rows_to_host(int(fi.n_events))
+        self._account(fi)
+        if fi.n_events == 0:
+            return None
+        return self._canonical_then_shuffle(ev, counts, perms, int(fi.n_shot_on), int(fi.n_shot_off))
+
+    def _canonical_then_shuffle(self, ev, counts, perms, shot_on, shot_off):
+        """Device rows of one (iteration, polarity) group come in no particular order. The reference
+        builds each iteration as ON rows then OFF rows in row-major pixel order and shuffles it with
+        randperm (emulator.py:861-870, 1024-1059); shot rows are appended unshuffled (:906-919)."""
+        W = self._W
+        out = np.empty_like(ev)
+        off = 0
+        for it in range(len(perms)):
+            c_on, c_off = int(counts[2 * it]), int(counts[2 * it + 1])
+            k = c_on + c_off
+            if k == 0:
+                continue
+            blk = ev[off:off + k]
+            key = blk[:, 2].astype(np.int64) * W + blk[:, 1].astype(np.int64)
+            key[c_on:] += (1 << 40)   # keep OFF rows after ON rows
+            blk = blk[np.argsort(key, kind="stable")]
+            out[off:off + k] = blk[perms[it]] if self.exact_order else blk
+            off += k
+        for c in (shot_on, shot_off):
+            if c:
+                blk = ev[off:off + c]
+                key = blk[:, 2].astype(np.int64) * W + blk[:, 1].astype(np.int64)
+                out[off:off + c] = blk[np.argsort(key, kind="stable")]
+                off += c
+        assert off == len(ev)
+        return out
+
+    def _account(self, fi):
+        self.num_events_on += int(fi.n_on)
+        self.num_events_off += int(fi.n_off)
+        self.num_events_total += int(fi.n_events)
+
+    # batched path ------------------------------------------------------------------------------
+    def _run_step(self, frames_dev, code, t_frames, return_device=False):
+        """frames_dev: [T,H,W] device tensor, T <= max_frames_per_step. Returns (rows, offsets[T+1])."""
+        T = frames_dev.shape[0]
+        L, h = self._lib, self._h
+        n = self._H * self._W
+        ts = (ctypes.c_double * T)(*[float(t) for t in t_frames])
+        with torch.cuda.device(self.device):
+            st = self._stream()
+            self._ensure_event_buffers(self.event_rows_hint or max(2 * n, 1 << 16))
+            info = (_lib.V2eFrameInfo * T)()
+            done, rows = ctypes.c_int(0), ctypes.c_uint64(0)
+            first, resume, base = 0, 0, 0
+            while True:
+                _lib.check(L.v2e_emu_step(h, ctypes.c_void_p(frames_dev.data_ptr()), code, T, ts,
+                                          float(self.t_previous), None, None,
+                                          ctypes.c_void_p(self._ev_dev.data_ptr()), self._ev_dev.shape[0],
+                                          base, first, resume, st))
+                rc = L.v2e_emu_collect(h, info, T, ctypes.byref(done), ctypes.byref(rows), st)
+                if rc != _lib.V2E_E_CAPACITY:
+                    _lib.check(rc)
+                    break
+                # grow (keeping rows already written) and resume at the frame that did not fit
+                first, resume = done.value, 1
+                base = int(info[first].ev_base)
+                need = base + int(info[first].n_events)
+                old = self._ev_dev
+                self._ev_dev = None
+                self._ensure_event_buffers(max(2 * need, 2 * old.shape[0]))
+                self._ev_dev[:base].copy_(old[:base])
+            total = int(rows.value)
+            offsets = np.array([int(info[f].ev_base) for f in range(T)] + [total], np.int64)
+            for f in range(T):
+                self._account(info[f])
+            self.last_frame_info = info[T - 1]
+            if return_device:
+                return self._ev_dev[:total], offsets
+            return self._rows_to_host(total), offsets
+
+    def generate_events_batch(self, frames, t_frames, return_device=False):
+        """Fast path (not in the reference): all frames of a clip in a few launches per frame and no
+        per-frame host synchronisation. frames: [T,H,W]; t_frames: [T] seconds, non-decreasing.
+        Returns (rows [N,4] float32, offsets [T+1]) -- rows of frame f are rows[offsets[f]:offsets[f+1]].
+        The first frame of a fresh emulator only initialises state (zero rows), as in the reference.
+        Needs rng_mode="device" when leak or shot noise is on."""
+        if self.rng_mode == "replay" and (self.leak_rate_hz > 0 or self.shot_noise_rate_hz > 0):
+            raise RuntimeError("generate_events_batch with per-frame noise needs rng_mode='device' "
+                               "(replay mode must interleave host draws frame by frame)")
+        fr, code = self._to_device_frames(frames)
+        if fr.dim() != 3:
+            raise ValueError("frames must be [T, height, width]")
+        t_frames = [float(t) for t in t_frames]
+        T = fr.shape[0]
+        if len(t_frames) != T:
+            raise ValueError("t_frames length mismatch")
+        for a, b in zip([self.t_previous] + t_frames[:-1], t_frames):
+            if b < a:
+                raise ValueError("this frame time={} must be later than previous frame time={}".format(b, a))
+        chunks, offs = [], [0]
+        start = 0
+        if not self._initialized:
+            self._first_frame(fr[0], code, t_frames[0])
+            self.frame_counter += 1
+            offs.append(0)
+            start = 1
+        f = start
+        while f < T:
+            e = min(T, f + self.max_frames_per_step)
+            rows, o = self._run_step(fr[f:e], code, t_frames[f:e], return_device=return_device)
+            chunks.append(rows.clone() if return_device else rows)
+            offs.extend((o[1:] + offs[-1] - o[0]).tolist())
+            self.t_previous = t_frames[e - 1]
+            self.frame_counter += e - f
+            f = e
+        if return_device:
+            ev = torch.cat(chunks) if chunks else torch.zeros((0, 4), dtype=torch.float32, device=self.device)
+        else:
+            ev = np.concatenate(chunks) if chunks else np.zeros((0, 4), np.float32)
+        return ev, np.asarray(offs, np.int64)
+
+    # state tensors by the reference's attribute names (emulator.py:756-764 reads them via getattr)
+    def _state(self, name):
+        if not self._initialized:
+            return None
+        which = _STATE_IDS[name]
+        ptr = self._lib.v2e_emu_state_ptr(self._h, which)
+        if not ptr:
+            return None
+        f64 = (which <= 1 and self._state_f64) or which == 6
+        view = _DevView(ptr, (self._H, self._W), "<f8" if f64 else "<f4", self)
+        torch.cuda.current_stream(self.device).synchronize()
+        return torch.as_tensor(view, device=self.device)
+
+    lp_log_frame = property(lambda self: self._state("lp_log_frame"))
+    base_log_frame = property(lambda self: self._state("base_log_frame"))
+    timestamp_mem = property(lambda self: self._state("timestamp_mem"))
+    noise_rate_array = property(lambda self: self._state("noise_rate_array"))
+    cs_surround_frame = property(lambda self: self._state("cs_surround_frame"))
+
+    @property
+    def pos_thres(self):
+        t = self._state("pos_thres") if self._initialized else None
+        return t if t is not None else self.pos_thres_nominal
+
+    @property
+    def neg_thres(self):
+        t = self._state("neg_thres") if self._initialized else None
+        return t if t is not None else self.neg_thres_nominal

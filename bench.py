@@ -33,12 +33,15 @@ def peaks():
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
 
 
-def texture_clip(H, W, T, seed=0, dx=2, dy=1, block=4):
-    """SURVEY 8(d) C3-style input: random 4x4-block texture translating (dx,dy) px per frame, uint8."""
+def texture_clip(H, W, T, seed=0, dx=1, dy=0, up=16, lo=40.0, hi=215.0):
+    """Smooth random texture (uniform noise, bicubic x16) translating 1 px per frame, uint8: with the
+    CLI-default pixel parameters this gives ~0.1 events/pixel/frame (SURVEY 8d asks for >= 0.05)."""
+    import torch
     rng = np.random.default_rng(seed)
-    pad_x, pad_y = dx * T + 8, dy * T + 8
-    base = rng.integers(0, 256, ((H + pad_y) // block + 2, (W + pad_x) // block + 2), dtype=np.uint8)
-    big = np.kron(base, np.ones((block, block), np.uint8))
+    ph, pw = H + dy * T + 2 * up, W + dx * T + 2 * up
+    base = torch.from_numpy(rng.uniform(lo, hi, (1, 1, ph // up + 3, pw // up + 3)).astype(np.float32))
+    big = torch.nn.functional.interpolate(base, scale_factor=up, mode="bicubic", align_corners=False)[0, 0]
+    big = big.clamp(0, 255).round().to(torch.uint8).numpy()
     out = np.empty((T, H, W), np.uint8)
     for k in range(T):
         out[k] = big[k * dy:k * dy + H, k * dx:k * dx + W]
@@ -126,7 +129,7 @@ def main():
     dt = 1.0 / (fps_src * U)                       # 10x slow-motion timestamps
     times = np.arange(T) * dt
     kw = dict(CLI_DEFAULTS)
-    workload = "emulator_%dx%d_texture_T%d_cli_defaults_dt%.4gms" % (W, H, T, dt * 1e3)
+    workload = "emulator_%dx%d_smooth_texture_1px_per_frame_T%d_cli_defaults_dt%.4gms" % (W, H, T, dt * 1e3)
     pk = peaks()
 
     if args.impl == "reference":

@@ -367,6 +367,7 @@ emu_update_kernel(EmuDev d, FrameParams p, const void *frame, const float *leak_
     uint32_t *hist = d.hist_pre + (size_t)slot * d.seg_stride;
     const int i0 = (blockIdx.x * kThreads + tid) * kVec;
     int local_max = 0;
+    int mags[4] = {0, 0, 0, 0}, pols[4] = {0, 0, 0, 0}, flg[4] = {0, 0, 0, 0};
     if (i0 < d.n) {
         double x[4];
         load_frame4<FT>(frame, i0, d.n, x);
@@ -451,21 +452,34 @@ emu_update_kernel(EmuDev d, FrameParams p, const void *frame, const float *leak_
             if (mag > local_max) local_max = mag;
             if (mag > kRecMaxCount) { cnt = cnt < 0 ? -kRecMaxCount : kRecMaxCount; }
             recs[k] = (short)((cnt << kRecShift) | flags);
-            if (mag | flags) {
-                const int pol = cnt < 0;
-                const int lim = mag < d.iter_cap ? mag : d.iter_cap;
-                for (int it = 0; it < lim; it++) {
-                    int s = 2 * it + pol;
-                    if (s < kSegSmem) atomicAdd(&s_hist[s], 1u);
-                    else atomicAdd(&hist[s], 1u);
-                }
-                if (flags & 1) atomicAdd(&s_hist[kSegSmem], 1u);
-                if (flags & 2) atomicAdd(&s_hist[kSegSmem + 1], 1u);
-            }
+            mags[k] = mag < d.iter_cap ? mag : d.iter_cap;
+            pols[k] = cnt < 0;
+            flg[k] = flags;
         }
         if (!lp_done) st4((S *)d.lp, i0, lp);
         if (d.leak_on) st4((S *)d.base, i0, base);
         *(short4 *)(d.rec + i0) = make_short4(recs[0], recs[1], recs[2], recs[3]);
+    }
+    // per-(iteration,polarity) histogram, one shared-memory atomic per warp and segment
+    {
+        const int lane = tid & 31;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int wmax = __reduce_max_sync(0xffffffffu, mags[k]);
+            for (int it = 0; it < wmax; it++) {
+                unsigned on = __ballot_sync(0xffffffffu, mags[k] > it && !pols[k]);
+                unsigned off = __ballot_sync(0xffffffffu, mags[k] > it && pols[k]);
+                if (lane == 0) {
+                    if (on) { if (2 * it < kSegSmem) atomicAdd(&s_hist[2 * it], __popc(on)); else atomicAdd(&hist[2 * it], __popc(on)); }
+                    if (off) { if (2 * it + 1 < kSegSmem) atomicAdd(&s_hist[2 * it + 1], __popc(off)); else atomicAdd(&hist[2 * it + 1], __popc(off)); }
+                }
+            }
+            unsigned son = __ballot_sync(0xffffffffu, flg[k] & 1), soff = __ballot_sync(0xffffffffu, flg[k] & 2);
+            if (lane == 0) {
+                if (son) atomicAdd(&s_hist[kSegSmem], __popc(son));
+                if (soff) atomicAdd(&s_hist[kSegSmem + 1], __popc(soff));
+            }
+        }
     }
     // block max -> one atomicMax per block
     local_max = warp_reduce_max(local_max);
@@ -480,22 +494,27 @@ emu_update_kernel(EmuDev d, FrameParams p, const void *frame, const float *leak_
     }
 }
 
-// walks the emitted iterations of one active pixel; F(it, ts) is called for every event that
-// survives the refractory filter (emulator.py:819-850). Returns the number of surviving events
-// and updates tm (timestamp_mem) when the filter is active.
+// Warp-synchronous walk over the emitted iterations of "pixel k of every lane" (emulator.py:810-850).
+// All 32 lanes must call it. For every iteration up to the warp's largest count, F(it, t, on, off,
+// pass) receives the ballots of lanes whose event survives the refractory filter (ON / OFF) and this
+// lane's own verdict. tm (timestamp_mem) is updated when the filter is active. Returns the number of
+// surviving events of this lane's pixel.
 template <typename F>
-__device__ __forceinline__ int walk_pixel(int mag, const TsParams &ts, bool filter, float refr_f,
-                                          float &tm, F &&f) {
+__device__ __forceinline__ int warp_walk(int mag, int pol, const TsParams &ts, bool filter, float refr_f,
+                                         float &tm, F &&f) {
+    const int wmax = __reduce_max_sync(0xffffffffu, mag);
     int fin = 0;
-    for (int it = 0; it < mag; it++) {
-        float t = linspace_f32(ts, it);
-        if (filter) {
-            float since = t - tm;
-            if (!(since > refr_f)) continue;
-            tm = t;
+    for (int it = 0; it < wmax; it++) {
+        const float t = linspace_f32(ts, it);
+        bool pass = it < mag;
+        if (filter && pass) {
+            pass = (t - tm) > refr_f;              // pos_cord*ts[i] - timestamp_mem > refractory
+            if (pass) tm = t;
         }
-        f(it, t);
-        fin++;
+        const unsigned on = __ballot_sync(0xffffffffu, pass && !pol);
+        const unsigned off = __ballot_sync(0xffffffffu, pass && pol);
+        f(it, t, on, off, pass);
+        fin += pass;
     }
     return fin;
 }
@@ -507,7 +526,7 @@ __global__ void __launch_bounds__(kThreads)
 emu_filter_kernel(EmuDev d, FrameParams p, int slot, int do_plan) {
     __shared__ uint32_t s_hist[kSegSmem];
     if (*(volatile int32_t *)d.abort_flag) return;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     FrameCtrl *c = d.ctrl + slot;
     const int32_t max_n = *(volatile int32_t *)&c->max_n;
     const TsParams ts = make_ts(p, max_n, d.refr_d);
@@ -516,19 +535,23 @@ emu_filter_kernel(EmuDev d, FrameParams p, int slot, int do_plan) {
         __syncthreads();
         uint32_t *hist = d.hist_post + (size_t)slot * d.seg_stride;
         const int i0 = (blockIdx.x * kThreads + tid) * kVec;
+        short recs[4] = {0, 0, 0, 0};
         if (i0 < d.n) {
             short4 r4 = *(const short4 *)(d.rec + i0);
-            short recs[4] = {r4.x, r4.y, r4.z, r4.w};
+            recs[0] = r4.x; recs[1] = r4.y; recs[2] = r4.z; recs[3] = r4.w;
+        }
+        const bool warp_any = __any_sync(0xffffffffu, ((recs[0] | recs[1] | recs[2] | recs[3]) & ~3) != 0);
+        if (warp_any) {
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 int cnt = recs[k] >> kRecShift;
-                if (cnt == 0) continue;
                 int mag = cnt < 0 ? -cnt : cnt, pol = cnt < 0;
-                float tm = d.tmem[i0 + k];
-                walk_pixel(mag, ts, true, d.refr_f, tm, [&](int it, float) {
-                    int s = 2 * it + pol;
-                    if (s < kSegSmem) atomicAdd(&s_hist[s], 1u);
-                    else atomicAdd(&hist[s], 1u);
+                float tm = mag ? d.tmem[i0 + k] : 0.f;
+                warp_walk(mag, pol, ts, true, d.refr_f, tm, [&](int it, float, unsigned on, unsigned off, bool) {
+                    if (lane == 0) {
+                        if (on) { if (2 * it < kSegSmem) atomicAdd(&s_hist[2 * it], __popc(on)); else atomicAdd(&hist[2 * it], __popc(on)); }
+                        if (off) { if (2 * it + 1 < kSegSmem) atomicAdd(&s_hist[2 * it + 1], __popc(off)); else atomicAdd(&hist[2 * it + 1], __popc(off)); }
+                    }
                 });
             }
         }
@@ -582,7 +605,8 @@ emu_shot_kernel(EmuDev d, FrameParams p, const void *frame, const float *shot_ra
 
 // ---------------------------------------------------------------------------------------------
 // emit kernel: compaction of the active pixels into packed rows + state patch
-// (emulator.py:810-870, 906-942, 1024-1059)
+// (emulator.py:810-870, 906-942, 1024-1059). Warp-ballot compaction: one shared-memory atomic per
+// warp and (iteration, polarity) segment, one global atomic per block and segment.
 // ---------------------------------------------------------------------------------------------
 template <typename S>
 __global__ void __launch_bounds__(kThreads)
@@ -590,7 +614,8 @@ emu_emit_kernel(EmuDev d, FrameParams p, int slot, float4 *events) {
     __shared__ uint32_t s_cnt[kSegSmem + 2];
     __shared__ uint32_t s_base[kSegSmem + 2];
     if (*(volatile int32_t *)d.abort_flag) return;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
     FrameCtrl *c = d.ctrl + slot;
     if (!c->planned) return;
     if (c->n_events == 0) return;
@@ -605,29 +630,32 @@ emu_emit_kernel(EmuDev d, FrameParams p, int slot, float4 *events) {
     __syncthreads();
     const int i0 = (blockIdx.x * kThreads + tid) * kVec;
     short recs[4] = {0, 0, 0, 0};
-    bool any = false;
     if (i0 < d.n) {
         short4 r4 = *(const short4 *)(d.rec + i0);
         recs[0] = r4.x; recs[1] = r4.y; recs[2] = r4.z; recs[3] = r4.w;
-        any = (r4.x | r4.y | r4.z | r4.w) != 0;
     }
+    const bool warp_any = __any_sync(0xffffffffu, (recs[0] | recs[1] | recs[2] | recs[3]) != 0);
+    float tm0[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) tm0[k] = (filter && (recs[k] >> kRecShift) != 0) ? d.tmem[i0 + k] : 0.f;
     // pass 1: block-level counts per segment
-    if (any) {
+    if (warp_any) {
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            int r = recs[k];
-            if (r == 0) continue;
-            int cnt = r >> kRecShift, flags = r & 3;
+            int cnt = recs[k] >> kRecShift, flags = recs[k] & 3;
             int mag = cnt < 0 ? -cnt : cnt, pol = cnt < 0;
-            if (mag) {
-                float tm = filter ? d.tmem[i0 + k] : 0.f;
-                walk_pixel(mag, ts, filter, d.refr_f, tm, [&](int it, float) {
-                    int s = 2 * it + pol;
-                    if (s < kSegSmem) atomicAdd(&s_cnt[s], 1u);
-                });
+            float tm = tm0[k];
+            warp_walk(mag, pol, ts, filter, d.refr_f, tm, [&](int it, float, unsigned on, unsigned off, bool) {
+                if (lane == 0) {
+                    if (on && 2 * it < kSegSmem) atomicAdd(&s_cnt[2 * it], __popc(on));
+                    if (off && 2 * it + 1 < kSegSmem) atomicAdd(&s_cnt[2 * it + 1], __popc(off));
+                }
+            });
+            unsigned son = __ballot_sync(0xffffffffu, flags & 1), soff = __ballot_sync(0xffffffffu, flags & 2);
+            if (lane == 0) {
+                if (son) atomicAdd(&s_cnt[kSegSmem], __popc(son));
+                if (soff) atomicAdd(&s_cnt[kSegSmem + 1], __popc(soff));
             }
-            if (flags & 1) atomicAdd(&s_cnt[kSegSmem], 1u);
-            if (flags & 2) atomicAdd(&s_cnt[kSegSmem + 1], 1u);
         }
     }
     __syncthreads();
@@ -641,28 +669,35 @@ emu_emit_kernel(EmuDev d, FrameParams p, int slot, float4 *events) {
     }
     __syncthreads();
     // pass 2: write rows, patch state
-    if (any) {
+    if (warp_any) {
+        // lane 0 claims `count` consecutive rows of segment `seg` for this warp
+        auto claim = [&](int seg_smem, int seg, unsigned count) -> uint32_t {
+            if (seg_smem >= 0) return s_base[seg_smem] + atomicAdd(&s_cnt[seg_smem], count);
+            return segoff[seg] + atomicAdd(&cursor[seg], count);
+        };
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            int r = recs[k];
-            if (r == 0) continue;
             const int idx = i0 + k;
-            int cnt = r >> kRecShift, flags = r & 3;
+            int cnt = recs[k] >> kRecShift, flags = recs[k] & 3;
             int mag = cnt < 0 ? -cnt : cnt, pol = cnt < 0;
             const float fx = (float)(idx % d.W), fy = (float)(idx / d.W);
-            int fin = 0;
-            if (mag) {
-                float tm = filter ? d.tmem[idx] : 0.f;
-                const float pv = pol ? -1.0f : 1.0f;
-                fin = walk_pixel(mag, ts, filter, d.refr_f, tm, [&](int it, float t) {
-                    int s = 2 * it + pol;
-                    uint64_t row;
-                    if (s < kSegSmem) row = ev_base + s_base[s] + atomicAdd(&s_cnt[s], 1u);
-                    else row = ev_base + segoff[s] + atomicAdd(&cursor[s], 1u);
+            const float pv = pol ? -1.0f : 1.0f;
+            float tm = tm0[k];
+            int fin = warp_walk(mag, pol, ts, filter, d.refr_f, tm,
+                                [&](int it, float t, unsigned on, unsigned off, bool pass) {
+                uint32_t b_on = 0, b_off = 0;
+                if (lane == 0) {
+                    if (on) b_on = claim(2 * it < kSegSmem ? 2 * it : -1, 2 * it, __popc(on));
+                    if (off) b_off = claim(2 * it + 1 < kSegSmem ? 2 * it + 1 : -1, 2 * it + 1, __popc(off));
+                }
+                b_on = __shfl_sync(0xffffffffu, b_on, 0);
+                b_off = __shfl_sync(0xffffffffu, b_off, 0);
+                if (pass) {
+                    uint64_t row = ev_base + (pol ? b_off + __popc(off & lt_mask) : b_on + __popc(on & lt_mask));
                     events[row] = make_float4(t, fx, fy, pv);
-                });
-                if (filter && fin) d.tmem[idx] = tm;
-            }
+                }
+            });
+            if (filter && fin) d.tmem[idx] = tm;
             if (fin || flags) {
                 S *basep = (S *)d.base + idx;
                 S b = *basep;
@@ -673,13 +708,17 @@ emu_emit_kernel(EmuDev d, FrameParams p, int slot, float4 *events) {
                 if (flags) b = ((const S *)d.lp)[idx];   // emulator.py:940-942
                 *basep = b;
             }
-            if (flags & 1) {
-                uint64_t row = ev_base + s_base[kSegSmem] + atomicAdd(&s_cnt[kSegSmem], 1u);
-                events[row] = make_float4(ts_last, fx, fy, 1.0f);
-            }
-            if (flags & 2) {
-                uint64_t row = ev_base + s_base[kSegSmem + 1] + atomicAdd(&s_cnt[kSegSmem + 1], 1u);
-                events[row] = make_float4(ts_last, fx, fy, -1.0f);
+            unsigned son = __ballot_sync(0xffffffffu, flags & 1), soff = __ballot_sync(0xffffffffu, flags & 2);
+            if (son | soff) {
+                uint32_t b_on = 0, b_off = 0;
+                if (lane == 0) {
+                    if (son) b_on = claim(kSegSmem, 0, __popc(son));
+                    if (soff) b_off = claim(kSegSmem + 1, 0, __popc(soff));
+                }
+                b_on = __shfl_sync(0xffffffffu, b_on, 0);
+                b_off = __shfl_sync(0xffffffffu, b_off, 0);
+                if (flags & 1) events[ev_base + b_on + __popc(son & lt_mask)] = make_float4(ts_last, fx, fy, 1.0f);
+                if (flags & 2) events[ev_base + b_off + __popc(soff & lt_mask)] = make_float4(ts_last, fx, fy, -1.0f);
             }
         }
     }

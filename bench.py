@@ -44,7 +44,8 @@ def texture_clip(H, W, T, seed=0, dx=1, dy=0, up=16, lo=40.0, hi=215.0):
     big = big.clamp(0, 255).round().to(torch.uint8).numpy()
     out = np.empty((T, H, W), np.uint8)
     for k in range(T):
-        out[k] = big[k * dy:k * dy + H, k * dx:k * dx + W]
+        j = k if k < T // 2 else T - 1 - k      # forward then backward: the clip loops without a jump
+        out[k] = big[j * dy:j * dy + H, j * dx:j * dx + W]
     return out
 
 
@@ -171,7 +172,7 @@ def main():
     def fresh():
         em = EventEmulator(device="cuda:%d" % local_rank, rng_mode="device", seed=1234 + rank,
                            max_frames_per_step=64, **kw)
-        em.event_rows_hint = 24 * 1024 * 1024
+        em.event_rows_hint = 40 * 1024 * 1024
         return em
 
     def barrier():
@@ -179,30 +180,35 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run_device(em):
-        rows, offs = em.generate_events_batch(frames_dev, times, return_device=True)
-        return rows.shape[0]
+    clip_dt = T * dt
 
-    def run_e2e(em):
-        fr = frames_host.to(dev, non_blocking=True)
-        rows, offs = em.generate_events_batch(fr, times, return_device=False)
-        return rows.shape[0]
+    def timed(e2e, steps, warmup):
+        """One emulator, the (looping) clip fed `warmup + steps` times with advancing timestamps."""
+        em = fresh()
+        k = 0
 
-    def timed(fn, steps, warmup):
+        def one():
+            nonlocal k
+            t = times + k * clip_dt
+            k += 1
+            if e2e:
+                fr = frames_host.to(dev, non_blocking=True)
+                rows, offs = em.generate_events_batch(fr, t, return_device=False)
+            else:
+                rows, offs = em.generate_events_batch(frames_dev, t, return_device=True)
+            return rows.shape[0]
         for _ in range(warmup):
-            em = fresh(); fn(em); em.cleanup()
-        ems = [fresh() for _ in range(steps)]
+            one()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         n = 0
-        for em in ems:
-            n += fn(em)
+        for _ in range(steps):
+            n += one()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
-        for em in ems:
-            em.cleanup()
+        em.cleanup()
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         cnt = torch.tensor([float(n)], device=dev, dtype=torch.float64)
         if world > 1:
@@ -213,9 +219,9 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_dev, ev_dev = timed(run_device, args.steps, args.warmup)
+    ms_dev, ev_dev = timed(False, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
-    ms_e2e, ev_e2e = timed(run_e2e, args.steps, max(1, args.warmup))
+    ms_e2e, ev_e2e = timed(True, args.steps, max(1, args.warmup))
 
     # roofline of the dominant kernel (update): CUDA events inside the library around every launch
     em = fresh()
@@ -228,7 +234,7 @@ def main():
     f = 2
     while f < T:
         e = min(T, f + 64)
-        em._run_step(frames_dev[f:e], _lib.U8, times[f:e], return_device=True)
+        em._run_step(frames_dev[f:e], _lib.U8, times[f:e])
         _lib.check(em._lib.v2e_emu_profile_read(em._h, ms3, n3, em._stream()))
         tot_ms += np.array(list(ms3)); tot_n += np.array(list(n3))
         em.t_previous = float(times[e - 1])
@@ -262,7 +268,7 @@ def main():
             "frames_per_s": world * T * steps / (ms_dev * 1e-3),
             "e2e": {"value": e2e, "unit": "Mevents/s", "h2d_bytes_per_step": T * H * W,
                     "d2h_bytes_per_step": int(16 * ev_e2e / steps / world), "ms_per_step": ms_e2e / steps},
-            "gpu_launches": int(steps * (T - 1) * kernels_per_frame + steps * (1 + (T + 62) // 64)),
+            "gpu_launches": int(steps * T * kernels_per_frame + steps * ((T + 63) // 64)),
             "roofline": {"kernel": "emu_update_kernel<double,u8>", "bound": "hbm", "achieved": achieved,
                          "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
                          "traffic": None, "peak_source": pk["source"], "bytes_per_launch": upd_bytes,

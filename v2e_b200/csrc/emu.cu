@@ -74,6 +74,7 @@ struct FrameParams {
     float dt_f;                         // float32(delta_time)       (emulator_utils.py:129)
     uint32_t frame_index;               // Philox counter word
     double shot_c;                      // (shot_noise_rate_hz/2)*delta_time (emulator_utils.py:323-324)
+    double shot_bound;                  // >= every pixel's ON/OFF shot probability of this frame (x >= 0)
     uint64_t capacity;
 };
 
@@ -349,17 +350,22 @@ __global__ void __launch_bounds__(kThreads) emu_first_frame_kernel(EmuDev d, Fra
 
 // ---------------------------------------------------------------------------------------------
 // update kernel: emulator.py:663-775 for 4 pixels per thread
+// RNG: 0 = replay (host-drawn fields), 1 = device (Philox). Everything else is a uniform runtime
+// flag. Tables in shared memory: lin_log(0..255) as float64 and inten01(0..255) = (x+20)/275
+// (the same IEEE division the reference does, evaluated once per block instead of once per pixel).
 // ---------------------------------------------------------------------------------------------
-template <typename S, int FT>
+template <typename S, int FT, int RNG>
 __global__ void __launch_bounds__(kThreads)
 emu_update_kernel(EmuDev d, FrameParams p, const void *frame, const float *leak_randn,
                   const float *shot_rand, int slot, int do_plan, int lp_done) {
-    __shared__ float s_lut[256];
+    __shared__ double s_lut[256];
+    __shared__ double s_inten[256];
     __shared__ uint32_t s_hist[kSegSmem + 2];
     __shared__ int s_max;
     if (*(volatile int32_t *)d.abort_flag) return;
     const int tid = threadIdx.x;
-    s_lut[tid] = d.lut[tid];
+    s_lut[tid] = (double)d.lut[tid];
+    s_inten[tid] = ((double)tid + 20.0) / 275.0;
     if (tid < kSegSmem + 2) s_hist[tid] = 0;
     if (tid == 0) s_max = 0;
     __syncthreads();
@@ -384,20 +390,21 @@ emu_update_kernel(EmuDev d, FrameParams p, const void *frame, const float *leak_
             for (int k = 0; k < 4; k++) { thp[k] = (float)d.pos_nom; thn[k] = (float)d.neg_nom; }
         }
         if (d.csdvs) ld4(d.surround, i0, su);
-        const bool shot_here = d.shot_on && (d.rng_mode == 1 || shot_rand != nullptr);
+        const bool shot_here = d.shot_on && (RNG == 1 || shot_rand != nullptr);
         if (d.leak_on) {
             ld4(d.noise_rate, i0, nr);
-            if (d.rng_mode == 0) load_f32x4_any(leak_randn, i0, d.n, lr);
+            if (RNG == 0) load_f32x4_any(leak_randn, i0, d.n, lr);
         }
-        if (shot_here && d.rng_mode == 0) load_f32x4_any(shot_rand, i0, d.n, sr);
-        if (d.rng_mode == 1 && (d.leak_on || d.shot_on)) {
-            uint2 key = make_uint2((uint32_t)d.seed, (uint32_t)(d.seed >> 32));
+        if (RNG == 0 && shot_here) load_f32x4_any(shot_rand, i0, d.n, sr);
+        if (RNG == 1) {
+            const uint2 key = make_uint2((uint32_t)d.seed, (uint32_t)(d.seed >> 32));
             if (d.leak_on) {
+                // Box-Muller on fast intrinsics: this stream only has to be N(0,1), not torch's bits
                 uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 >> 2), p.frame_index, 0u, 0x6c65616bu), key);
-                float a = sqrtf(-2.0f * logf(u01_open(r.x))), b = sqrtf(-2.0f * logf(u01_open(r.z)));
+                float a = __fsqrt_rn(-2.0f * __logf(u01_open(r.x))), b = __fsqrt_rn(-2.0f * __logf(u01_open(r.z)));
                 float sa, ca, sb, cb;
-                sincosf(6.283185307179586f * u01_half(r.y), &sa, &ca);
-                sincosf(6.283185307179586f * u01_half(r.w), &sb, &cb);
+                __sincosf(6.283185307179586f * u01_half(r.y), &sa, &ca);
+                __sincosf(6.283185307179586f * u01_half(r.w), &sb, &cb);
                 lr[0] = a * ca; lr[1] = a * sa; lr[2] = b * cb; lr[3] = b * sb;
             }
             if (d.shot_on) {
@@ -409,23 +416,23 @@ emu_update_kernel(EmuDev d, FrameParams p, const void *frame, const float *leak_
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const double xv = x[k];
+            const bool is_code = FT == V2E_U8 || (xv >= 0.0 && xv <= 255.0 && xv == floor(xv));
             // photoreceptor low-pass (emulator_utils.py:57-109)
             if (!lp_done) {
-                float lnf = 0.f;
-                if (!d.hdr)
-                    lnf = (FT == V2E_U8 || (xv >= 0.0 && xv <= 255.0 && xv == floor(xv))) ? s_lut[(int)xv]
-                                                                                          : lin_log_eval(xv);
+                double ln;                               // float32 lin_log value, widened (or raw if hdr)
+                if (d.hdr) ln = xv;
+                else ln = is_code ? s_lut[(int)xv] : (double)lin_log_eval(xv);
                 if (sizeof(S) == 8) {
-                    double ln = d.hdr ? xv : (double)lnf;
                     if (d.lowpass_on) {
-                        double eps = ((xv + 20.0) / 275.0) * p.eps_scale;
+                        double inten01 = is_code ? s_inten[(int)xv] : (xv + 20.0) / 275.0;
+                        double eps = inten01 * p.eps_scale;
                         if (eps > 1.0) eps = 1.0;
                         lp[k] = (S)((1.0 - eps) * (double)lp[k] + eps * ln);
                     } else {
                         lp[k] = (S)ln;
                     }
                 } else {
-                    lp[k] = (S)lnf;
+                    lp[k] = (S)ln;                       // exact: ln is a widened float32
                 }
             }
             // leak (emulator_utils.py:114-134): float32 products, subtract in S
@@ -442,10 +449,16 @@ emu_update_kernel(EmuDev d, FrameParams p, const void *frame, const float *leak_
             if (sizeof(S) == 8 && !d.per_pixel_thres) { tp = (S)d.pos_nom; tn = (S)d.neg_nom; }
             else { tp = (S)thp[k]; tn = (S)thn[k]; }
             int32_t cnt = 0;
-            if (diff > (S)0) cnt = div_floor_count<S>(diff, tp);
-            else if (diff < (S)0) cnt = -div_floor_count<S>(-diff, tn);
+            if (diff >= tp) cnt = div_floor_count<S>(diff, tp);
+            else if (-diff >= tn) cnt = -div_floor_count<S>(-diff, tn);
+            // shot noise: exact test only when the draw can possibly cross (shot_bound >= any
+            // per-pixel probability; see make_params)
             int flags = 0;
-            if (shot_here) flags = shot_flags(d, p, xv, sr[k], thp[k], thn[k]);
+            if (shot_here) {
+                const double r = (double)sr[k];
+                if (!(xv >= 0.0 && xv <= 255.0) || r < p.shot_bound || r > 1.0 - p.shot_bound)
+                    flags = shot_flags(d, p, xv, sr[k], thp[k], thn[k]);
+            }
             const bool valid = (i0 + k) < d.n;
             if (!valid) { cnt = 0; flags = 0; }
             int32_t mag = cnt < 0 ? -cnt : cnt;
@@ -463,21 +476,27 @@ emu_update_kernel(EmuDev d, FrameParams p, const void *frame, const float *leak_
     // per-(iteration,polarity) histogram, one shared-memory atomic per warp and segment
     {
         const int lane = tid & 31;
+        const int any_sig = __any_sync(0xffffffffu, (mags[0] | mags[1] | mags[2] | mags[3]) != 0);
+        const int any_shot = __any_sync(0xffffffffu, (flg[0] | flg[1] | flg[2] | flg[3]) != 0);
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const int wmax = __reduce_max_sync(0xffffffffu, mags[k]);
-            for (int it = 0; it < wmax; it++) {
-                unsigned on = __ballot_sync(0xffffffffu, mags[k] > it && !pols[k]);
-                unsigned off = __ballot_sync(0xffffffffu, mags[k] > it && pols[k]);
-                if (lane == 0) {
-                    if (on) { if (2 * it < kSegSmem) atomicAdd(&s_hist[2 * it], __popc(on)); else atomicAdd(&hist[2 * it], __popc(on)); }
-                    if (off) { if (2 * it + 1 < kSegSmem) atomicAdd(&s_hist[2 * it + 1], __popc(off)); else atomicAdd(&hist[2 * it + 1], __popc(off)); }
+            if (any_sig) {
+                const int wmax = __reduce_max_sync(0xffffffffu, mags[k]);
+                for (int it = 0; it < wmax; it++) {
+                    unsigned on = __ballot_sync(0xffffffffu, mags[k] > it && !pols[k]);
+                    unsigned off = __ballot_sync(0xffffffffu, mags[k] > it && pols[k]);
+                    if (lane == 0) {
+                        if (on) { if (2 * it < kSegSmem) atomicAdd(&s_hist[2 * it], __popc(on)); else atomicAdd(&hist[2 * it], __popc(on)); }
+                        if (off) { if (2 * it + 1 < kSegSmem) atomicAdd(&s_hist[2 * it + 1], __popc(off)); else atomicAdd(&hist[2 * it + 1], __popc(off)); }
+                    }
                 }
             }
-            unsigned son = __ballot_sync(0xffffffffu, flg[k] & 1), soff = __ballot_sync(0xffffffffu, flg[k] & 2);
-            if (lane == 0) {
-                if (son) atomicAdd(&s_hist[kSegSmem], __popc(son));
-                if (soff) atomicAdd(&s_hist[kSegSmem + 1], __popc(soff));
+            if (any_shot) {
+                unsigned son = __ballot_sync(0xffffffffu, flg[k] & 1), soff = __ballot_sync(0xffffffffu, flg[k] & 2);
+                if (lane == 0) {
+                    if (son) atomicAdd(&s_hist[kSegSmem], __popc(son));
+                    if (soff) atomicAdd(&s_hist[kSegSmem + 1], __popc(soff));
+                }
             }
         }
     }
@@ -745,6 +764,7 @@ struct V2eEmu {
     uint32_t frame_counter;     // frames counted so far (Philox counter word, rng_mode 1)
     uint32_t step_base;         // frame_counter at the start of the current step
     double last_dt;             // delta_time of the last single-frame phase_count
+    double min_thres;           // smallest per-pixel threshold uploaded by v2e_emu_set_fields
     int profile;                // 1: bracket every kernel of v2e_emu_step with CUDA events
     cudaEvent_t *ev;            // [max_slots][3 kinds][2]
     int prof_frames;
@@ -783,6 +803,18 @@ static FrameParams make_params(const V2eEmu *h, double t_frame, double t_prev, u
     p.dt_f = (float)p.dt;
     p.frame_index = frame_index;
     p.shot_c = (h->cfg.shot_noise_rate_hz / 2) * p.dt;
+    {
+        // probability = shot_c * ((f-1)*inten01 + 1) * nominal/threshold; for x >= 0 the intensity term
+        // is <= max(1, f) on 0 <= x <= 255 and thresholds are clamped at 0.01 by the caller (emulator.py:464, 471)
+        double inten_max = h->cfg.shot_inten_factor > 1 ? h->cfg.shot_inten_factor : 1.0;   // 0 <= x <= 255
+        double pre_max = 1.0;
+        if (h->cfg.per_pixel_thres) {
+            double nom = h->cfg.pos_thres_nominal > h->cfg.neg_thres_nominal ? h->cfg.pos_thres_nominal
+                                                                               : h->cfg.neg_thres_nominal;
+            pre_max = nom / h->min_thres;
+        }
+        p.shot_bound = fabs(p.shot_c) * inten_max * pre_max * 1.0001 + 1e-300;
+    }
     p.capacity = capacity;
     return p;
 }
@@ -824,6 +856,7 @@ extern "C" int v2e_emu_create(const V2eEmuCfg *cfg, V2eEmu **out) {
     d.shot_inten_m1 = cfg->shot_inten_factor - 1;
     d.seed = cfg->seed;
     h->state_elem = d.state_f64 ? 8 : 4;
+    h->min_thres = 0.01;
     size_t np = (size_t)d.n_pad;
 #define ALLOC(ptr, bytes)                                                     \
     do {                                                                      \
@@ -888,6 +921,10 @@ extern "C" int v2e_emu_set_fields(V2eEmu *h, const float *pos, const float *neg,
         if (!pos || !neg) return fail(V2E_E_INVALID, "per-pixel thresholds required");
         CU(cudaMemcpy(h->d.pos_thres, pos, bytes, cudaMemcpyHostToDevice));
         CU(cudaMemcpy(h->d.neg_thres, neg, bytes, cudaMemcpyHostToDevice));
+        float mn = pos[0];
+        for (int i = 0; i < h->d.n; i++) { mn = pos[i] < mn ? pos[i] : mn; mn = neg[i] < mn ? neg[i] : mn; }
+        if (!(mn > 0)) return fail(V2E_E_INVALID, "thresholds must be positive");
+        h->min_thres = (double)mn;
     }
     if (h->d.leak_on) {
         if (!nr) return fail(V2E_E_INVALID, "noise_rate field required when leak_rate_hz > 0");
@@ -922,17 +959,23 @@ extern "C" int v2e_emu_first_frame(V2eEmu *h, const void *frame, int dtype, doub
     return V2E_OK;
 }
 
-template <typename S>
-static int launch_update(V2eEmu *h, const FrameParams &p, const void *frame, int dt, const float *lr,
-                         const float *sr, int slot, int do_plan, int lp_done, cudaStream_t st) {
+template <typename S, int RNG>
+static int launch_update_r(V2eEmu *h, const FrameParams &p, const void *frame, int dt, const float *lr,
+                           const float *sr, int slot, int do_plan, int lp_done, cudaStream_t st) {
     int g = grid_for(h->d);
     switch (dt) {
-        case V2E_U8: emu_update_kernel<S, V2E_U8><<<g, kThreads, 0, st>>>(h->d, p, frame, lr, sr, slot, do_plan, lp_done); break;
-        case V2E_F32: emu_update_kernel<S, V2E_F32><<<g, kThreads, 0, st>>>(h->d, p, frame, lr, sr, slot, do_plan, lp_done); break;
-        case V2E_F64: emu_update_kernel<S, V2E_F64><<<g, kThreads, 0, st>>>(h->d, p, frame, lr, sr, slot, do_plan, lp_done); break;
+        case V2E_U8: emu_update_kernel<S, V2E_U8, RNG><<<g, kThreads, 0, st>>>(h->d, p, frame, lr, sr, slot, do_plan, lp_done); break;
+        case V2E_F32: emu_update_kernel<S, V2E_F32, RNG><<<g, kThreads, 0, st>>>(h->d, p, frame, lr, sr, slot, do_plan, lp_done); break;
+        case V2E_F64: emu_update_kernel<S, V2E_F64, RNG><<<g, kThreads, 0, st>>>(h->d, p, frame, lr, sr, slot, do_plan, lp_done); break;
         default: return fail(V2E_E_INVALID, "bad frame dtype");
     }
     return V2E_OK;
+}
+template <typename S>
+static int launch_update(V2eEmu *h, const FrameParams &p, const void *frame, int dt, const float *lr,
+                         const float *sr, int slot, int do_plan, int lp_done, cudaStream_t st) {
+    return h->d.rng_mode == 1 ? launch_update_r<S, 1>(h, p, frame, dt, lr, sr, slot, do_plan, lp_done, st)
+                              : launch_update_r<S, 0>(h, p, frame, dt, lr, sr, slot, do_plan, lp_done, st);
 }
 
 static int launch_shot(V2eEmu *h, const FrameParams &p, const void *frame, int dt, const float *sr,

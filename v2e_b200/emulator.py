@@ -295,11 +295,12 @@ class EventEmulator(object):
         if self._ev_dev is None or self._ev_dev.shape[0] < rows:
             rows = max(int(rows), 16)
             self._ev_dev = torch.empty((rows, 4), dtype=torch.float32, device=self.device)
-            self._ev_pin = torch.empty((rows, 4), dtype=torch.float32).pin_memory()
 
     def _rows_to_host(self, n_rows, base=0):
         if n_rows == 0:
             return np.zeros((0, 4), np.float32)
+        if self._ev_pin is None or self._ev_pin.shape[0] < n_rows:   # pinned staging, grown on demand
+            self._ev_pin = torch.empty((int(n_rows * 1.25) + 1024, 4), dtype=torch.float32).pin_memory()
         self._ev_pin[:n_rows].copy_(self._ev_dev[base:base + n_rows], non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         return self._ev_pin[:n_rows].numpy().copy()
@@ -337,7 +338,8 @@ class EventEmulator(object):
         if self.rng_mode == "replay" and (per_frame_rng or self.exact_order):
             ev = self._generate_replay(fr, code, t_frame)
         else:
-            ev, _ = self._run_step(fr.unsqueeze(0), code, [t_frame])
+            total, _ = self._run_step(fr.unsqueeze(0), code, [t_frame])
+            ev = self._rows_to_host(total)
         self.t_previous = t_frame
         if ev is not None and len(ev) > 0:
             return ev
@@ -431,18 +433,20 @@ class EventEmulator(object):
         self.num_events_total += int(fi.n_events)
 
     # batched path ------------------------------------------------------------------------------
-    def _run_step(self, frames_dev, code, t_frames, return_device=False):
-        """frames_dev: [T,H,W] device tensor, T <= max_frames_per_step. Returns (rows, offsets[T+1])."""
+    def _run_step(self, frames_dev, code, t_frames, base_row=0):
+        """frames_dev: [T,H,W] device tensor, T <= max_frames_per_step. Appends this chunk's rows to the
+        device event buffer starting at base_row; returns (end_row, absolute offsets[T+1])."""
         T = frames_dev.shape[0]
         L, h = self._lib, self._h
         n = self._H * self._W
         ts = (ctypes.c_double * T)(*[float(t) for t in t_frames])
         with torch.cuda.device(self.device):
             st = self._stream()
-            self._ensure_event_buffers(self.event_rows_hint or max(2 * n, 1 << 16))
+            if self._ev_dev is None:
+                self._ensure_event_buffers(self.event_rows_hint or max(2 * n, 1 << 16))
             info = (_lib.V2eFrameInfo * T)()
             done, rows = ctypes.c_int(0), ctypes.c_uint64(0)
-            first, resume, base = 0, 0, 0
+            first, resume, base = 0, 0, int(base_row)
             while True:
                 _lib.check(L.v2e_emu_step(h, ctypes.c_void_p(frames_dev.data_ptr()), code, T, ts,
                                           float(self.t_previous), None, None,
@@ -460,21 +464,21 @@ class EventEmulator(object):
                 self._ev_dev = None
                 self._ensure_event_buffers(max(2 * need, 2 * old.shape[0]))
                 self._ev_dev[:base].copy_(old[:base])
+                del old
             total = int(rows.value)
             offsets = np.array([int(info[f].ev_base) for f in range(T)] + [total], np.int64)
             for f in range(T):
                 self._account(info[f])
             self.last_frame_info = info[T - 1]
-            if return_device:
-                return self._ev_dev[:total], offsets
-            return self._rows_to_host(total), offsets
+            return total, offsets
 
     def generate_events_batch(self, frames, t_frames, return_device=False):
         """Fast path (not in the reference): all frames of a clip in a few launches per frame and no
         per-frame host synchronisation. frames: [T,H,W]; t_frames: [T] seconds, non-decreasing.
         Returns (rows [N,4] float32, offsets [T+1]) -- rows of frame f are rows[offsets[f]:offsets[f+1]].
-        The first frame of a fresh emulator only initialises state (zero rows), as in the reference.
-        Needs rng_mode="device" when leak or shot noise is on."""
+        With return_device=True rows is a view of the emulator's device buffer (valid until the next
+        call). The first frame of a fresh emulator only initialises state (zero rows), as in the
+        reference. Needs rng_mode="device" when leak or shot noise is on."""
         if self.rng_mode == "replay" and (self.leak_rate_hz > 0 or self.shot_noise_rate_hz > 0):
             raise RuntimeError("generate_events_batch with per-frame noise needs rng_mode='device' "
                                "(replay mode must interleave host draws frame by frame)")
@@ -488,27 +492,27 @@ class EventEmulator(object):
         for a, b in zip([self.t_previous] + t_frames[:-1], t_frames):
             if b < a:
                 raise ValueError("this frame time={} must be later than previous frame time={}".format(b, a))
-        chunks, offs = [], [0]
+        offs = [0]
         start = 0
         if not self._initialized:
             self._first_frame(fr[0], code, t_frames[0])
             self.frame_counter += 1
             offs.append(0)
             start = 1
-        f = start
+        f, row = start, 0
         while f < T:
             e = min(T, f + self.max_frames_per_step)
-            rows, o = self._run_step(fr[f:e], code, t_frames[f:e], return_device=return_device)
-            chunks.append(rows.clone() if return_device else rows)
-            offs.extend((o[1:] + offs[-1] - o[0]).tolist())
+            row, o = self._run_step(fr[f:e], code, t_frames[f:e], base_row=row)
+            offs.extend(o[1:].tolist())
             self.t_previous = t_frames[e - 1]
             self.frame_counter += e - f
             f = e
+        offs = np.asarray(offs, np.int64)
         if return_device:
-            ev = torch.cat(chunks) if chunks else torch.zeros((0, 4), dtype=torch.float32, device=self.device)
-        else:
-            ev = np.concatenate(chunks) if chunks else np.zeros((0, 4), np.float32)
-        return ev, np.asarray(offs, np.int64)
+            if self._ev_dev is None:
+                return torch.zeros((0, 4), dtype=torch.float32, device=self.device), offs
+            return self._ev_dev[:row], offs
+        return self._rows_to_host(row), offs
 
     # state tensors by the reference's attribute names (emulator.py:756-764 reads them via getattr)
     def _state(self, name):

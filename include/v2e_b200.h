@@ -58,7 +58,7 @@ typedef struct V2eEmuCfg {
     double shot_inten_factor;       /* emulator.py:213 SHOT_NOISE_INTEN_FACTOR = 0.25 */
     int32_t rng_mode;               /* 0 = replay: caller uploads the per-frame random fields the
                                            reference would draw (bit-exact with torch's CPU generator);
-                                       1 = device: counter-based Philox4x32-10 inside the kernels */
+                                       1 = device: counter-based Philox4x32-7 inside the kernels */
     int32_t iter_cap;               /* max events per pixel per frame that can be emitted (>=1) */
     uint64_t seed;                  /* rng_mode 1 only */
     int32_t csdvs;                  /* 1: centre-surround model enabled (emulator.py:245-265) */

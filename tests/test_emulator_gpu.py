@@ -154,14 +154,14 @@ def test_event_buffer_growth_resumes_without_loss():
     H, W, T = 48, 64, 12
     fr = texture_frames(H, W, T, seed=1, speed=2.0)
     ts = [k * 1e-3 for k in range(T)]
-    orc = OracleEmulator(**kw)
+    orc = OracleEmulator(seed=5, **kw)
     want = [orc.generate_events(f, t) for f, t in zip(fr, ts)]
     em = _emulator(rng_mode="device", **kw)
     em.event_rows_hint = 64
     rows, offs = em.generate_events_batch(fr, ts)
     for i in range(T):
         assert_events_equal(rows[offs[i]:offs[i + 1]], want[i], exact_order=False, ctx="frame %d" % i)
-    em2 = _emulator(**kw)
+    em2 = _emulator(seed=5, **kw)       # same seed: same randperm replay as the oracle run above
     em2.event_rows_hint = 16
     for i in range(T):
         assert_events_equal(em2.generate_events(fr[i], ts[i]), want[i], exact_order=True, ctx="frame %d" % i)
@@ -224,6 +224,7 @@ def test_full_size_crop_property_1280x720():
         assert np.array_equal(a, b), "frame %d" % i
         total += len(sub)
     assert total > 0
-    # invariant after every frame: |lp - base| < threshold everywhere (all crossings were emitted)
+    # invariant after every frame: every crossing was emitted, so |lp - base| stays below the threshold,
+    # up to the float32 rounding of the base update count*theta (emulator.py:936-937): <= 0.5 ulp32(5.5)
     d = (em.lp_log_frame - em.base_log_frame).abs().max().item()
-    assert d < 0.2 + 1e-9
+    assert d < 0.2 + 2.4e-7

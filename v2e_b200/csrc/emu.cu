@@ -36,6 +36,7 @@ constexpr int kVec = 4;                 // pixels per thread
 constexpr int kSegSmem = 64;            // (iteration,polarity) segments aggregated in shared memory
 constexpr int kRecShift = 2;            // record = (signed count << 2) | shot_off << 1 | shot_on
 constexpr int kRecMaxCount = 8191;
+constexpr int kPhiloxRounds = 7;         // Philox4x32-7: the lightest variant that passes BigCrush (Salmon et al. 2011)
 
 struct FrameCtrl {                      // one per frame slot, device memory, zeroed per step
     int32_t max_n;
@@ -83,8 +84,14 @@ struct FrameParams {
 // ---------------------------------------------------------------------------------------------
 // aten/src/ATen/native/BinaryOps.h div_floor_floating, a >= 0, b > 0
 template <typename S> __device__ __forceinline__ int32_t div_floor_count(S a, S b);
+// Exact shortcuts (a >= b > 0): for b <= a < 2b, fmod(a,b) = a-b exactly (Sterbenz), a-(a-b) = b,
+// b/b = 1 -> 1; for 2b <= a < 3b, fmod = a-2b exactly, a-(a-2b) = 2b, 2b/b = 2 -> 2. The test
+// (a-2b) < b decides a < 3b correctly even where a-2b rounds (a > 4b). Beyond that: the full formula.
 template <> __device__ __forceinline__ int32_t div_floor_count<double>(double a, double b) {
     if (a < b) return 0;                // fmod(a,b)=a -> (a-a)/b = 0
+    const double b2 = b + b;
+    if (a < b2) return 1;
+    if (a - b2 < b) return 2;
     double mod = fmod(a, b);
     double div = (a - mod) / b;
     double fl = floor(div);
@@ -93,6 +100,9 @@ template <> __device__ __forceinline__ int32_t div_floor_count<double>(double a,
 }
 template <> __device__ __forceinline__ int32_t div_floor_count<float>(float a, float b) {
     if (a < b) return 0;
+    const float b2 = b + b;
+    if (a < b2) return 1;
+    if (a - b2 < b) return 2;
     float mod = fmodf(a, b);
     float div = (a - mod) / b;
     float fl = floorf(div);
@@ -130,12 +140,13 @@ __device__ __forceinline__ float lin_log_eval(double x) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Philox4x32-10 (rng_mode 1)
+// Philox4x32-R (rng_mode 1)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+template <int ROUNDS>
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
-    for (int r = 0; r < 10; r++) {
+    for (int r = 0; r < ROUNDS; r++) {
         uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
         uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
         ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
@@ -355,7 +366,7 @@ __global__ void __launch_bounds__(kThreads) emu_first_frame_kernel(EmuDev d, Fra
 // (the same IEEE division the reference does, evaluated once per block instead of once per pixel).
 // ---------------------------------------------------------------------------------------------
 template <typename S, int FT, int RNG>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 emu_update_kernel(EmuDev d, FrameParams p, const void *frame, const float *leak_randn,
                   const float *shot_rand, int slot, int do_plan, int lp_done) {
     __shared__ double s_lut[256];
@@ -400,7 +411,7 @@ emu_update_kernel(EmuDev d, FrameParams p, const void *frame, const float *leak_
             const uint2 key = make_uint2((uint32_t)d.seed, (uint32_t)(d.seed >> 32));
             if (d.leak_on) {
                 // Box-Muller on fast intrinsics: this stream only has to be N(0,1), not torch's bits
-                uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 >> 2), p.frame_index, 0u, 0x6c65616bu), key);
+                uint4 r = philox4x32<kPhiloxRounds>(make_uint4((uint32_t)(i0 >> 2), p.frame_index, 0u, 0x6c65616bu), key);
                 float a = __fsqrt_rn(-2.0f * __logf(u01_open(r.x))), b = __fsqrt_rn(-2.0f * __logf(u01_open(r.z)));
                 float sa, ca, sb, cb;
                 __sincosf(6.283185307179586f * u01_half(r.y), &sa, &ca);
@@ -408,7 +419,7 @@ emu_update_kernel(EmuDev d, FrameParams p, const void *frame, const float *leak_
                 lr[0] = a * ca; lr[1] = a * sa; lr[2] = b * cb; lr[3] = b * sb;
             }
             if (d.shot_on) {
-                uint4 r = philox4x32_10(make_uint4((uint32_t)(i0 >> 2), p.frame_index, 1u, 0x73686f74u), key);
+                uint4 r = philox4x32<kPhiloxRounds>(make_uint4((uint32_t)(i0 >> 2), p.frame_index, 1u, 0x73686f74u), key);
                 sr[0] = u01_half(r.x); sr[1] = u01_half(r.y); sr[2] = u01_half(r.z); sr[3] = u01_half(r.w);
             }
         }

@@ -10,7 +10,7 @@ Two RNG modes:
   rng_mode="replay" (default): thresholds / noise-rate / per-frame leak and shot fields are drawn on
       the host exactly like the reference and uploaded; per-iteration `randperm` calls are replayed
       so the returned rows are bit-identical *including order* to the reference's CPU output.
-  rng_mode="device": per-frame noise comes from an in-kernel Philox4x32-10 stream; no per-frame
+  rng_mode="device": per-frame noise comes from an in-kernel Philox4x32-7 stream; no per-frame
       host work, frames can be batched (`generate_events_batch`). Counts are bit-exact whenever no
       per-frame noise is enabled, statistically equivalent otherwise.
 

@@ -161,6 +161,25 @@ int v2e_emu_state_is_f64(V2eEmu *h);
 /* device pointer of a state array (same `which`), for zero-copy views */
 void *v2e_emu_state_ptr(V2eEmu *h, int which);
 
+/* ------------------------------------------------------------------------- */
+/* SuperSloMo network pieces: replace v2ecore/model.py (UNet :158-226, backWarp :229-300)
+ * and the per-frame tensor code of v2ecore/slomo.py:330-444.                      */
+/* ------------------------------------------------------------------------- */
+
+/* conv2d(stride 1, "same" zero padding) + bias + LeakyReLU(slope) as a tcgen05 implicit GEMM
+ * (model.py:72-76, 145-154, 213-225: every conv of the UNet is followed by leaky_relu(0.1)).
+ * Activations: NHWC fp16, channel counts padded to a multiple of 16 (padding channels zero).
+ *   x1_dev [N,H,W,C1], optional x2_dev [N,H,W,C2] (C2 = 0: none) -- the logical input is
+ *   cat(x1, x2) along channels (model.py:150-153) without materialising it.
+ * wgt_dev: fp16 [Cout_pad][KH*KW*(C1+C2)], K index = (r*KW+s)*(C1+C2) + c. bias_dev: fp32 [Cout_pad].
+ * Cout_pad in {16,32,64} or a multiple of 128.
+ * out_mode 0: out_dev fp16 NHWC with channel stride out_cstride (>= Cout_pad);
+ * out_mode 1: out_dev fp32 [N,H,W,8], the first 8 output channels (network heads). */
+int v2e_conv2d_lrelu_sm100(const void *x1_dev, int C1, const void *x2_dev, int C2,
+                           const void *wgt_dev, const float *bias_dev, int Cout_pad, int KH, int KW,
+                           int N, int H, int W, void *out_dev, int out_cstride, int out_mode,
+                           int co_real, float slope, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

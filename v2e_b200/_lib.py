@@ -53,6 +53,8 @@ _SIGS = {
     "v2e_emu_read_counts": (_i, [_vp, ctypes.POINTER(ctypes.c_int32), _vp, _i, _vp]),
     "v2e_emu_phase_shot": (_i, [_vp, _vp, _i, _d, _d, _vp, _u64, _vp]),
     "v2e_emu_phase_emit": (_i, [_vp, _d, _d, _vp, _u64, _vp]),
+    "v2e_conv2d_lrelu_sm100": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i,
+                                    ctypes.c_float, _vp]),
     "v2e_emu_profile": (_i, [_vp, _i]),
     "v2e_emu_profile_read": (_i, [_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_i), _vp]),
     "v2e_emu_get_state": (_i, [_vp, _i, _vp, ctypes.POINTER(_i)]),

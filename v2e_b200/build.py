@@ -65,7 +65,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out.decode())
         if p.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s" % (u, out.decode()))
-    cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcuda"]
+    cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs
     subprocess.check_call(cmd)
     return LIB
 

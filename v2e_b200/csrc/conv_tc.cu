@@ -1,0 +1,310 @@
+// Implicit-GEMM convolution + bias + LeakyReLU on the 5th-gen tensor cores (sm_100a).
+//
+// Replaces the 23 conv2d+leaky_relu pairs of the reference's UNet (v2ecore/model.py:10-226, called
+// from v2ecore/slomo.py:343, 415-419), which the reference runs as stock cuDNN kernels.
+//
+//   D[pixel, cout] = sum_{tap=(r,s)} sum_{c} X[n, y+r-ph, x+s-pw, c] * Wt[cout, tap, c]      (+bias, lrelu)
+//
+// Layout: activations NHWC fp16 (C padded to a multiple of 16), weights [Cout_pad][KH*KW*Ctot] fp16
+// (K index = tap*Ctot + c), accumulation fp32 in TMEM.
+// One CTA computes a 128-pixel (8 rows x 16 columns) x BN-channel output tile:
+//   warp 0      : TMA producer. For every filter tap and every KC-channel slab it issues one 4-D tiled
+//                 load of the *shifted* 8x16 window (cp.async.bulk.tensor, 128B/64B/32B swizzle) --
+//                 out-of-bounds rows/columns are zero-filled by TMA, which is exactly the conv's zero
+//                 padding, so no im2col buffer and no halo logic -- plus one 2-D load of the BN x KC
+//                 weight slab. A concatenated input (up-blocks: cat(x, skip), model.py:150-153) is
+//                 read from two tensor maps, so the concat is never materialised.
+//   warp 1      : allocates TMEM, issues tcgen05.mma (M=128, N=BN, K=16, kind::f16) from the swizzled
+//                 shared-memory stages, commits to mbarriers.
+//   warps 2..5  : epilogue: tcgen05.ld the accumulator (lane == pixel), + bias, LeakyReLU(0.1),
+//                 convert and store NHWC (fp16) or the first channels as fp32 (network outputs).
+// Pipeline: kStages-deep mbarrier ring between producer and MMA issuer; two CTAs per SM overlap one
+// tile's epilogue with the other's main loop.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/v2e_b200.h"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int kTileH = 8, kTileW = 16, kBM = kTileH * kTileW;   // 128 pixels = UMMA M
+constexpr int kStages = 3;
+constexpr int kConvThreads = 192;
+
+struct ConvParams {
+    int N, H, W;
+    int C1, C2;                 // padded channel counts of the two inputs (C2 = 0: single input)
+    int KH, KW;
+    int KC;                     // channels per K slab: 64 / 32 / 16  -> swizzle 128B / 64B / 32B
+    int BN;                     // output channels per CTA (UMMA N)
+    int tiles_x, tiles_y;
+    int out_cstride;            // channel stride (elements) of the fp16 NHWC output
+    int out_mode;               // 0: fp16 NHWC; 1: fp32 [N,H,W,8], first co_real channels
+    int co_real;
+    float slope;
+    const float *bias;          // [Cout_pad]
+    void *out;
+};
+
+__global__ void __launch_bounds__(kConvThreads)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+               const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve: stages of [A 128 x KC fp16][B BN x KC fp16], 1024-byte aligned
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t a_bytes = kBM * p.KC * 2;
+    const uint32_t b_bytes_raw = p.BN * p.KC * 2;
+    const uint32_t b_bytes = (b_bytes_raw + 1023) & ~1023u;
+    const uint32_t stage_bytes = a_bytes + b_bytes;
+    __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], tmem_full_bar;
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x;
+    const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, n = tile / (p.tiles_x * p.tiles_y);
+    const int x0 = tx * kTileW, y0 = ty * kTileH;
+    const int n0 = blockIdx.y * p.BN;
+    const int Ctot = p.C1 + p.C2;
+    const int slabs = Ctot / p.KC;
+    const int k_iters = p.KH * p.KW * slabs;
+    const uint32_t tmem_cols = p.BN < 32 ? 32 : p.BN;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA);
+        if (p.C2) prefetch_tmap(&tmA2);
+        prefetch_tmap(&tmB);
+    }
+    if (warp == 1) {
+        tmem_alloc(&tmem_base_smem, tmem_cols);
+        tmem_relinquish();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_acc = tmem_base_smem;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const int ph = p.KH / 2, pw = p.KW / 2;
+            int it = 0;
+            for (int tap = 0; tap < p.KH * p.KW; tap++) {
+                const int r = tap / p.KW, s = tap % p.KW;
+                for (int sl = 0; sl < slabs; sl++, it++) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t *sa = smem + stage * stage_bytes, *sb = sa + a_bytes;
+                    mbar_expect_tx(&full_bar[stage], a_bytes + b_bytes_raw);
+                    const int c = sl * p.KC;
+                    if (c < p.C1) tma_load_4d(sa, &tmA, &full_bar[stage], c, x0 + s - pw, y0 + r - ph, n);
+                    else tma_load_4d(sa, &tmA2, &full_bar[stage], c - p.C1, x0 + s - pw, y0 + r - ph, n);
+                    tma_load_2d(sb, &tmB, &full_bar[stage], tap * Ctot + c, n0);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t swz = p.KC == 64 ? 2u : (p.KC == 32 ? 4u : 6u);   // SmemDescriptor layout_type
+            const uint32_t sbo = 8u * p.KC * 2u;                             // bytes between 8-row groups
+            const uint32_t idesc = make_idesc_f16(kBM, p.BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int it = 0; it < k_iters; it++) {
+                mbar_wait(&full_bar[stage], phase);
+                tcgen05_fence_after();
+                const uint32_t sa = smem_u32(smem + stage * stage_bytes), sb = sa + a_bytes;
+                const uint64_t da = make_smem_desc(sa, swz, sbo), db = make_smem_desc(sb, swz, sbo);
+                const int ksteps = p.KC / 16;
+                for (int j = 0; j < ksteps; j++) {
+                    // advance both descriptors by 16 elements (32 bytes) along K inside the swizzle atom
+                    umma_f16(tmem_acc, da + (uint64_t)(j * 2), db + (uint64_t)(j * 2), idesc, (it | j) != 0);
+                }
+                umma_commit(&empty_bar[stage]);          // frees the smem slot once these MMAs retire
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(&tmem_full_bar);                 // accumulator complete
+        }
+    } else {
+        // ===== epilogue: 4 warps, TMEM lane group = warp % 4 =====
+        const int q = warp & 3;
+        const int m = q * 32 + lane;                     // pixel row of the tile == TMEM lane
+        const int py = y0 + m / kTileW, px = x0 + m % kTileW;
+        const bool inb = py < p.H && px < p.W;
+        mbar_wait(&tmem_full_bar, 0);
+        tcgen05_fence_after();
+        const size_t pix = ((size_t)n * p.H + py) * p.W + px;
+        for (int c0 = 0; c0 < p.BN; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            tmem_ld_wait();
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                float x = __uint_as_float(v[j]) + __ldg(p.bias + n0 + c0 + j);
+                f[j] = x > 0.f ? x : x * p.slope;
+            }
+            if (inb) {
+                if (p.out_mode == 0) {
+                    __half2 h[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) h[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+                    uint4 *dst = (uint4 *)((__half *)p.out + pix * p.out_cstride + n0 + c0);
+                    dst[0] = *(uint4 *)&h[0];
+                    dst[1] = *(uint4 *)&h[4];
+                } else if (c0 == 0 && n0 == 0) {
+                    float4 *dst = (float4 *)((float *)p.out + pix * 8);
+                    dst[0] = make_float4(f[0], f[1], f[2], f[3]);
+                    dst[1] = make_float4(f[4], f[5], f[6], f[7]);
+                }
+            }
+        }
+        tcgen05_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_acc, tmem_cols);
+    }
+}
+
+}  // namespace
+
+// =============================================================================================
+// host side
+// =============================================================================================
+static thread_local char g_conv_err[512];
+extern int v2e_set_error(int code, const char *fmt, const char *detail);
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+static CUtensorMapSwizzle swizzle_for(int kc) {
+    return kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+// NHWC fp16 activation [N,H,W,C]: box = KC channels x 16 columns x 8 rows x 1 image
+int v2e_make_act_tmap(CUtensorMap *tm, const void *ptr, int N, int H, int W, int C, int KC) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return v2e_set_error(V2E_E_CUDA, "cuTensorMapEncodeTiled unavailable%s", "");
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)kTileW, (cuuint32_t)kTileH, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void *)ptr, dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(KC), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        snprintf(g_conv_err, sizeof(g_conv_err), "activation map N=%d H=%d W=%d C=%d KC=%d CUresult=%d", N, H, W, C, KC, (int)r);
+        return v2e_set_error(V2E_E_CUDA, "cuTensorMapEncodeTiled failed: %s", g_conv_err);
+    }
+    return V2E_OK;
+}
+
+// weights [Cout_pad][Ktot] fp16: box = KC x BN
+int v2e_make_wgt_tmap(CUtensorMap *tm, const void *ptr, int Cout_pad, int Ktot, int KC, int BN) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return v2e_set_error(V2E_E_CUDA, "cuTensorMapEncodeTiled unavailable%s", "");
+    cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout_pad};
+    cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
+    cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)BN};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *)ptr, dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(KC), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        snprintf(g_conv_err, sizeof(g_conv_err), "weight map Cout=%d K=%d KC=%d BN=%d CUresult=%d", Cout_pad, Ktot, KC, BN, (int)r);
+        return v2e_set_error(V2E_E_CUDA, "cuTensorMapEncodeTiled failed: %s", g_conv_err);
+    }
+    return V2E_OK;
+}
+
+int v2e_conv_pick_kc(int C1, int C2) {
+    int g = C2 ? (C1 < C2 ? C1 : C2) : C1;
+    return g % 64 == 0 ? 64 : (g % 32 == 0 ? 32 : 16);
+}
+int v2e_conv_pick_bn(int Cout_pad) { return Cout_pad >= 128 ? 128 : Cout_pad; }
+
+struct V2eConvLaunch {
+    CUtensorMap tmA, tmA2, tmB;
+    ConvParams p;
+    dim3 grid;
+    size_t smem;
+};
+
+int v2e_conv_prepare(V2eConvLaunch *L, const void *x1, int C1, const void *x2, int C2, const void *wgt,
+                     const float *bias, int Cout_pad, int KH, int KW, int N, int H, int W, void *out,
+                     int out_cstride, int out_mode, int co_real, float slope) {
+    if (C1 % 16 || C2 % 16 || Cout_pad % 16 || (Cout_pad > 128 && Cout_pad % 128))
+        return v2e_set_error(V2E_E_INVALID, "conv: channel counts must be padded to 16 (Cout to 16/32/64/128k)%s", "");
+    memset(L, 0, sizeof(*L));
+    ConvParams &p = L->p;
+    p.N = N; p.H = H; p.W = W; p.C1 = C1; p.C2 = C2; p.KH = KH; p.KW = KW;
+    p.KC = v2e_conv_pick_kc(C1, C2);
+    p.BN = v2e_conv_pick_bn(Cout_pad);
+    p.tiles_x = (W + kTileW - 1) / kTileW;
+    p.tiles_y = (H + kTileH - 1) / kTileH;
+    p.out_cstride = out_cstride; p.out_mode = out_mode; p.co_real = co_real; p.slope = slope;
+    p.bias = bias; p.out = out;
+    int rc;
+    if ((rc = v2e_make_act_tmap(&L->tmA, x1, N, H, W, C1, p.KC))) return rc;
+    if (C2) { if ((rc = v2e_make_act_tmap(&L->tmA2, x2, N, H, W, C2, p.KC))) return rc; }
+    else L->tmA2 = L->tmA;
+    if ((rc = v2e_make_wgt_tmap(&L->tmB, wgt, Cout_pad, KH * KW * (C1 + C2), p.KC, p.BN))) return rc;
+    L->grid = dim3((unsigned)(p.tiles_x * p.tiles_y * N), (unsigned)(Cout_pad / p.BN), 1);
+    size_t stage = (size_t)kBM * p.KC * 2 + (((size_t)p.BN * p.KC * 2 + 1023) & ~(size_t)1023);
+    L->smem = stage * kStages + 1024;
+    return V2E_OK;
+}
+
+int v2e_conv_launch(const V2eConvLaunch *L, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set = true;
+    }
+    conv_tc_kernel<<<L->grid, kConvThreads, L->smem, st>>>(L->tmA, L->tmA2, L->tmB, L->p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return v2e_set_error(V2E_E_CUDA, "conv_tc_kernel launch: %s", cudaGetErrorString(e));
+    return V2E_OK;
+}
+
+size_t v2e_conv_launch_size(void) { return sizeof(V2eConvLaunch); }
+
+// ---- standalone C-ABI entry (tests, and integrators who bring their own network driver) -------------
+extern "C" int v2e_conv2d_lrelu_sm100(const void *x1_dev, int C1, const void *x2_dev, int C2,
+                                      const void *wgt_dev, const float *bias_dev, int Cout_pad, int KH, int KW,
+                                      int N, int H, int W, void *out_dev, int out_cstride, int out_mode,
+                                      int co_real, float slope, void *stream) {
+    V2eConvLaunch L;
+    int rc = v2e_conv_prepare(&L, x1_dev, C1, x2_dev, C2, wgt_dev, bias_dev, Cout_pad, KH, KW, N, H, W, out_dev,
+                              out_cstride, out_mode, co_real, slope);
+    if (rc) return rc;
+    return v2e_conv_launch(&L, (cudaStream_t)stream);
+}

@@ -797,6 +797,7 @@ static int fail(int code, const char *fmt, const char *detail = "") {
         if (e_ != cudaSuccess) return fail(V2E_E_CUDA, #call ": %s", cudaGetErrorString(e_)); \
     } while (0)
 
+int v2e_set_error(int code, const char *fmt, const char *detail) { return fail(code, fmt, detail); }
 extern "C" const char *v2e_last_error(void) { return g_err; }
 extern "C" int v2e_version(void) { return 100; }
 

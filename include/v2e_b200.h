@@ -180,6 +180,49 @@ int v2e_conv2d_lrelu_sm100(const void *x1_dev, int C1, const void *x2_dev, int C
                            int N, int H, int W, void *out_dev, int out_cstride, int out_mode,
                            int co_real, float slope, void *stream);
 
+/* The 23 convolutions of one UNet (model.py:184-196) in forward order: conv1, conv2,
+ * down1..down5 {conv1, conv2}, up1..up5 {conv1, conv2}, conv3. Host pointers to the float32
+ * tensors of the reference's state_dict ([Cout][Cin][KH][KW] weights, [Cout] biases), i.e. what
+ * torch.load(ckpt)['state_dictFC' / 'state_dictAT'] holds (slomo.py:225-227). */
+typedef struct V2eUNetWeights {
+    const float *w[23];
+    const float *b[23];
+} V2eUNetWeights;
+
+typedef struct V2eSlomo V2eSlomo;
+
+/* H, W: network resolution (multiples of 32, dataloader.py:122-123). Packs the weights to fp16
+ * on the device and allocates activations for max_batch frame pairs. Synchronous. */
+int v2e_slomo_create(int H, int W, int max_batch, const V2eUNetWeights *flow,
+                     const V2eUNetWeights *interp, V2eSlomo **out);
+int v2e_slomo_destroy(V2eSlomo *h);
+/* frames_u8_dev: [B+1][H][W] consecutive source frames at network resolution. Normalises them
+ * (slomo.py:148-162, CUDA branch: x/255 - 0.428) and runs the flow UNet for the B pairs
+ * (slomo.py:338-345). Enqueue only. */
+int v2e_slomo_set_pairs(V2eSlomo *h, const uint8_t *frames_u8_dev, int B, void *stream);
+/* max over the batch of the flow magnitudes (slomo.py:358-366). Synchronises. */
+int v2e_slomo_max_flow(V2eSlomo *h, float *max_speed_host, void *stream);
+/* One intermediate frame per pair at fraction t in (0,1) (slomo.py:404-437).
+ * out_u8_dev: [B][H][W] = uint8((Ft_p + 0.428) * 255) as torchvision's ToPILImage computes it;
+ * out_f32_dev: optional [B][H][W] float32 Ft_p before quantisation (parity probe), may be NULL. */
+int v2e_slomo_interp(V2eSlomo *h, double t, uint8_t *out_u8_dev, float *out_f32_dev, void *stream);
+/* Measurement hooks: bracket every convolution launch with CUDA events; profile_read synchronises
+ * and returns the summed device time, the number of launches and their algorithmic FLOPs
+ * (2 x MACs over the unpadded channel counts) since the last read. */
+int v2e_slomo_profile(V2eSlomo *h, int enable);
+int v2e_slomo_profile_read(V2eSlomo *h, float *conv_ms, int *conv_launches, double *conv_flops, void *stream);
+/* device pointers of the last flow / interpolation network outputs, fp32 [B][H][W][8] */
+const float *v2e_slomo_flow_ptr(V2eSlomo *h);
+const float *v2e_slomo_intrp_ptr(V2eSlomo *h);
+
+/* Pillow-exact 8-bit resampling of 'L' images (Pillow Resample.c; dataloader.py:142 uses LANCZOS,
+ * slomo.py:438 BILINEAR). filter: 0 = BILINEAR, 1 = LANCZOS. Images are [n][h][w] uint8. */
+typedef struct V2eResizer V2eResizer;
+int v2e_resize_create(int src_w, int src_h, int dst_w, int dst_h, int filter, int max_images,
+                      V2eResizer **out);
+int v2e_resize_destroy(V2eResizer *r);
+int v2e_resize_run(V2eResizer *r, const uint8_t *src_dev, uint8_t *dst_dev, int n_images, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,195 @@
+"""GPU parity tests of the SuperSloMo path: tcgen05 conv kernel, UNet, warps/blend, Pillow-exact
+resizes and the SuperSloMo drop-in, against the float32 torch reference (oracle/slomo_ref.py) and
+the fixtures produced by the unmodified reference classes.
+
+Floating-point path. The CUDA kernels use fp16 operands with fp32 accumulation (same 10-bit
+mantissa as the TF32 tensor-core math the reference's cuDNN convolutions use by default on
+Ampere+); tolerances are stated per test."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import slomo_ref
+from helpers import GOLDEN_DIR
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _lib():
+    from v2e_b200 import _lib as L
+    return L, L.load()
+
+
+def pad16(c):
+    return (c + 15) // 16 * 16
+
+
+def cout_pad(c):
+    p = pad16(c)
+    return 16 if p <= 16 else 32 if p <= 32 else 64 if p <= 64 else (p + 127) // 128 * 128
+
+
+def to_nhwc16(x):
+    N, C, H, W = x.shape
+    out = torch.zeros((N, H, W, pad16(C)), dtype=torch.float16, device=x.device)
+    out[..., :C] = x.permute(0, 2, 3, 1).half()
+    return out.contiguous()
+
+
+def pack_w(w, C1, C2):
+    Cout, Cin, KH, KW = w.shape
+    C1p, C2p = pad16(C1), (pad16(C2) if C2 else 0)
+    Cp = cout_pad(Cout)
+    out = torch.zeros((Cp, KH * KW, C1p + C2p), dtype=torch.float16, device=w.device)
+    wt = w.permute(0, 2, 3, 1).reshape(Cout, KH * KW, Cin).half()
+    out[:Cout, :, :C1] = wt[:, :, :C1]
+    if C2:
+        out[:Cout, :, C1p:C1p + C2] = wt[:, :, C1:]
+    return out.reshape(Cp, -1).contiguous(), Cp
+
+
+CONV_CASES = [
+    # N, H, W, C1, C2, Cout, K, out_mode
+    (1, 8, 16, 64, 0, 64, 3, 0), (1, 8, 16, 64, 0, 64, 1, 0), (2, 17, 23, 64, 0, 32, 3, 0),
+    (1, 32, 32, 32, 0, 32, 7, 0), (1, 32, 48, 32, 0, 64, 5, 0), (1, 16, 32, 2, 0, 32, 7, 0),
+    (1, 16, 32, 12, 0, 32, 7, 0), (1, 8, 10, 512, 0, 512, 3, 0), (1, 16, 20, 512, 512, 512, 3, 0),
+    (1, 64, 80, 32, 32, 32, 3, 0), (1, 32, 40, 64, 64, 64, 3, 0), (1, 32, 32, 32, 0, 5, 3, 1),
+    (1, 32, 32, 32, 0, 4, 3, 1), (2, 64, 96, 256, 0, 128, 3, 0), (1, 5, 7, 128, 0, 256, 3, 0),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_tc_matches_torch(case):
+    """tcgen05 implicit-GEMM conv + bias + LeakyReLU vs torch conv2d on the same fp16-rounded operands
+    (fp32 accumulate on both sides). Tolerance: fp16 output rounding, 2e-3 relative + 2e-3 absolute."""
+    N, H, W, C1, C2, Cout, K, mode = case
+    Lm, L = _lib()
+    g = torch.Generator().manual_seed(hash(case) & 0xFFFF)
+    x1 = torch.randn((N, C1, H, W), generator=g).to(DEV)
+    x2 = torch.randn((N, C2, H, W), generator=g).to(DEV) if C2 else None
+    w = (torch.randn((Cout, C1 + C2, K, K), generator=g) / np.sqrt((C1 + C2) * K * K)).to(DEV)
+    b = (torch.randn((Cout,), generator=g) * 0.1).to(DEV)
+    a1 = to_nhwc16(x1)
+    a2 = to_nhwc16(x2) if C2 else None
+    wp, Cp = pack_w(w, C1, C2)
+    bp = torch.zeros(Cp, device=DEV)
+    bp[:Cout] = b
+    out = torch.full((N, H, W, Cp if mode == 0 else 8), float("nan"),
+                     dtype=torch.float16 if mode == 0 else torch.float32, device=DEV)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    p = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
+    Lm.check(L.v2e_conv2d_lrelu_sm100(p(a1), a1.shape[-1], p(a2), a2.shape[-1] if C2 else 0, p(wp), p(bp), Cp,
+                                      K, K, N, H, W, p(out), Cp, mode, min(Cout, 8), ctypes.c_float(0.1), st))
+    torch.cuda.synchronize()
+    xin = torch.cat([x1, x2], 1) if C2 else x1
+    ref = torch.nn.functional.conv2d(xin.half().float(), w.half().float(), b, padding=K // 2)
+    ref = torch.nn.functional.leaky_relu(ref, 0.1).permute(0, 2, 3, 1)
+    got = out[..., :min(Cout, out.shape[-1])].float()
+    refc = ref[..., :got.shape[-1]]
+    assert torch.isfinite(got).all()
+    assert ((got - refc).abs() <= 2e-3 * refc.abs() + 2e-3).all(), (got - refc).abs().max().item()
+    if mode == 0 and Cp > Cout:   # padded output channels must be exactly lrelu(0) = 0
+        assert (out[..., Cout:] == 0).all()
+
+
+@pytest.mark.parametrize("sizes", [((346, 260), (320, 256), 1), ((320, 256), (346, 260), 0),
+                                   ((1280, 720), (1280, 704), 1), ((1280, 704), (1280, 720), 0),
+                                   ((100, 70), (96, 64), 1), ((96, 64), (100, 70), 0), ((130, 96), (128, 96), 1)])
+def test_resize_is_pillow_exact(sizes):
+    """8-bit LANCZOS / BILINEAR resampling must equal Pillow bit for bit (dataloader.py:142, slomo.py:438)."""
+    from PIL import Image
+    (sw, sh), (dw, dh), filt = sizes
+    Lm, L = _lib()
+    rng = np.random.default_rng(sw * 7 + dh)
+    imgs = rng.integers(0, 256, (3, sh, sw), dtype=np.uint8)
+    imgs[1] = np.kron(rng.integers(0, 256, (sh // 4 + 1, sw // 4 + 1), dtype=np.uint8), np.ones((4, 4), np.uint8))[:sh, :sw]
+    r = ctypes.c_void_p()
+    Lm.check(L.v2e_resize_create(sw, sh, dw, dh, filt, 3, ctypes.byref(r)))
+    src = torch.from_numpy(imgs).to(DEV)
+    dst = torch.zeros((3, dh, dw), dtype=torch.uint8, device=DEV)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    Lm.check(L.v2e_resize_run(r, ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(dst.data_ptr()), 3, st))
+    got = dst.cpu().numpy()
+    L.v2e_resize_destroy(r)
+    for i in range(3):
+        want = np.asarray(Image.fromarray(imgs[i]).resize((dw, dh), Image.LANCZOS if filt else Image.BILINEAR))
+        assert np.array_equal(got[i], want), "image %d: %d pixels differ" % (i, int((got[i] != want).sum()))
+
+
+def _weights(seed):
+    return (slomo_ref.make_test_weights(100 + seed, 2, 4, head_gain=25.0),
+            slomo_ref.make_test_weights(200 + seed, 12, 5, head_gain=0.3))
+
+
+def test_unets_and_blend_match_float32_reference():
+    """Flow UNet, interpolation UNet and the blended frame vs the float32 torch reference on the same
+    inputs. Tolerances (fp16 operands through 23 layers): network outputs within 2% of their RMS
+    (max error) ; blended frame Ft_p within 0.01 (2.5 DN) max, 0.001 (0.25 DN) mean."""
+    from v2e_b200.slomo import SloMoEngine
+    sd_fc, sd_at = _weights(3)
+    H, W, B = 96, 128, 2
+    frames = np.stack([np.asarray(f) for f in __import__("make_golden_slomo_frames").smooth_frames(B + 1, H, W, 5)])
+    eng = SloMoEngine(sd_fc, sd_at, (W, H), B, DEV)
+    fr = torch.from_numpy(frames).to(DEV)
+    eng.set_pairs(fr)
+    flow = eng.flow_out().clone().cpu()[..., :4].permute(0, 3, 1, 2)
+    I, _ = slomo_ref.load_pair_tensors(frames, (W, H))
+    ref_flow, ref_outs = slomo_ref.interp_batch(sd_fc, sd_at, I[:B], I[1:B + 1], 2)
+    rms = ref_flow.pow(2).mean().sqrt().item()
+    assert (flow - ref_flow).abs().max().item() < 0.02 * rms + 0.02, ((flow - ref_flow).abs().max().item(), rms)
+    out = torch.empty((B, H, W), dtype=torch.uint8, device=DEV)
+    ft = torch.empty((B, H, W), dtype=torch.float32, device=DEV)
+    for k in range(2):
+        eng.interp((k + 0.5) / 2, out, ft)
+        ref_intrp, ref_ft = ref_outs[k]
+        d = (ft.cpu() - ref_ft[:, 0]).abs()
+        assert d.max().item() < 0.01 and d.mean().item() < 0.001, (d.max().item(), d.mean().item())
+        q = out.cpu().numpy().astype(np.int32) - slomo_ref.to_u8(ref_ft)[:, 0].numpy().astype(np.int32)
+        assert np.abs(q).max() <= 3 and np.abs(q).mean() < 0.3
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ["slomo_64x96_u2_b1", "slomo_70x100_u3_b2", "slomo_96x130_auto"])
+def test_superslomo_dropin_matches_reference_golden(name, tmp_path):
+    """SuperSloMo.interpolate (folder of .npy in, .png out) against the frames the unmodified reference
+    wrote for the same inputs and weights. Same frame count, same interpTimes (exact), uint8 frames
+    within 3 DN max / 0.3 DN mean (fp16 tensor-core convolutions vs the reference's fp32 CPU convs)."""
+    import cv2
+    from v2e_b200.slomo import SuperSloMo
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    seed = int(z["seed"])
+    sd_fc, sd_at = _weights(seed)
+    import hashlib
+    dig = "".join(hashlib.sha1(b"".join(sd[k].numpy().tobytes() for k in sorted(sd))).hexdigest() for sd in (sd_fc, sd_at))
+    if dig != str(z["weights_sha1"]):
+        pytest.skip("torch.randn on this host does not reproduce the fixture's weights")
+    src, dst = tmp_path / "src", tmp_path / "dst"
+    src.mkdir(); dst.mkdir()
+    for i, f in enumerate(z["frames"]):
+        np.save(str(src / ("%08d.npy" % i)), f)
+    s = SuperSloMo(model=None, auto_upsample=bool(z["auto"]), upsampling_factor=int(z["U"]),
+                   batch_size=int(z["batch_size"]), state_dicts={"state_dictFC": sd_fc, "state_dictAT": sd_at})
+    H, W = z["frames"].shape[1:]
+    times, avg = s.interpolate(str(src), str(dst), (W, H))
+    n = len(os.listdir(str(dst)))
+    got = np.stack([cv2.imread(str(dst / ("%d.png" % i)), cv2.IMREAD_GRAYSCALE) for i in range(n)])
+    assert got.shape == z["out"].shape
+    assert np.array_equal(times, z["times"]) and avg == float(z["avg"])
+    d = np.abs(got.astype(np.int32) - z["out"].astype(np.int32))
+    assert d.max() <= 3 and d.mean() < 0.3, (d.max(), d.mean())
+    s.cleanup()
+
+
+def test_superslomo_errors():
+    from v2e_b200.slomo import SuperSloMo
+    with pytest.raises(ValueError):
+        SuperSloMo(model=None, auto_upsample=False, upsampling_factor=1)
+    s = SuperSloMo(model="/nonexistent.ckpt", auto_upsample=False, upsampling_factor=2)
+    with pytest.raises(FileNotFoundError):
+        s.interpolate_frames(np.zeros((3, 64, 64), np.uint8))
+    with pytest.raises(ValueError):
+        s.interpolate("/tmp", None, (64, 64))

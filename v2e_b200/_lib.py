@@ -22,6 +22,10 @@ class V2eEmuCfg(ctypes.Structure):
     ]
 
 
+class V2eUNetWeights(ctypes.Structure):
+    _fields_ = [("w", ctypes.c_void_p * 23), ("b", ctypes.c_void_p * 23)]
+
+
 class V2eFrameInfo(ctypes.Structure):
     _fields_ = [
         ("max_n", ctypes.c_int32), ("filter_active", ctypes.c_int32),
@@ -55,6 +59,19 @@ _SIGS = {
     "v2e_emu_phase_emit": (_i, [_vp, _d, _d, _vp, _u64, _vp]),
     "v2e_conv2d_lrelu_sm100": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i,
                                     ctypes.c_float, _vp]),
+    "v2e_slomo_create": (_i, [_i, _i, _i, _vp, _vp, ctypes.POINTER(_vp)]),
+    "v2e_slomo_destroy": (_i, [_vp]),
+    "v2e_slomo_set_pairs": (_i, [_vp, _vp, _i, _vp]),
+    "v2e_slomo_max_flow": (_i, [_vp, ctypes.POINTER(ctypes.c_float), _vp]),
+    "v2e_slomo_interp": (_i, [_vp, _d, _vp, _vp, _vp]),
+    "v2e_slomo_profile": (_i, [_vp, _i]),
+    "v2e_slomo_profile_read": (_i, [_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_i),
+                                    ctypes.POINTER(ctypes.c_double), _vp]),
+    "v2e_slomo_flow_ptr": (_vp, [_vp]),
+    "v2e_slomo_intrp_ptr": (_vp, [_vp]),
+    "v2e_resize_create": (_i, [_i, _i, _i, _i, _i, _i, ctypes.POINTER(_vp)]),
+    "v2e_resize_destroy": (_i, [_vp]),
+    "v2e_resize_run": (_i, [_vp, _vp, _vp, _i, _vp]),
     "v2e_emu_profile": (_i, [_vp, _i]),
     "v2e_emu_profile_read": (_i, [_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_i), _vp]),
     "v2e_emu_get_state": (_i, [_vp, _i, _vp, ctypes.POINTER(_i)]),

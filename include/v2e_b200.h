@@ -180,6 +180,17 @@ int v2e_conv2d_lrelu_sm100(const void *x1_dev, int C1, const void *x2_dev, int C
                            int N, int H, int W, void *out_dev, int out_cstride, int out_mode,
                            int co_real, float slope, void *stream);
 
+/* Same operation through the halo-resident row kernel (wide layers: W >= 256, Cout_pad <= 128): one CTA
+ * owns a 1 x 128-pixel row segment, loads each KC-channel halo slab once and addresses all filter taps
+ * as descriptor offsets. wgt_row_dev: fp16 [slabs][KH*KW][Cout_pad][KC] with slabs = (C1+C2)/KC;
+ * KC from v2e_conv_row_pick_kc (0 = layer does not qualify). bo_mode: descriptor base-offset policy
+ * for the shifted windows (1 = (start>>7)&7). */
+int v2e_conv2d_lrelu_sm100_row(const void *x1_dev, int C1, const void *x2_dev, int C2,
+                               const void *wgt_row_dev, const float *bias_dev, int Cout_pad, int KH,
+                               int KW, int KC, int N, int H, int W, void *out_dev, int out_cstride,
+                               int out_mode, int co_real, float slope, int bo_mode, void *stream);
+int v2e_conv_row_pick_kc(int C1, int C2, int Cout_pad, int KH, int KW, int W);
+
 /* The 23 convolutions of one UNet (model.py:184-196) in forward order: conv1, conv2,
  * down1..down5 {conv1, conv2}, up1..up5 {conv1, conv2}, conv3. Host pointers to the float32
  * tensors of the reference's state_dict ([Cout][Cin][KH][KW] weights, [Cout] biases), i.e. what
@@ -206,6 +217,8 @@ int v2e_slomo_max_flow(V2eSlomo *h, float *max_speed_host, void *stream);
  * out_u8_dev: [B][H][W] = uint8((Ft_p + 0.428) * 255) as torchvision's ToPILImage computes it;
  * out_f32_dev: optional [B][H][W] float32 Ft_p before quantisation (parity probe), may be NULL. */
 int v2e_slomo_interp(V2eSlomo *h, double t, uint8_t *out_u8_dev, float *out_f32_dev, void *stream);
+/* option 0: force the per-tap convolution kernel for every layer (A/B measurement), value 0/1 */
+int v2e_slomo_set_option(V2eSlomo *h, int option, int value);
 /* Measurement hooks: bracket every convolution launch with CUDA events; profile_read synchronises
  * and returns the summed device time, the number of launches and their algorithmic FLOPs
  * (2 x MACs over the unpadded channel counts) since the last read. */

@@ -484,29 +484,46 @@ emu_update_kernel(EmuDev d, FrameParams p, const void *frame, const float *leak_
         if (d.leak_on) st4((S *)d.base, i0, base);
         *(short4 *)(d.rec + i0) = make_short4(recs[0], recs[1], recs[2], recs[3]);
     }
-    // per-(iteration,polarity) histogram, one shared-memory atomic per warp and segment
+    // per-(iteration,polarity) histogram. Iterations 0 and 1 (almost all events) are counted per thread
+    // and reduced with one REDUX per segment; a pixel with >= 3 events (rare) takes the ballot loop.
     {
         const int lane = tid & 31;
-        const int any_sig = __any_sync(0xffffffffu, (mags[0] | mags[1] | mags[2] | mags[3]) != 0);
-        const int any_shot = __any_sync(0xffffffffu, (flg[0] | flg[1] | flg[2] | flg[3]) != 0);
+        int c0on = 0, c0off = 0, c1on = 0, c1off = 0, son = 0, soff = 0, deep = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            if (any_sig) {
+            c0on += (mags[k] > 0) & !pols[k];
+            c0off += (mags[k] > 0) & pols[k];
+            c1on += (mags[k] > 1) & !pols[k];
+            c1off += (mags[k] > 1) & pols[k];
+            son += flg[k] & 1;
+            soff += (flg[k] >> 1) & 1;
+            deep |= mags[k] > 2;
+        }
+        const int packed = c0on | (c0off << 4) | (c1on << 8) | (c1off << 12) | (son << 16) | (soff << 20);
+        if (__any_sync(0xffffffffu, packed != 0)) {
+            // 4-bit fields, <= 4 per lane: sums over 32 lanes (<= 128) need 8 bits -> two REDUX of 3 fields
+            const int lo = __reduce_add_sync(0xffffffffu, (c0on) | (c0off << 10) | (c1on << 20));
+            const int hi = __reduce_add_sync(0xffffffffu, (c1off) | (son << 10) | (soff << 20));
+            if (lane == 0) {
+                if (lo & 1023) atomicAdd(&s_hist[0], lo & 1023);
+                if ((lo >> 10) & 1023) atomicAdd(&s_hist[1], (lo >> 10) & 1023);
+                if ((lo >> 20) & 1023) atomicAdd(&s_hist[2], (lo >> 20) & 1023);
+                if (hi & 1023) atomicAdd(&s_hist[3], hi & 1023);
+                if ((hi >> 10) & 1023) atomicAdd(&s_hist[kSegSmem], (hi >> 10) & 1023);
+                if ((hi >> 20) & 1023) atomicAdd(&s_hist[kSegSmem + 1], (hi >> 20) & 1023);
+            }
+        }
+        if (__any_sync(0xffffffffu, deep)) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
                 const int wmax = __reduce_max_sync(0xffffffffu, mags[k]);
-                for (int it = 0; it < wmax; it++) {
+                for (int it = 2; it < wmax; it++) {
                     unsigned on = __ballot_sync(0xffffffffu, mags[k] > it && !pols[k]);
                     unsigned off = __ballot_sync(0xffffffffu, mags[k] > it && pols[k]);
                     if (lane == 0) {
                         if (on) { if (2 * it < kSegSmem) atomicAdd(&s_hist[2 * it], __popc(on)); else atomicAdd(&hist[2 * it], __popc(on)); }
                         if (off) { if (2 * it + 1 < kSegSmem) atomicAdd(&s_hist[2 * it + 1], __popc(off)); else atomicAdd(&hist[2 * it + 1], __popc(off)); }
                     }
-                }
-            }
-            if (any_shot) {
-                unsigned son = __ballot_sync(0xffffffffu, flg[k] & 1), soff = __ballot_sync(0xffffffffu, flg[k] & 2);
-                if (lane == 0) {
-                    if (son) atomicAdd(&s_hist[kSegSmem], __popc(son));
-                    if (soff) atomicAdd(&s_hist[kSegSmem + 1], __popc(soff));
                 }
             }
         }

@@ -30,6 +30,13 @@ int v2e_conv_prepare(V2eConvLaunch *L, const void *x1, int C1, const void *x2, i
                      int out_cstride, int out_mode, int co_real, float slope);
 int v2e_conv_launch(const V2eConvLaunch *L, cudaStream_t st);
 size_t v2e_conv_launch_size(void);
+struct V2eRowLaunch;
+int v2e_row_pick_kc(int C1, int C2, int Cout_pad, int KH, int KW, int W);
+size_t v2e_row_launch_size(void);
+int v2e_row_prepare(V2eRowLaunch *L, const void *x1, int C1, const void *x2, int C2, const void *wgt_row,
+                    const float *bias, int Cout_pad, int KH, int KW, int KC, int N, int H, int W, void *out,
+                    int out_cstride, int out_mode, int co_real, float slope, int n_sms, int bo_mode);
+int v2e_row_launch(const V2eRowLaunch *L, cudaStream_t st);
 int v2e_set_error(int code, const char *fmt, const char *detail);
 
 #define CU(call)                                                                              \
@@ -295,6 +302,8 @@ struct UNet {
     int in_ch, out_ch;
     LayerSpec L[23];
     __half *w[23];
+    __half *w_row[23];           // [slabs][taps][Cout_pad][KC] for layers that run on the row kernel
+    int row_kc[23];              // 0: per-tap kernel
     float *b[23];
     int cout_pad[23], c1p[23], c2p[23];
 };
@@ -329,7 +338,8 @@ struct V2eSlomo {
     float *img;                   // [B+1,H,W] fp32
     float *maxspeed;              // device scalar
     int curB;
-    std::vector<char> launch_mem;
+    std::vector<char> launch_mem, row_mem;
+    int n_sms, force_tap_kernel;
     // measurement hooks: CUDA events around every conv launch
     int profile;
     std::vector<cudaEvent_t> ev;
@@ -337,7 +347,14 @@ struct V2eSlomo {
     double conv_flops;           // algorithmic FLOPs (2*MAC, unpadded channels) of the bracketed launches
 };
 
-static int upload_unet(UNet &u, const V2eUNetWeights *wts) {
+// spatial level (power of two divisor) at which layer i runs
+static int layer_level(int i) {
+    if (i < 2 || i == 22) return 0;
+    if (i < 12) return (i - 2) / 2 + 1;            // down1..down5 -> 1..5
+    return 4 - (i - 12) / 2;                       // up1..up5 -> 4..0
+}
+
+static int upload_unet(UNet &u, const V2eUNetWeights *wts, int W) {
     for (int i = 0; i < 23; i++) {
         const LayerSpec &l = u.L[i];
         const int c1p = pad16(l.cin1), c2p = l.cin2 ? pad16(l.cin2) : 0, cp = cout_padded(l.cout), taps = l.k * l.k;
@@ -354,6 +371,20 @@ static int upload_unet(UNet &u, const V2eUNetWeights *wts) {
             }
         std::vector<float> bias(cp, 0.f);
         for (int o = 0; o < l.cout; o++) bias[o] = wts->b[i][o];
+        u.w_row[i] = nullptr;
+        u.row_kc[i] = v2e_row_pick_kc(c1p, c2p, cp, l.k, l.k, W >> layer_level(i));
+        if (u.row_kc[i]) {
+            const int kc = u.row_kc[i], slabs = (c1p + c2p) / kc;
+            std::vector<__half> rowp((size_t)slabs * taps * cp * kc);
+            for (int sl = 0; sl < slabs; sl++)
+                for (int t = 0; t < taps; t++)
+                    for (int o = 0; o < cp; o++)
+                        for (int c = 0; c < kc; c++)
+                            rowp[(((size_t)sl * taps + t) * cp + o) * kc + c] =
+                                packed[(size_t)o * ktot + (size_t)t * (c1p + c2p) + sl * kc + c];
+            CU(cudaMalloc((void **)&u.w_row[i], rowp.size() * sizeof(__half)));
+            CU(cudaMemcpy(u.w_row[i], rowp.data(), rowp.size() * sizeof(__half), cudaMemcpyHostToDevice));
+        }
         CU(cudaMalloc((void **)&u.w[i], packed.size() * sizeof(__half)));
         CU(cudaMalloc((void **)&u.b[i], bias.size() * sizeof(float)));
         CU(cudaMemcpy(u.w[i], packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice));
@@ -373,7 +404,7 @@ extern "C" int v2e_slomo_create(int H, int W, int max_batch, const V2eUNetWeight
     unet_spec(h->flow, 2, 4);
     unet_spec(h->interp, 12, 5);
     int rc;
-    if ((rc = upload_unet(h->flow, flow)) || (rc = upload_unet(h->interp, interp))) { delete h; return rc; }
+    if ((rc = upload_unet(h->flow, flow, W)) || (rc = upload_unet(h->interp, interp, W))) { delete h; return rc; }
     const size_t B = max_batch, HW = (size_t)H * W;
     auto alloc16 = [&](__half **p, size_t elems) { return cudaMalloc((void **)p, elems * sizeof(__half)); };
     const int ch[6] = {32, 64, 128, 256, 512, 512};
@@ -398,6 +429,9 @@ extern "C" int v2e_slomo_create(int H, int W, int max_batch, const V2eUNetWeight
     CU(cudaMalloc((void **)&h->img, (B + 1) * HW * sizeof(float)));
     CU(cudaMalloc((void **)&h->maxspeed, sizeof(float)));
     h->launch_mem.resize(v2e_conv_launch_size());
+    h->row_mem.resize(v2e_row_launch_size());
+    { int dev = 0; cudaGetDevice(&dev); h->n_sms = 148; cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, dev); }
+    h->force_tap_kernel = 0;
     *out = h;
     return V2E_OK;
 }
@@ -405,7 +439,7 @@ extern "C" int v2e_slomo_create(int H, int W, int max_batch, const V2eUNetWeight
 extern "C" int v2e_slomo_destroy(V2eSlomo *h) {
     if (!h) return V2E_OK;
     for (UNet *u : {&h->flow, &h->interp})
-        for (int i = 0; i < 23; i++) { if (u->w[i]) cudaFree(u->w[i]); if (u->b[i]) cudaFree(u->b[i]); }
+        for (int i = 0; i < 23; i++) { if (u->w[i]) cudaFree(u->w[i]); if (u->b[i]) cudaFree(u->b[i]); if (u->w_row[i]) cudaFree(u->w_row[i]); }
     void *ptrs[] = {h->in16, h->x0, h->s1, h->flow_out, h->intrp_out, h->img, h->maxspeed};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int l = 0; l < 5; l++) {
@@ -419,22 +453,33 @@ extern "C" int v2e_slomo_destroy(V2eSlomo *h) {
 
 static int conv(V2eSlomo *h, const UNet &u, int li, const __half *x1, const __half *x2, int B, int H, int W, void *out,
                 int out_mode, cudaStream_t st) {
+    int rc;
+    const bool row = u.row_kc[li] != 0 && !h->force_tap_kernel;
     V2eConvLaunch *L = (V2eConvLaunch *)h->launch_mem.data();
-    int rc = v2e_conv_prepare(L, x1, u.c1p[li], x2, x2 ? u.c2p[li] : 0, u.w[li], u.b[li], u.cout_pad[li], u.L[li].k,
+    V2eRowLaunch *R = (V2eRowLaunch *)h->row_mem.data();
+    if (row)
+        rc = v2e_row_prepare(R, x1, u.c1p[li], x2, x2 ? u.c2p[li] : 0, u.w_row[li], u.b[li], u.cout_pad[li], u.L[li].k,
+                             u.L[li].k, u.row_kc[li], B, H, W, out, u.cout_pad[li], out_mode, u.L[li].cout, kSlope,
+                             h->n_sms, 0);
+    else
+        rc = v2e_conv_prepare(L, x1, u.c1p[li], x2, x2 ? u.c2p[li] : 0, u.w[li], u.b[li], u.cout_pad[li], u.L[li].k,
                               u.L[li].k, B, H, W, out, u.cout_pad[li], out_mode, u.L[li].cout, kSlope);
     if (rc) return rc;
-    if (!h->profile) return v2e_conv_launch(L, st);
-    if (h->ev_used + 2 > h->ev.size()) {
-        size_t old = h->ev.size();
-        h->ev.resize(old + 512);
-        for (size_t i = old; i < h->ev.size(); i++) cudaEventCreate(&h->ev[i]);
+    if (h->profile) {
+        if (h->ev_used + 2 > h->ev.size()) {
+            size_t old = h->ev.size();
+            h->ev.resize(old + 512);
+            for (size_t i = old; i < h->ev.size(); i++) cudaEventCreate(&h->ev[i]);
+        }
+        cudaEventRecord(h->ev[h->ev_used], st);
     }
-    cudaEventRecord(h->ev[h->ev_used], st);
-    rc = v2e_conv_launch(L, st);
-    cudaEventRecord(h->ev[h->ev_used + 1], st);
-    h->ev_used += 2;
-    const LayerSpec &l = u.L[li];
-    h->conv_flops += 2.0 * B * H * W * (double)l.cout * (l.cin1 + l.cin2) * l.k * l.k;
+    rc = row ? v2e_row_launch(R, st) : v2e_conv_launch(L, st);
+    if (h->profile) {
+        cudaEventRecord(h->ev[h->ev_used + 1], st);
+        h->ev_used += 2;
+        const LayerSpec &l = u.L[li];
+        h->conv_flops += 2.0 * B * H * W * (double)l.cout * (l.cin1 + l.cin2) * l.k * l.k;
+    }
     return rc;
 }
 
@@ -509,6 +554,12 @@ extern "C" int v2e_slomo_interp(V2eSlomo *h, double t, uint8_t *out_u8_dev, floa
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return v2e_set_error(V2E_E_CUDA, "v2e_slomo_interp: %s", cudaGetErrorString(e));
     return V2E_OK;
+}
+
+extern "C" int v2e_slomo_set_option(V2eSlomo *h, int option, int value) {
+    if (!h) return v2e_set_error(V2E_E_INVALID, "null handle%s", "");
+    if (option == 0) { h->force_tap_kernel = value; return V2E_OK; }
+    return v2e_set_error(V2E_E_INVALID, "unknown option%s", "");
 }
 
 extern "C" int v2e_slomo_profile(V2eSlomo *h, int enable) {

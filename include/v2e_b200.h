@@ -180,16 +180,16 @@ int v2e_conv2d_lrelu_sm100(const void *x1_dev, int C1, const void *x2_dev, int C
                            int N, int H, int W, void *out_dev, int out_cstride, int out_mode,
                            int co_real, float slope, void *stream);
 
-/* Same operation through the halo-resident row kernel (wide layers: W >= 256, Cout_pad <= 128): one CTA
- * owns a 1 x 128-pixel row segment, loads each KC-channel halo slab once and addresses all filter taps
- * as descriptor offsets. wgt_row_dev: fp16 [slabs][KH*KW][Cout_pad][KC] with slabs = (C1+C2)/KC;
- * KC from v2e_conv_row_pick_kc (0 = layer does not qualify). bo_mode: descriptor base-offset policy
- * for the shifted windows (1 = (start>>7)&7). */
-int v2e_conv2d_lrelu_sm100_row(const void *x1_dev, int C1, const void *x2_dev, int C2,
-                               const void *wgt_row_dev, const float *bias_dev, int Cout_pad, int KH,
-                               int KW, int KC, int N, int H, int W, void *out_dev, int out_cstride,
-                               int out_mode, int co_real, float slope, int bo_mode, void *stream);
-int v2e_conv_row_pick_kc(int C1, int C2, int Cout_pad, int KH, int KW, int W);
+/* Same operation through the strip kernel (full-resolution layers: W >= 128, Cout_pad <= 128, the
+ * whole weight tensor resident in shared memory): a CTA walks down a 128-pixel-wide column strip with a
+ * ring of input rows in shared memory; one new input row per output row, filter taps are descriptor
+ * offsets. wgt_row_dev: fp16 [slabs][KH*KW][Cout_pad][KC], slabs = (C1+C2)/KC, KC from
+ * v2e_conv_strip_pick_kc (0 = the layer does not qualify). */
+int v2e_conv2d_lrelu_sm100_strip(const void *x1_dev, int C1, const void *x2_dev, int C2,
+                                 const void *wgt_row_dev, const float *bias_dev, int Cout_pad, int KH,
+                                 int KW, int N, int H, int W, void *out_dev, int out_cstride,
+                                 int out_mode, int co_real, float slope, void *stream);
+int v2e_conv_strip_pick_kc(int C1, int C2, int Cout_pad, int KH, int KW, int W);
 
 /* The 23 convolutions of one UNet (model.py:184-196) in forward order: conv1, conv2,
  * down1..down5 {conv1, conv2}, up1..up5 {conv1, conv2}, conv3. Host pointers to the float32

@@ -30,9 +30,9 @@ for name, c1, c2, co, k, lvl in layers:
     out = torch.empty((B, h, w, 8 if mode else cp), dtype=torch.float32 if mode else torch.float16, device=dev)
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     p = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
-    kc = L.v2e_conv_row_pick_kc(c1p, c2p, cp, k, k, w) if USE_ROW else 0
+    kc = L.v2e_conv_strip_pick_kc(c1p, c2p, cp, k, k, w) if USE_ROW else 0
     if kc:
-        f = lambda: L.v2e_conv2d_lrelu_sm100_row(p(a1), c1p, p(a2), c2p, p(wt), p(bias), cp, k, k, kc, B, h, w, p(out), cp, mode, min(co, 8), ctypes.c_float(0.1), 0, st)
+        f = lambda: L.v2e_conv2d_lrelu_sm100_strip(p(a1), c1p, p(a2), c2p, p(wt), p(bias), cp, k, k, B, h, w, p(out), cp, mode, min(co, 8), ctypes.c_float(0.1), st)
         name = name + '*'
     else:
         f = lambda: L.v2e_conv2d_lrelu_sm100(p(a1), c1p, p(a2), c2p, p(wt), p(bias), cp, k, k, B, h, w, p(out), cp, mode, min(co, 8), ctypes.c_float(0.1), st)

@@ -115,28 +115,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            const uint32_t swz = p.KC == 64 ? 2u : (p.KC == 32 ? 4u : 6u);   // SmemDescriptor layout_type
-            const uint32_t sbo = 8u * p.KC * 2u;                             // bytes between 8-row groups
-            const uint32_t idesc = make_idesc_f16(kBM, p.BN);
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int it = 0; it < k_iters; it++) {
-                mbar_wait(&full_bar[stage], phase);
-                tcgen05_fence_after();
-                const uint32_t sa = smem_u32(smem + stage * stage_bytes), sb = sa + a_bytes;
-                const uint64_t da = make_smem_desc(sa, swz, sbo), db = make_smem_desc(sb, swz, sbo);
-                const int ksteps = p.KC / 16;
-                for (int j = 0; j < ksteps; j++) {
-                    // advance both descriptors by 16 elements (32 bytes) along K inside the swizzle atom
-                    umma_f16(tmem_acc, da + (uint64_t)(j * 2), db + (uint64_t)(j * 2), idesc, (it | j) != 0);
-                }
-                umma_commit(&empty_bar[stage]);          // frees the smem slot once these MMAs retire
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
-            }
-            umma_commit(&tmem_full_bar);                 // accumulator complete
+        // ===== MMA issuer: converged warp, one elected lane issues (see umma_f16_pred) =====
+        const uint32_t leader = elect_one();
+        const uint32_t swz = p.KC == 64 ? 2u : (p.KC == 32 ? 4u : 6u);   // SmemDescriptor layout_type
+        const uint32_t sbo = 8u * p.KC * 2u;                             // bytes between 8-row groups
+        const uint32_t idesc = make_idesc_f16(kBM, p.BN);
+        const uint64_t dhi = make_smem_desc(0, swz, sbo);                // everything but the start address
+        const uint32_t sa0 = smem_u32(smem) >> 4, stage16 = stage_bytes >> 4, a16 = a_bytes >> 4;
+        const int ksteps = p.KC / 16;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int it = 0; it < k_iters; it++) {
+            mbar_wait(&full_bar[stage], phase);
+            tcgen05_fence_after();
+            const uint32_t alo = sa0 + (uint32_t)stage * stage16 + (uint32_t)(dhi & 0xFFFF0000u);
+            const uint32_t blo = alo + a16;
+            for (int j = 0; j < ksteps; j++)
+                umma_f16_pred(tmem_acc, desc_with_lo(dhi, alo + 2u * j), desc_with_lo(dhi, blo + 2u * j), idesc,
+                              (uint32_t)((it | j) != 0), leader);
+            umma_commit_pred(&empty_bar[stage], leader);     // frees the smem slot once these MMAs retire
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
+        umma_commit_pred(&tmem_full_bar, leader);            // accumulator complete
     } else {
         // ===== epilogue: 4 warps, TMEM lane group = warp % 4 =====
         const int q = warp & 3;
@@ -181,53 +181,57 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 
-// ---------------------------------------------------------------------------------------------
-// Row kernel: wide layers (the full- and half-resolution convs that dominate the UNet's time).
-// The per-tap kernel above reloads the shifted window for every filter tap (KH*KW x the data through
-// L2 -> smem); here one CTA owns a 1 x 128-pixel output row segment and, per KC-channel slab, loads the
-// (KH) x (128+KW-1)-pixel halo window ONCE (a single 4-D TMA box, zero-filled outside the image) together
-// with that slab's weights for all taps. Every tap is then a *descriptor offset* into the resident halo:
-// start address + (r*PW + s) rows, same swizzle, so KH*KW*(KC/16) tcgen05.mma are issued per barrier
-// round trip. Persistent CTAs, two smem stages, two TMEM accumulators (epilogue of tile i overlaps the
-// MMAs of tile i+1).
-// ---------------------------------------------------------------------------------------------
 constexpr int kRowTile = 128;
-constexpr int kRowStages = 2;
 
-struct RowParams {
+// ---------------------------------------------------------------------------------------------
+// Strip kernel: the full-resolution layers (N = 32 output channels, 7x7 / 3x3) that dominate the UNet.
+// A CTA walks down a 128-pixel-wide column strip. The layer's whole weight tensor stays resident in
+// shared memory; input rows live in a ring of NSLOT row buffers ([128+KW-1 pixels] x KC channels per
+// slab, TMA-swizzled). Moving one output row down costs ONE new input row from L2 (instead of KH rows
+// with a per-tile halo, or KH*KW windows with per-tap loads); every filter tap (r, s) is a descriptor
+// offset: ring slot of input row y+r-ph, start + s pixels. Two TMEM accumulators overlap the epilogue of
+// row y with the MMAs of row y+1.
+// ---------------------------------------------------------------------------------------------
+struct StripParams {
     int N, H, W;
     int C1, C2;
     int KH, KW;
     int KC, BN;
-    int tiles_x, n_tiles;
-    int a_bytes, b_bytes;          // per stage
-    int b_rows_per_load, b_loads;
+    int tiles_x, seg_h, n_seg, n_items;
+    int nslot;
+    int slab_bytes;                // bytes of one row buffer of one slab (1024-aligned)
+    int w_bytes;                   // all weights: slabs*taps*BN*KC*2
+    int w_rows_per_load, w_loads;
     int out_cstride, out_mode, co_real;
-    int bo_mode;                   // 1: descriptor base_offset = (start >> 7) & 7 for shifted windows
     float slope;
     const float *bias;
     void *out;
 };
+constexpr int kMaxSlot = 12;
 
+template <int KW, int KC>
 __global__ void __launch_bounds__(kConvThreads)
-conv_row_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-                const __grid_constant__ CUtensorMap tmB, const RowParams p) {
+conv_strip_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                  const __grid_constant__ CUtensorMap tmB, const StripParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    const uint32_t stage_bytes = (uint32_t)(p.a_bytes + p.b_bytes);
-    __shared__ __align__(8) uint64_t full_bar[kRowStages], empty_bar[kRowStages], tmem_full_bar[2], tmem_empty_bar[2];
+    __shared__ __align__(8) uint64_t full_bar[kMaxSlot], empty_bar[kMaxSlot], w_bar, tmem_full_bar[2], tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_smem;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Ctot = p.C1 + p.C2;
-    const int slabs = Ctot / p.KC;
-    const int taps = p.KH * p.KW;
-    const int PW = kRowTile + p.KW - 1;
-    const uint32_t acc_cols = p.BN < 32 ? 32 : p.BN;           // columns per accumulator
-    const uint32_t tmem_cols = acc_cols * 2 < 32 ? 32 : acc_cols * 2;
+    const int slabs = Ctot / KC;
+    const int taps = p.KH * KW;
+    constexpr int PW = kRowTile + KW - 1;
+    const int ph = p.KH / 2, pw = KW / 2;
+    const uint32_t row_bytes = (uint32_t)p.slab_bytes * slabs;       // one ring slot (all slabs)
+    uint8_t *ring = smem + ((p.w_bytes + 1023) & ~1023);
+    const uint32_t acc_cols = p.BN < 32 ? 32 : p.BN;
+    const uint32_t tmem_cols = acc_cols * 2;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kRowStages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < p.nslot; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&w_bar, 1);
         for (int s = 0; s < 2; s++) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 4); }
         fence_barrier_init();
     }
@@ -248,106 +252,140 @@ conv_row_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            const int ph = p.KH / 2, pw = p.KW / 2;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-                const int tx = tile % p.tiles_x, row = tile / p.tiles_x;
-                const int y = row % p.H, n = row / p.H;
+            mbar_expect_tx(&w_bar, (uint32_t)p.w_bytes);
+            for (int l = 0; l < p.w_loads; l++)
+                tma_load_2d(smem + (size_t)l * p.w_rows_per_load * KC * 2, &tmB, &w_bar, 0, l * p.w_rows_per_load);
+            uint32_t cnt = 0;                                   // input rows loaded so far (all items)
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                const int tx = item % p.tiles_x, rest = item / p.tiles_x;
+                const int seg = rest % p.n_seg, n = rest / p.n_seg;
+                const int ya = seg * p.seg_h, yb = min(p.H, ya + p.seg_h);
                 const int x0 = tx * kRowTile;
-                for (int sl = 0; sl < slabs; sl++) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t *sa = smem + stage * stage_bytes, *sb = sa + p.a_bytes;
-                    mbar_expect_tx(&full_bar[stage], (uint32_t)(PW * p.KH * p.KC * 2 + taps * p.BN * p.KC * 2));
-                    const int c = sl * p.KC;
-                    if (c < p.C1) tma_load_4d(sa, &tmA, &full_bar[stage], c, x0 - pw, y - ph, n);
-                    else tma_load_4d(sa, &tmA2, &full_bar[stage], c - p.C1, x0 - pw, y - ph, n);
-                    const int row0 = sl * taps * p.BN;
-                    for (int l = 0; l < p.b_loads; l++)
-                        tma_load_2d(sb + (size_t)l * p.b_rows_per_load * p.KC * 2, &tmB, &full_bar[stage], 0,
-                                    row0 + l * p.b_rows_per_load);
-                    if (++stage == kRowStages) { stage = 0; phase ^= 1; }
+                for (int i = ya - ph; i < yb + ph; i++, cnt++) {
+                    const int slot = (int)(cnt % (uint32_t)p.nslot);
+                    const uint32_t phase = (cnt / (uint32_t)p.nslot) & 1u;
+                    mbar_wait(&empty_bar[slot], phase ^ 1);
+                    mbar_expect_tx(&full_bar[slot], (uint32_t)(PW * KC * 2 * slabs));
+                    uint8_t *dst = ring + (size_t)slot * row_bytes;
+                    for (int sl = 0; sl < slabs; sl++) {
+                        const int c = sl * KC;
+                        if (c < p.C1) tma_load_4d(dst + (size_t)sl * p.slab_bytes, &tmA, &full_bar[slot], c, x0 - pw, i, n);
+                        else tma_load_4d(dst + (size_t)sl * p.slab_bytes, &tmA2, &full_bar[slot], c - p.C1, x0 - pw, i, n);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            const uint32_t swz = p.KC == 64 ? 2u : (p.KC == 32 ? 4u : 6u);
-            const uint32_t rowbytes = (uint32_t)p.KC * 2u;
-            const uint32_t sbo = 8u * rowbytes;
-            const uint32_t idesc = make_idesc_f16(kBM, p.BN);
-            const int ksteps = p.KC / 16;
-            int stage = 0;
-            uint32_t phase = 0, acc = 0, acc_phase = 0;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        // ===== MMA issuer: converged warp, one elected lane issues; taps/k-steps fully unrolled =====
+        const uint32_t leader = elect_one();
+        constexpr uint32_t swz = KC == 64 ? 2u : (KC == 32 ? 4u : 6u);
+        constexpr uint32_t rowb = (uint32_t)KC * 2u;
+        constexpr uint32_t sbo = 8u * rowb;
+        constexpr int ksteps = KC / 16;
+        const uint32_t idesc = make_idesc_f16(kBM, p.BN);
+        const uint64_t dhi = make_smem_desc(0, swz, sbo);
+        const uint32_t lo_flags = (uint32_t)(dhi & 0xFFFF0000u);
+        const uint32_t w16 = (smem_u32(smem) >> 4) | lo_flags, ring16 = (smem_u32(ring) >> 4) | lo_flags;
+        const uint32_t row16 = row_bytes >> 4, slab16 = (uint32_t)p.slab_bytes >> 4;
+        const uint32_t tap16 = ((uint32_t)p.BN * rowb) >> 4;              // one tap's weight tile
+        mbar_wait(&w_bar, 0);
+        uint32_t cnt = 0;                                   // index of the first input row of this item
+        uint32_t acc = 0, acc_phase = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            const int rest = item / p.tiles_x;
+            const int seg = rest % p.n_seg;
+            const int ya = seg * p.seg_h, yb = min(p.H, ya + p.seg_h);
+            const int rows_in = (yb - ya) + 2 * ph;
+            int waited = 0;                                 // input rows of this item known to be in smem
+            for (int y = ya; y < yb; y++) {
+                const int need = (y - ya) + p.KH;           // rows 0 .. y-ya+KH-1 of the item
+                for (; waited < need; waited++) {
+                    const uint32_t g = cnt + (uint32_t)waited;
+                    mbar_wait(&full_bar[g % (uint32_t)p.nslot], (g / (uint32_t)p.nslot) & 1u);
+                }
                 mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
                 tcgen05_fence_after();
                 const uint32_t tmem_acc = tmem_base + acc * acc_cols;
-                for (int sl = 0; sl < slabs; sl++) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tcgen05_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * stage_bytes), sb = sa + (uint32_t)p.a_bytes;
-                    for (int r = 0; r < p.KH; r++)
-                        for (int s = 0; s < p.KW; s++) {
-                            const uint32_t a0 = sa + (uint32_t)(r * PW + s) * rowbytes;
-                            const uint32_t b0 = sb + (uint32_t)(r * p.KW + s) * (uint32_t)p.BN * rowbytes;
-                            uint64_t da = make_smem_desc(a0, swz, sbo), db = make_smem_desc(b0, swz, sbo);
-                            if (p.bo_mode) da |= (uint64_t)((a0 >> 7) & 7u) << 49;
-                            for (int j = 0; j < ksteps; j++)
-                                umma_f16(tmem_acc, da + (uint64_t)(j * 2), db + (uint64_t)(j * 2), idesc,
-                                         (sl | r | s | j) != 0);
+                uint32_t first = 0;                         // 0 for the very first MMA of the row (overwrite)
+                for (int r = 0; r < p.KH; r++) {
+                    const uint32_t g = cnt + (uint32_t)(y - ya + r);
+                    const uint32_t a_row = ring16 + (g % (uint32_t)p.nslot) * row16;
+                    for (int sl = 0; sl < slabs; sl++) {
+                        const uint32_t a_lo = a_row + (uint32_t)sl * slab16;
+                        const uint32_t b_lo = w16 + (uint32_t)((sl * taps + r * KW)) * tap16;
+#pragma unroll
+                        for (int s = 0; s < KW; s++) {
+#pragma unroll
+                            for (int j = 0; j < ksteps; j++) {
+                                umma_f16_pred(tmem_acc, desc_with_lo(dhi, a_lo + (uint32_t)(s * (rowb >> 4) + 2 * j)),
+                                              desc_with_lo(dhi, b_lo + (uint32_t)s * tap16 + (uint32_t)(2 * j)), idesc,
+                                              first, leader);
+                                first = 1;
+                            }
                         }
-                    umma_commit(&empty_bar[stage]);
-                    if (++stage == kRowStages) { stage = 0; phase ^= 1; }
+                    }
                 }
-                umma_commit(&tmem_full_bar[acc]);
+                umma_commit_pred(&tmem_full_bar[acc], leader);
+                // input row (y - ph) is not needed by later output rows: release its slot
+                {
+                    const uint32_t g = cnt + (uint32_t)(y - ya);
+                    umma_commit_pred(&empty_bar[g % (uint32_t)p.nslot], leader);
+                }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
+            // release the KH-1 rows still held by this item
+            for (int k = (yb - ya); k < rows_in; k++) {
+                const uint32_t g = cnt + (uint32_t)k;
+                umma_commit_pred(&empty_bar[g % (uint32_t)p.nslot], leader);
+            }
+            cnt += (uint32_t)rows_in;
         }
     } else {
         // ===== epilogue =====
         const int q = warp & 3;
         const int m = q * 32 + lane;
         uint32_t acc = 0, acc_phase = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-            const int tx = tile % p.tiles_x, row = tile / p.tiles_x;
-            const int y = row % p.H, n = row / p.H;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            const int tx = item % p.tiles_x, rest = item / p.tiles_x;
+            const int seg = rest % p.n_seg, n = rest / p.n_seg;
+            const int ya = seg * p.seg_h, yb = min(p.H, ya + p.seg_h);
             const int px = tx * kRowTile + m;
             const bool inb = px < p.W;
-            mbar_wait(&tmem_full_bar[acc], acc_phase);
-            tcgen05_fence_after();
-            const uint32_t tmem_acc = tmem_base + acc * acc_cols;
-            const size_t pix = ((size_t)n * p.H + y) * p.W + px;
-            for (int c0 = 0; c0 < p.BN; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld_32x32b_x16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-                tmem_ld_wait();
-                float f[16];
+            for (int y = ya; y < yb; y++) {
+                mbar_wait(&tmem_full_bar[acc], acc_phase);
+                tcgen05_fence_after();
+                const uint32_t tmem_acc = tmem_base + acc * acc_cols;
+                const size_t pix = ((size_t)n * p.H + y) * p.W + px;
+                for (int c0 = 0; c0 < p.BN; c0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld_32x32b_x16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+                    tmem_ld_wait();
+                    float f[16];
 #pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    float x = __uint_as_float(v[j]) + __ldg(p.bias + c0 + j);
-                    f[j] = x > 0.f ? x : x * p.slope;
-                }
-                if (inb) {
-                    if (p.out_mode == 0) {
-                        __half2 h[8];
+                    for (int j = 0; j < 16; j++) {
+                        float x = __uint_as_float(v[j]) + __ldg(p.bias + c0 + j);
+                        f[j] = x > 0.f ? x : x * p.slope;
+                    }
+                    if (inb) {
+                        if (p.out_mode == 0) {
+                            __half2 h[8];
 #pragma unroll
-                        for (int j = 0; j < 8; j++) h[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
-                        uint4 *dst = (uint4 *)((__half *)p.out + pix * p.out_cstride + c0);
-                        dst[0] = *(uint4 *)&h[0];
-                        dst[1] = *(uint4 *)&h[4];
-                    } else if (c0 == 0) {
-                        float4 *dst = (float4 *)((float *)p.out + pix * 8);
-                        dst[0] = make_float4(f[0], f[1], f[2], f[3]);
-                        dst[1] = make_float4(f[4], f[5], f[6], f[7]);
+                            for (int j = 0; j < 8; j++) h[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+                            uint4 *dst = (uint4 *)((__half *)p.out + pix * p.out_cstride + c0);
+                            dst[0] = *(uint4 *)&h[0];
+                            dst[1] = *(uint4 *)&h[4];
+                        } else if (c0 == 0) {
+                            float4 *dst = (float4 *)((float *)p.out + pix * 8);
+                            dst[0] = make_float4(f[0], f[1], f[2], f[3]);
+                            dst[1] = make_float4(f[4], f[5], f[6], f[7]);
+                        }
                     }
                 }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
     __syncthreads();
@@ -486,114 +524,132 @@ extern "C" int v2e_conv2d_lrelu_sm100(const void *x1_dev, int C1, const void *x2
     return v2e_conv_launch(&L, (cudaStream_t)stream);
 }
 
-// ---- row kernel host side ------------------------------------------------------------------------
-struct V2eRowLaunch {
+// ---- strip kernel host side ------------------------------------------------------------------------
+struct V2eStripLaunch {
     CUtensorMap tmA, tmA2, tmB;
-    RowParams p;
+    StripParams p;
     int grid;
     size_t smem;
 };
 
-// halo box: KC channels x (128+KW-1) columns x KH rows x 1 image
-static int make_halo_tmap(CUtensorMap *tm, const void *ptr, int N, int H, int W, int C, int KC, int KH, int KW) {
+// one input row of the strip: KC channels x (128+KW-1) columns
+static int make_rowseg_tmap(CUtensorMap *tm, const void *ptr, int N, int H, int W, int C, int KC, int KW) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return v2e_set_error(V2E_E_CUDA, "cuTensorMapEncodeTiled unavailable%s", "");
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-    cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)(kRowTile + KW - 1), (cuuint32_t)KH, 1};
+    cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)(kRowTile + KW - 1), 1, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void *)ptr, dims, strides, box, es,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(KC), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        snprintf(g_conv_err, sizeof(g_conv_err), "halo map N=%d H=%d W=%d C=%d KC=%d CUresult=%d", N, H, W, C, KC, (int)r);
-        return v2e_set_error(V2E_E_CUDA, "cuTensorMapEncodeTiled failed: %s", g_conv_err);
-    }
+    if (r != CUDA_SUCCESS) return v2e_set_error(V2E_E_CUDA, "cuTensorMapEncodeTiled failed for a strip row map%s", "");
     return V2E_OK;
 }
 
-// Picks the slab width for the row kernel: the largest KC in {64,32,16} dividing both inputs whose
-// stage (halo + all taps' weights) fits twice in shared memory. Returns 0 if the layer does not qualify.
-int v2e_row_pick_kc(int C1, int C2, int Cout_pad, int KH, int KW, int W) {
-    if (Cout_pad > 128 || W < 2 * kRowTile) return 0;
+// Slab width and ring depth for the strip kernel; returns KC (0: layer does not qualify), *nslot_out.
+int v2e_strip_pick(int C1, int C2, int Cout_pad, int KH, int KW, int W, int *nslot_out) {
+    if (Cout_pad > 128 || W < kRowTile || (KW != 3 && KW != 5 && KW != 7)) return 0;
     const int g = C2 ? (C1 < C2 ? C1 : C2) : C1;
-    for (int kc = 64; kc >= 16; kc >>= 1) {
-        if (g % kc) continue;
-        size_t a = ((size_t)KH * (kRowTile + KW - 1) * kc * 2 + 1023) & ~(size_t)1023;
-        size_t b = (size_t)KH * KW * Cout_pad * kc * 2;
-        if (kRowStages * (a + b) + 2048 <= 220 * 1024) return kc;
-    }
-    return 0;
+    const int kc = g % 64 == 0 ? 64 : (g % 32 == 0 ? 32 : 16);
+    const int slabs = (C1 + C2) / kc;
+    const size_t wb = ((size_t)slabs * KH * KW * Cout_pad * kc * 2 + 1023) & ~(size_t)1023;
+    const size_t slab = ((size_t)(kRowTile + KW - 1) * kc * 2 + 1023) & ~(size_t)1023;
+    const size_t budget = 222 * 1024;
+    if (wb + 2048 >= budget) return 0;
+    int nslot = (int)((budget - wb - 2048) / (slab * slabs));
+    if (nslot > kMaxSlot) nslot = kMaxSlot;
+    if (nslot < KH + 1) return 0;
+    if (nslot_out) *nslot_out = nslot;
+    return kc;
 }
 
-size_t v2e_row_launch_size(void) { return sizeof(V2eRowLaunch); }
+size_t v2e_strip_launch_size(void) { return sizeof(V2eStripLaunch); }
 
-// wgt_row: fp16 [slabs][taps][Cout_pad][KC] (see pack in slomo.cu / tests)
-int v2e_row_prepare(V2eRowLaunch *L, const void *x1, int C1, const void *x2, int C2, const void *wgt_row,
-                    const float *bias, int Cout_pad, int KH, int KW, int KC, int N, int H, int W, void *out,
-                    int out_cstride, int out_mode, int co_real, float slope, int n_sms, int bo_mode) {
+int v2e_strip_prepare(V2eStripLaunch *L, const void *x1, int C1, const void *x2, int C2, const void *wgt_row,
+                      const float *bias, int Cout_pad, int KH, int KW, int N, int H, int W, void *out,
+                      int out_cstride, int out_mode, int co_real, float slope, int n_sms) {
     memset(L, 0, sizeof(*L));
-    RowParams &p = L->p;
+    StripParams &p = L->p;
+    int nslot = 0;
+    const int KC = v2e_strip_pick(C1, C2, Cout_pad, KH, KW, W, &nslot);
+    if (!KC) return v2e_set_error(V2E_E_INVALID, "layer does not qualify for the strip kernel%s", "");
     p.N = N; p.H = H; p.W = W; p.C1 = C1; p.C2 = C2; p.KH = KH; p.KW = KW; p.KC = KC; p.BN = Cout_pad;
     p.tiles_x = (W + kRowTile - 1) / kRowTile;
-    p.n_tiles = p.tiles_x * H * N;
-    p.a_bytes = (int)(((size_t)KH * (kRowTile + KW - 1) * KC * 2 + 1023) & ~(size_t)1023);
-    p.b_bytes = KH * KW * Cout_pad * KC * 2;
-    const int taps = KH * KW;
-    int taps_per_load = 256 / Cout_pad;
-    if (taps_per_load > taps) taps_per_load = taps;
-    while (taps % taps_per_load) taps_per_load--;          // equal-sized loads
-    p.b_rows_per_load = taps_per_load * Cout_pad;
-    p.b_loads = taps / taps_per_load;
+    // segment height: enough items to balance the SMs (>= ~6 per SM), at least 4*KH rows per item
+    int seg_h = H;
+    const int strips = p.tiles_x * N;
+    while (seg_h > 4 * KH && (long)strips * ((H + seg_h - 1) / seg_h) < 6L * n_sms) seg_h = (seg_h + 1) / 2;
+    p.seg_h = seg_h;
+    p.n_seg = (H + seg_h - 1) / seg_h;
+    p.n_items = strips * p.n_seg;
+    p.nslot = nslot;
+    const int slabs = (C1 + C2) / KC, taps = KH * KW;
+    p.slab_bytes = (int)(((size_t)(kRowTile + KW - 1) * KC * 2 + 1023) & ~(size_t)1023);
+    p.w_bytes = slabs * taps * Cout_pad * KC * 2;
+    int rows_total = slabs * taps * Cout_pad;
+    int rpl = 256;                                           // rows per weight load: largest divisor <= 256, multiple of 8
+    while ((rows_total % rpl) || (rpl % 8)) rpl--;
+    p.w_rows_per_load = rpl;
+    p.w_loads = rows_total / rpl;
     p.out_cstride = out_cstride; p.out_mode = out_mode; p.co_real = co_real; p.slope = slope;
-    p.bias = bias; p.out = out; p.bo_mode = bo_mode;
+    p.bias = bias; p.out = out;
     int rc;
-    if ((rc = make_halo_tmap(&L->tmA, x1, N, H, W, C1, KC, KH, KW))) return rc;
-    if (C2) { if ((rc = make_halo_tmap(&L->tmA2, x2, N, H, W, C2, KC, KH, KW))) return rc; }
+    if ((rc = make_rowseg_tmap(&L->tmA, x1, N, H, W, C1, KC, KW))) return rc;
+    if (C2) { if ((rc = make_rowseg_tmap(&L->tmA2, x2, N, H, W, C2, KC, KW))) return rc; }
     else L->tmA2 = L->tmA;
-    const int slabs = (C1 + C2) / KC;
     {
         EncodeTiledFn fn = encode_fn();
-        cuuint64_t dims[2] = {(cuuint64_t)KC, (cuuint64_t)slabs * taps * Cout_pad};
+        cuuint64_t dims[2] = {(cuuint64_t)KC, (cuuint64_t)rows_total};
         cuuint64_t strides[1] = {(cuuint64_t)KC * 2};
-        cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)p.b_rows_per_load};
+        cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)rpl};
         cuuint32_t es[2] = {1, 1};
         CUresult r = fn(&L->tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *)wgt_row, dims, strides, box, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(KC), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return v2e_set_error(V2E_E_CUDA, "cuTensorMapEncodeTiled failed for row weights%s", "");
+        if (r != CUDA_SUCCESS) return v2e_set_error(V2E_E_CUDA, "cuTensorMapEncodeTiled failed for strip weights%s", "");
     }
-    L->grid = p.n_tiles < n_sms ? p.n_tiles : n_sms;
-    L->smem = (size_t)kRowStages * (p.a_bytes + p.b_bytes) + 1024;
+    L->grid = p.n_items < n_sms ? p.n_items : n_sms;
+    L->smem = (size_t)((p.w_bytes + 1023) & ~1023) + (size_t)nslot * p.slab_bytes * slabs + 1024;
     return V2E_OK;
 }
 
-int v2e_row_launch(const V2eRowLaunch *L, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(conv_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-        attr_set = true;
+int v2e_strip_launch(const V2eStripLaunch *L, cudaStream_t st) {
+#define STRIP_CASE(KW_, KC_)                                                                                  \
+    if (L->p.KW == KW_ && L->p.KC == KC_) {                                                                    \
+        static bool attr_set = false;                                                                           \
+        if (!attr_set) {                                                                                        \
+            cudaFuncSetAttribute(conv_strip_kernel<KW_, KC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); \
+            attr_set = true;                                                                                    \
+        }                                                                                                       \
+        conv_strip_kernel<KW_, KC_><<<L->grid, kConvThreads, L->smem, st>>>(L->tmA, L->tmA2, L->tmB, L->p);     \
+        launched = true;                                                                                        \
     }
-    conv_row_kernel<<<L->grid, kConvThreads, L->smem, st>>>(L->tmA, L->tmA2, L->tmB, L->p);
+    bool launched = false;
+    STRIP_CASE(3, 16) STRIP_CASE(3, 32) STRIP_CASE(3, 64)
+    STRIP_CASE(5, 16) STRIP_CASE(5, 32) STRIP_CASE(5, 64)
+    STRIP_CASE(7, 16) STRIP_CASE(7, 32) STRIP_CASE(7, 64)
+#undef STRIP_CASE
+    if (!launched) return v2e_set_error(V2E_E_UNSUPPORTED, "strip kernel: unsupported filter width / slab%s", "");
     cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return v2e_set_error(V2E_E_CUDA, "conv_row_kernel launch: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) return v2e_set_error(V2E_E_CUDA, "conv_strip_kernel launch: %s", cudaGetErrorString(e));
     return V2E_OK;
 }
 
-extern "C" int v2e_conv2d_lrelu_sm100_row(const void *x1_dev, int C1, const void *x2_dev, int C2,
-                                          const void *wgt_row_dev, const float *bias_dev, int Cout_pad, int KH,
-                                          int KW, int KC, int N, int H, int W, void *out_dev, int out_cstride,
-                                          int out_mode, int co_real, float slope, int bo_mode, void *stream) {
-    V2eRowLaunch L;
+extern "C" int v2e_conv2d_lrelu_sm100_strip(const void *x1_dev, int C1, const void *x2_dev, int C2,
+                                            const void *wgt_row_dev, const float *bias_dev, int Cout_pad, int KH,
+                                            int KW, int N, int H, int W, void *out_dev, int out_cstride,
+                                            int out_mode, int co_real, float slope, void *stream) {
+    V2eStripLaunch L;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int rc = v2e_row_prepare(&L, x1_dev, C1, x2_dev, C2, wgt_row_dev, bias_dev, Cout_pad, KH, KW, KC, N, H, W,
-                             out_dev, out_cstride, out_mode, co_real, slope, sms, bo_mode);
+    int rc = v2e_strip_prepare(&L, x1_dev, C1, x2_dev, C2, wgt_row_dev, bias_dev, Cout_pad, KH, KW, N, H, W,
+                               out_dev, out_cstride, out_mode, co_real, slope, sms);
     if (rc) return rc;
-    return v2e_row_launch(&L, (cudaStream_t)stream);
+    return v2e_strip_launch(&L, (cudaStream_t)stream);
 }
 
-extern "C" int v2e_conv_row_pick_kc(int C1, int C2, int Cout_pad, int KH, int KW, int W) {
-    return v2e_row_pick_kc(C1, C2, Cout_pad, KH, KW, W);
+extern "C" int v2e_conv_strip_pick_kc(int C1, int C2, int Cout_pad, int KH, int KW, int W) {
+    return v2e_strip_pick(C1, C2, Cout_pad, KH, KW, W, nullptr);
 }

@@ -30,13 +30,13 @@ int v2e_conv_prepare(V2eConvLaunch *L, const void *x1, int C1, const void *x2, i
                      int out_cstride, int out_mode, int co_real, float slope);
 int v2e_conv_launch(const V2eConvLaunch *L, cudaStream_t st);
 size_t v2e_conv_launch_size(void);
-struct V2eRowLaunch;
-int v2e_row_pick_kc(int C1, int C2, int Cout_pad, int KH, int KW, int W);
-size_t v2e_row_launch_size(void);
-int v2e_row_prepare(V2eRowLaunch *L, const void *x1, int C1, const void *x2, int C2, const void *wgt_row,
-                    const float *bias, int Cout_pad, int KH, int KW, int KC, int N, int H, int W, void *out,
-                    int out_cstride, int out_mode, int co_real, float slope, int n_sms, int bo_mode);
-int v2e_row_launch(const V2eRowLaunch *L, cudaStream_t st);
+struct V2eStripLaunch;
+int v2e_strip_pick(int C1, int C2, int Cout_pad, int KH, int KW, int W, int *nslot_out);
+size_t v2e_strip_launch_size(void);
+int v2e_strip_prepare(V2eStripLaunch *L, const void *x1, int C1, const void *x2, int C2, const void *wgt_row,
+                      const float *bias, int Cout_pad, int KH, int KW, int N, int H, int W, void *out,
+                      int out_cstride, int out_mode, int co_real, float slope, int n_sms);
+int v2e_strip_launch(const V2eStripLaunch *L, cudaStream_t st);
 int v2e_set_error(int code, const char *fmt, const char *detail);
 
 #define CU(call)                                                                              \
@@ -302,8 +302,8 @@ struct UNet {
     int in_ch, out_ch;
     LayerSpec L[23];
     __half *w[23];
-    __half *w_row[23];           // [slabs][taps][Cout_pad][KC] for layers that run on the row kernel
-    int row_kc[23];              // 0: per-tap kernel
+    __half *w_row[23];           // [slabs][taps][Cout_pad][KC] for layers that run on the strip kernel
+    int row_kc[23];              // slab width of the strip kernel; 0: per-tap kernel
     float *b[23];
     int cout_pad[23], c1p[23], c2p[23];
 };
@@ -372,7 +372,7 @@ static int upload_unet(UNet &u, const V2eUNetWeights *wts, int W) {
         std::vector<float> bias(cp, 0.f);
         for (int o = 0; o < l.cout; o++) bias[o] = wts->b[i][o];
         u.w_row[i] = nullptr;
-        u.row_kc[i] = v2e_row_pick_kc(c1p, c2p, cp, l.k, l.k, W >> layer_level(i));
+        u.row_kc[i] = v2e_strip_pick(c1p, c2p, cp, l.k, l.k, W >> layer_level(i), nullptr);
         if (u.row_kc[i]) {
             const int kc = u.row_kc[i], slabs = (c1p + c2p) / kc;
             std::vector<__half> rowp((size_t)slabs * taps * cp * kc);
@@ -429,7 +429,7 @@ extern "C" int v2e_slomo_create(int H, int W, int max_batch, const V2eUNetWeight
     CU(cudaMalloc((void **)&h->img, (B + 1) * HW * sizeof(float)));
     CU(cudaMalloc((void **)&h->maxspeed, sizeof(float)));
     h->launch_mem.resize(v2e_conv_launch_size());
-    h->row_mem.resize(v2e_row_launch_size());
+    h->row_mem.resize(v2e_strip_launch_size());
     { int dev = 0; cudaGetDevice(&dev); h->n_sms = 148; cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, dev); }
     h->force_tap_kernel = 0;
     *out = h;
@@ -456,11 +456,10 @@ static int conv(V2eSlomo *h, const UNet &u, int li, const __half *x1, const __ha
     int rc;
     const bool row = u.row_kc[li] != 0 && !h->force_tap_kernel;
     V2eConvLaunch *L = (V2eConvLaunch *)h->launch_mem.data();
-    V2eRowLaunch *R = (V2eRowLaunch *)h->row_mem.data();
+    V2eStripLaunch *R = (V2eStripLaunch *)h->row_mem.data();
     if (row)
-        rc = v2e_row_prepare(R, x1, u.c1p[li], x2, x2 ? u.c2p[li] : 0, u.w_row[li], u.b[li], u.cout_pad[li], u.L[li].k,
-                             u.L[li].k, u.row_kc[li], B, H, W, out, u.cout_pad[li], out_mode, u.L[li].cout, kSlope,
-                             h->n_sms, 0);
+        rc = v2e_strip_prepare(R, x1, u.c1p[li], x2, x2 ? u.c2p[li] : 0, u.w_row[li], u.b[li], u.cout_pad[li], u.L[li].k,
+                               u.L[li].k, B, H, W, out, u.cout_pad[li], out_mode, u.L[li].cout, kSlope, h->n_sms);
     else
         rc = v2e_conv_prepare(L, x1, u.c1p[li], x2, x2 ? u.c2p[li] : 0, u.w[li], u.b[li], u.cout_pad[li], u.L[li].k,
                               u.L[li].k, B, H, W, out, u.cout_pad[li], out_mode, u.L[li].cout, kSlope);
@@ -473,7 +472,7 @@ static int conv(V2eSlomo *h, const UNet &u, int li, const __half *x1, const __ha
         }
         cudaEventRecord(h->ev[h->ev_used], st);
     }
-    rc = row ? v2e_row_launch(R, st) : v2e_conv_launch(L, st);
+    rc = row ? v2e_strip_launch(R, st) : v2e_conv_launch(L, st);
     if (h->profile) {
         cudaEventRecord(h->ev[h->ev_used + 1], st);
         h->ev_used += 2;

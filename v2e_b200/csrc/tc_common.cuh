@@ -65,6 +65,33 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
 }
+// Predicated forms for a converged warp: every lane executes the (warp-uniform) surrounding code so that
+// descriptors live in uniform registers; only the lane with `leader != 0` issues. This keeps the issue
+// loop at a few instructions per MMA (a single-lane `if` makes the compiler wrap every UTCHMMA in an
+// ELECT / BRA.U.ANY loop and compute descriptors in the vector datapath).
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred;
+}
+__device__ __forceinline__ void umma_f16_pred(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate, uint32_t leader) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pred(uint64_t *bar, uint32_t leader) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(smem_u32(bar)), "r"(leader) : "memory");
+}
+__device__ __forceinline__ uint64_t desc_with_lo(uint64_t hi_part, uint32_t lo) {
+    return (hi_part & 0xFFFFFFFF00000000ull) | (uint64_t)lo;
+}
 // arrives on the mbarrier once all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

@@ -36,6 +36,7 @@ constexpr int kVec = 4;                 // pixels per thread
 constexpr int kSegSmem = 64;            // (iteration,polarity) segments aggregated in shared memory
 constexpr int kRecShift = 2;            // record = (signed count << 2) | shot_off << 1 | shot_on
 constexpr int kRecMaxCount = 8191;
+constexpr int kListBlocks = 296;         // grid of the kernels that walk the active-pixel list
 constexpr int kPhiloxRounds = 7;         // Philox4x32-7: the lightest variant that passes BigCrush (Salmon et al. 2011)
 
 struct FrameCtrl {                      // one per frame slot, device memory, zeroed per step
@@ -63,6 +64,8 @@ struct EmuDev {                         // passed by value to every kernel
     float *pos_thres, *neg_thres, *noise_rate, *tmem;
     double *surround;
     int16_t *rec;
+    uint32_t *act_list;                 // [n_pad] pixel indices with a non-zero record (built by the update kernel)
+    uint32_t *act_count;                // [max_slots]
     const float *lut;                   // [256] lin_log
     FrameCtrl *ctrl;                    // [max_slots+1]
     uint32_t *hist_pre, *hist_post, *segoff, *cursor;   // [max_slots][seg_stride]
@@ -365,16 +368,23 @@ __global__ void __launch_bounds__(kThreads) emu_first_frame_kernel(EmuDev d, Fra
 // flag. Tables in shared memory: lin_log(0..255) as float64 and inten01(0..255) = (x+20)/275
 // (the same IEEE division the reference does, evaluated once per block instead of once per pixel).
 // ---------------------------------------------------------------------------------------------
-template <typename S, int FT, int RNG>
+// FAST: the configuration fixed at compile time to v2e's CLI defaults in device-RNG mode (per-pixel
+// thresholds, low-pass, leak and shot noise on, no hdr / csdvs): every uniform flag test disappears.
+template <typename S, int FT, int RNG, bool FAST>
 __global__ void __launch_bounds__(kThreads, 4)
 emu_update_kernel(EmuDev d, FrameParams p, const void *frame, const float *leak_randn,
-                  const float *shot_rand, int slot, int do_plan, int lp_done) {
+                  const float *shot_rand, int slot, int do_plan, int lp_done_arg) {
+    const bool f_pp = FAST || d.per_pixel_thres, f_leak = FAST || d.leak_on, f_lp = FAST || d.lowpass_on;
+    const bool f_shot = FAST || d.shot_on, f_hdr = FAST ? false : (bool)d.hdr, f_cs = FAST ? false : (bool)d.csdvs;
+    const bool lp_done = FAST ? false : (bool)lp_done_arg;
     __shared__ double s_lut[256];
     __shared__ double s_inten[256];
     __shared__ uint32_t s_hist[kSegSmem + 2];
     __shared__ int s_max;
+    __shared__ uint32_t s_wbase[kThreads / 32], s_act_total, s_gbase;
     if (*(volatile int32_t *)d.abort_flag) return;
     const int tid = threadIdx.x;
+    if (tid == 0) s_act_total = 0;
     s_lut[tid] = (double)d.lut[tid];
     s_inten[tid] = ((double)tid + 20.0) / 275.0;
     if (tid < kSegSmem + 2) s_hist[tid] = 0;
@@ -385,6 +395,7 @@ emu_update_kernel(EmuDev d, FrameParams p, const void *frame, const float *leak_
     const int i0 = (blockIdx.x * kThreads + tid) * kVec;
     int local_max = 0;
     int mags[4] = {0, 0, 0, 0}, pols[4] = {0, 0, 0, 0}, flg[4] = {0, 0, 0, 0};
+    short recs[4] = {0, 0, 0, 0};
     if (i0 < d.n) {
         double x[4];
         load_frame4<FT>(frame, i0, d.n, x);
@@ -393,23 +404,23 @@ emu_update_kernel(EmuDev d, FrameParams p, const void *frame, const float *leak_
         double su[4];
         ld4((const S *)d.lp, i0, lp);
         ld4((const S *)d.base, i0, base);
-        if (d.per_pixel_thres) {
+        if (f_pp) {
             ld4(d.pos_thres, i0, thp);
             ld4(d.neg_thres, i0, thn);
         } else {
 #pragma unroll
             for (int k = 0; k < 4; k++) { thp[k] = (float)d.pos_nom; thn[k] = (float)d.neg_nom; }
         }
-        if (d.csdvs) ld4(d.surround, i0, su);
-        const bool shot_here = d.shot_on && (RNG == 1 || shot_rand != nullptr);
-        if (d.leak_on) {
+        if (f_cs) ld4(d.surround, i0, su);
+        const bool shot_here = f_shot && (RNG == 1 || shot_rand != nullptr);
+        if (f_leak) {
             ld4(d.noise_rate, i0, nr);
             if (RNG == 0) load_f32x4_any(leak_randn, i0, d.n, lr);
         }
         if (RNG == 0 && shot_here) load_f32x4_any(shot_rand, i0, d.n, sr);
         if (RNG == 1) {
             const uint2 key = make_uint2((uint32_t)d.seed, (uint32_t)(d.seed >> 32));
-            if (d.leak_on) {
+            if (f_leak) {
                 // Box-Muller on fast intrinsics: this stream only has to be N(0,1), not torch's bits
                 uint4 r = philox4x32<kPhiloxRounds>(make_uint4((uint32_t)(i0 >> 2), p.frame_index, 0u, 0x6c65616bu), key);
                 float a = __fsqrt_rn(-2.0f * __logf(u01_open(r.x))), b = __fsqrt_rn(-2.0f * __logf(u01_open(r.z)));
@@ -418,12 +429,11 @@ emu_update_kernel(EmuDev d, FrameParams p, const void *frame, const float *leak_
                 __sincosf(6.283185307179586f * u01_half(r.w), &sb, &cb);
                 lr[0] = a * ca; lr[1] = a * sa; lr[2] = b * cb; lr[3] = b * sb;
             }
-            if (d.shot_on) {
+            if (f_shot) {
                 uint4 r = philox4x32<kPhiloxRounds>(make_uint4((uint32_t)(i0 >> 2), p.frame_index, 1u, 0x73686f74u), key);
                 sr[0] = u01_half(r.x); sr[1] = u01_half(r.y); sr[2] = u01_half(r.z); sr[3] = u01_half(r.w);
             }
         }
-        short recs[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const double xv = x[k];
@@ -431,10 +441,10 @@ emu_update_kernel(EmuDev d, FrameParams p, const void *frame, const float *leak_
             // photoreceptor low-pass (emulator_utils.py:57-109)
             if (!lp_done) {
                 double ln;                               // float32 lin_log value, widened (or raw if hdr)
-                if (d.hdr) ln = xv;
+                if (f_hdr) ln = xv;
                 else ln = is_code ? s_lut[(int)xv] : (double)lin_log_eval(xv);
                 if (sizeof(S) == 8) {
-                    if (d.lowpass_on) {
+                    if (f_lp) {
                         double inten01 = is_code ? s_inten[(int)xv] : (xv + 20.0) / 275.0;
                         double eps = inten01 * p.eps_scale;
                         if (eps > 1.0) eps = 1.0;
@@ -447,17 +457,17 @@ emu_update_kernel(EmuDev d, FrameParams p, const void *frame, const float *leak_
                 }
             }
             // leak (emulator_utils.py:114-134): float32 products, subtract in S
-            if (d.leak_on) {
+            if (f_leak) {
                 float rate = (d.leak_rate_f * nr[k]) * (1.0f - d.leak_jit_f * lr[k]);
                 float delta = (p.dt_f * rate) * thp[k];
                 base[k] = base[k] - (S)delta;
             }
             // difference and event counts (emulator.py:748-772, emulator_utils.py:137-173)
             S diff;
-            if (sizeof(S) == 8 && d.csdvs) diff = (S)(((double)lp[k] - su[k]) - (double)base[k]);
+            if (sizeof(S) == 8 && f_cs) diff = (S)(((double)lp[k] - su[k]) - (double)base[k]);
             else diff = lp[k] - base[k];
             S tp, tn;
-            if (sizeof(S) == 8 && !d.per_pixel_thres) { tp = (S)d.pos_nom; tn = (S)d.neg_nom; }
+            if (sizeof(S) == 8 && !f_pp) { tp = (S)d.pos_nom; tn = (S)d.neg_nom; }
             else { tp = (S)thp[k]; tn = (S)thn[k]; }
             int32_t cnt = 0;
             if (diff >= tp) cnt = div_floor_count<S>(diff, tp);
@@ -481,7 +491,7 @@ emu_update_kernel(EmuDev d, FrameParams p, const void *frame, const float *leak_
             flg[k] = flags;
         }
         if (!lp_done) st4((S *)d.lp, i0, lp);
-        if (d.leak_on) st4((S *)d.base, i0, base);
+        if (f_leak) st4((S *)d.base, i0, base);
         *(short4 *)(d.rec + i0) = make_short4(recs[0], recs[1], recs[2], recs[3]);
     }
     // per-(iteration,polarity) histogram. Iterations 0 and 1 (almost all events) are counted per thread
@@ -528,11 +538,33 @@ emu_update_kernel(EmuDev d, FrameParams p, const void *frame, const float *leak_
             }
         }
     }
+    // compaction of the active pixels (record != 0) into act_list: warp scan, one shared atomic per warp,
+    // one global atomic per block; the filter / emit kernels only walk this list
+    const int nact = (recs[0] != 0) + (recs[1] != 0) + (recs[2] != 0) + (recs[3] != 0);
+    int incl = nact;
+    {
+        const int lane = tid & 31;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int wtot = __shfl_sync(0xffffffffu, incl, 31);
+        if (lane == 31 && wtot) s_wbase[tid >> 5] = atomicAdd(&s_act_total, (uint32_t)wtot);
+    }
     // block max -> one atomicMax per block
     local_max = warp_reduce_max(local_max);
     if ((tid & 31) == 0 && local_max > 0) atomicMax(&s_max, local_max);
     __syncthreads();
     if (tid == 0 && s_max > 0) atomicMax(&c->max_n, s_max);
+    if (tid == 0 && s_act_total) s_gbase = atomicAdd(&d.act_count[slot], s_act_total);
+    __syncthreads();
+    if (nact) {
+        uint32_t pos = s_gbase + s_wbase[tid >> 5] + (uint32_t)(incl - nact);
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (recs[k] != 0) d.act_list[pos++] = (uint32_t)(i0 + k);
+    }
     if (tid < kSegSmem && s_hist[tid]) atomicAdd(&hist[tid], s_hist[tid]);
     if (tid >= kSegSmem && tid < kSegSmem + 2 && s_hist[tid])
         atomicAdd(&hist[2 * d.iter_cap + (tid - kSegSmem)], s_hist[tid]);
@@ -567,7 +599,8 @@ __device__ __forceinline__ int warp_walk(int mag, int pol, const TsParams &ts, b
 }
 
 // ---------------------------------------------------------------------------------------------
-// filter-count kernel (only when refractory_period_s > 0): filtered histogram, no state writes
+// filter-count kernel (only when refractory_period_s > 0): filtered histogram over the active-pixel
+// list, no state writes
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
 emu_filter_kernel(EmuDev d, FrameParams p, int slot, int do_plan) {
@@ -581,26 +614,24 @@ emu_filter_kernel(EmuDev d, FrameParams p, int slot, int do_plan) {
         if (tid < kSegSmem) s_hist[tid] = 0;
         __syncthreads();
         uint32_t *hist = d.hist_post + (size_t)slot * d.seg_stride;
-        const int i0 = (blockIdx.x * kThreads + tid) * kVec;
-        short recs[4] = {0, 0, 0, 0};
-        if (i0 < d.n) {
-            short4 r4 = *(const short4 *)(d.rec + i0);
-            recs[0] = r4.x; recs[1] = r4.y; recs[2] = r4.z; recs[3] = r4.w;
-        }
-        const bool warp_any = __any_sync(0xffffffffu, ((recs[0] | recs[1] | recs[2] | recs[3]) & ~3) != 0);
-        if (warp_any) {
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                int cnt = recs[k] >> kRecShift;
-                int mag = cnt < 0 ? -cnt : cnt, pol = cnt < 0;
-                float tm = mag ? d.tmem[i0 + k] : 0.f;
-                warp_walk(mag, pol, ts, true, d.refr_f, tm, [&](int it, float, unsigned on, unsigned off, bool) {
-                    if (lane == 0) {
-                        if (on) { if (2 * it < kSegSmem) atomicAdd(&s_hist[2 * it], __popc(on)); else atomicAdd(&hist[2 * it], __popc(on)); }
-                        if (off) { if (2 * it + 1 < kSegSmem) atomicAdd(&s_hist[2 * it + 1], __popc(off)); else atomicAdd(&hist[2 * it + 1], __popc(off)); }
-                    }
-                });
+        const uint32_t n_act = d.act_count[slot];
+        for (uint32_t base = blockIdx.x * kThreads; base < n_act; base += gridDim.x * kThreads) {
+            const uint32_t e = base + tid;
+            int mag = 0, pol = 0;
+            float tm = 0.f;
+            if (e < n_act) {
+                const uint32_t idx = d.act_list[e];
+                const int cnt = d.rec[idx] >> kRecShift;
+                mag = cnt < 0 ? -cnt : cnt;
+                pol = cnt < 0;
+                if (mag) tm = d.tmem[idx];
             }
+            warp_walk(mag, pol, ts, true, d.refr_f, tm, [&](int it, float, unsigned on, unsigned off, bool) {
+                if (lane == 0) {
+                    if (on) { if (2 * it < kSegSmem) atomicAdd(&s_hist[2 * it], __popc(on)); else atomicAdd(&hist[2 * it], __popc(on)); }
+                    if (off) { if (2 * it + 1 < kSegSmem) atomicAdd(&s_hist[2 * it + 1], __popc(off)); else atomicAdd(&hist[2 * it + 1], __popc(off)); }
+                }
+            });
         }
         __syncthreads();
         if (tid < kSegSmem && s_hist[tid]) atomicAdd(&hist[tid], s_hist[tid]);
@@ -638,7 +669,9 @@ emu_shot_kernel(EmuDev d, FrameParams p, const void *frame, const float *shot_ra
             if (i0 + k >= d.n) continue;
             int flags = shot_flags(d, p, x[k], sr[k], thp[k], thn[k]);
             if (flags) {
-                d.rec[i0 + k] = (short)(d.rec[i0 + k] | flags);
+                const short old = d.rec[i0 + k];
+                if (old == 0) d.act_list[atomicAdd(&d.act_count[slot], 1u)] = (uint32_t)(i0 + k);
+                d.rec[i0 + k] = (short)(old | flags);
                 if (flags & 1) atomicAdd(&s_cnt[0], 1u);
                 if (flags & 2) atomicAdd(&s_cnt[1], 1u);
             }
@@ -651,9 +684,9 @@ emu_shot_kernel(EmuDev d, FrameParams p, const void *frame, const float *shot_ra
 }
 
 // ---------------------------------------------------------------------------------------------
-// emit kernel: compaction of the active pixels into packed rows + state patch
+// emit kernel: walks the active-pixel list, writes packed rows + state patch
 // (emulator.py:810-870, 906-942, 1024-1059). Warp-ballot compaction: one shared-memory atomic per
-// warp and (iteration, polarity) segment, one global atomic per block and segment.
+// warp and (iteration, polarity) segment, one global atomic per block, chunk and segment.
 // ---------------------------------------------------------------------------------------------
 template <typename S>
 __global__ void __launch_bounds__(kThreads)
@@ -673,65 +706,65 @@ emu_emit_kernel(EmuDev d, FrameParams p, int slot, float4 *events) {
     const uint32_t *segoff = d.segoff + (size_t)slot * d.seg_stride;
     uint32_t *cursor = d.cursor + (size_t)slot * d.seg_stride;
     const uint64_t ev_base = c->ev_base;
-    if (tid < kSegSmem + 2) s_cnt[tid] = 0;
-    __syncthreads();
-    const int i0 = (blockIdx.x * kThreads + tid) * kVec;
-    short recs[4] = {0, 0, 0, 0};
-    if (i0 < d.n) {
-        short4 r4 = *(const short4 *)(d.rec + i0);
-        recs[0] = r4.x; recs[1] = r4.y; recs[2] = r4.z; recs[3] = r4.w;
-    }
-    const bool warp_any = __any_sync(0xffffffffu, (recs[0] | recs[1] | recs[2] | recs[3]) != 0);
-    float tm0[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) tm0[k] = (filter && (recs[k] >> kRecShift) != 0) ? d.tmem[i0 + k] : 0.f;
-    // pass 1: block-level counts per segment
-    if (warp_any) {
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            int cnt = recs[k] >> kRecShift, flags = recs[k] & 3;
-            int mag = cnt < 0 ? -cnt : cnt, pol = cnt < 0;
-            float tm = tm0[k];
+    const uint32_t n_act = d.act_count[slot];
+    // lane 0 claims `count` consecutive rows of segment `seg` for this warp
+    auto claim = [&](int seg_smem, int seg, unsigned count) -> uint32_t {
+        if (seg_smem >= 0) return s_base[seg_smem] + atomicAdd(&s_cnt[seg_smem], count);
+        return segoff[seg] + atomicAdd(&cursor[seg], count);
+    };
+    for (uint32_t base = blockIdx.x * kThreads; base < n_act; base += gridDim.x * kThreads) {
+        if (tid < kSegSmem + 2) s_cnt[tid] = 0;
+        __syncthreads();
+        const uint32_t e = base + tid;
+        int idx = 0, mag = 0, pol = 0, flags = 0;
+        float tm0 = 0.f, th = 0.f;
+        S b0 = (S)0, lpv = (S)0;
+        if (e < n_act) {
+            idx = (int)d.act_list[e];
+            const int r = d.rec[idx];
+            const int cnt = r >> kRecShift;
+            flags = r & 3;
+            mag = cnt < 0 ? -cnt : cnt;
+            pol = cnt < 0;
+            // everything the patch may need, issued together so the loads overlap
+            if (filter && mag) tm0 = d.tmem[idx];
+            th = pol ? (d.per_pixel_thres ? d.neg_thres[idx] : (float)d.neg_nom)
+                     : (d.per_pixel_thres ? d.pos_thres[idx] : (float)d.pos_nom);
+            b0 = ((const S *)d.base)[idx];
+            if (flags) lpv = ((const S *)d.lp)[idx];
+        }
+        // pass 1: block-level counts per segment
+        {
+            float tm = tm0;
             warp_walk(mag, pol, ts, filter, d.refr_f, tm, [&](int it, float, unsigned on, unsigned off, bool) {
                 if (lane == 0) {
                     if (on && 2 * it < kSegSmem) atomicAdd(&s_cnt[2 * it], __popc(on));
                     if (off && 2 * it + 1 < kSegSmem) atomicAdd(&s_cnt[2 * it + 1], __popc(off));
                 }
             });
-            unsigned son = __ballot_sync(0xffffffffu, flags & 1), soff = __ballot_sync(0xffffffffu, flags & 2);
+            const unsigned son = __ballot_sync(0xffffffffu, flags & 1), soff = __ballot_sync(0xffffffffu, flags & 2);
             if (lane == 0) {
                 if (son) atomicAdd(&s_cnt[kSegSmem], __popc(son));
                 if (soff) atomicAdd(&s_cnt[kSegSmem + 1], __popc(soff));
             }
         }
-    }
-    __syncthreads();
-    if (tid < kSegSmem + 2) {
-        uint32_t n = s_cnt[tid];
-        if (n) {
-            int seg = tid < kSegSmem ? tid : 2 * d.iter_cap + (tid - kSegSmem);
-            s_base[tid] = segoff[seg] + atomicAdd(&cursor[seg], n);
+        __syncthreads();
+        if (tid < kSegSmem + 2) {
+            const uint32_t n = s_cnt[tid];
+            if (n) {
+                const int seg = tid < kSegSmem ? tid : 2 * d.iter_cap + (tid - kSegSmem);
+                s_base[tid] = segoff[seg] + atomicAdd(&cursor[seg], n);
+            }
+            s_cnt[tid] = 0;
         }
-        s_cnt[tid] = 0;
-    }
-    __syncthreads();
-    // pass 2: write rows, patch state
-    if (warp_any) {
-        // lane 0 claims `count` consecutive rows of segment `seg` for this warp
-        auto claim = [&](int seg_smem, int seg, unsigned count) -> uint32_t {
-            if (seg_smem >= 0) return s_base[seg_smem] + atomicAdd(&s_cnt[seg_smem], count);
-            return segoff[seg] + atomicAdd(&cursor[seg], count);
-        };
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int idx = i0 + k;
-            int cnt = recs[k] >> kRecShift, flags = recs[k] & 3;
-            int mag = cnt < 0 ? -cnt : cnt, pol = cnt < 0;
+        __syncthreads();
+        // pass 2: write rows, patch state
+        {
             const float fx = (float)(idx % d.W), fy = (float)(idx / d.W);
             const float pv = pol ? -1.0f : 1.0f;
-            float tm = tm0[k];
-            int fin = warp_walk(mag, pol, ts, filter, d.refr_f, tm,
-                                [&](int it, float t, unsigned on, unsigned off, bool pass) {
+            float tm = tm0;
+            const int fin = warp_walk(mag, pol, ts, filter, d.refr_f, tm,
+                                      [&](int it, float t, unsigned on, unsigned off, bool pass) {
                 uint32_t b_on = 0, b_off = 0;
                 if (lane == 0) {
                     if (on) b_on = claim(2 * it < kSegSmem ? 2 * it : -1, 2 * it, __popc(on));
@@ -740,22 +773,19 @@ emu_emit_kernel(EmuDev d, FrameParams p, int slot, float4 *events) {
                 b_on = __shfl_sync(0xffffffffu, b_on, 0);
                 b_off = __shfl_sync(0xffffffffu, b_off, 0);
                 if (pass) {
-                    uint64_t row = ev_base + (pol ? b_off + __popc(off & lt_mask) : b_on + __popc(on & lt_mask));
+                    const uint64_t row = ev_base + (pol ? b_off + __popc(off & lt_mask) : b_on + __popc(on & lt_mask));
                     events[row] = make_float4(t, fx, fy, pv);
                 }
             });
             if (filter && fin) d.tmem[idx] = tm;
             if (fin || flags) {
-                S *basep = (S *)d.base + idx;
-                S b = *basep;
-                float th = pol ? (d.per_pixel_thres ? d.neg_thres[idx] : (float)d.neg_nom)
-                               : (d.per_pixel_thres ? d.pos_thres[idx] : (float)d.pos_nom);
-                float prod = (float)fin * th;            // int32*float32 -> float32 (emulator.py:936-937)
+                S b = b0;
+                const float prod = (float)fin * th;      // int32*float32 -> float32 (emulator.py:936-937)
                 if (pol) b = b - (S)prod; else b = b + (S)prod;
-                if (flags) b = ((const S *)d.lp)[idx];   // emulator.py:940-942
-                *basep = b;
+                if (flags) b = lpv;                      // emulator.py:940-942
+                ((S *)d.base)[idx] = b;
             }
-            unsigned son = __ballot_sync(0xffffffffu, flags & 1), soff = __ballot_sync(0xffffffffu, flags & 2);
+            const unsigned son = __ballot_sync(0xffffffffu, flags & 1), soff = __ballot_sync(0xffffffffu, flags & 2);
             if (son | soff) {
                 uint32_t b_on = 0, b_off = 0;
                 if (lane == 0) {
@@ -768,6 +798,7 @@ emu_emit_kernel(EmuDev d, FrameParams p, int slot, float4 *events) {
                 if (flags & 2) events[ev_base + b_off + __popc(soff & lt_mask)] = make_float4(ts_last, fx, fy, -1.0f);
             }
         }
+        __syncthreads();
     }
 }
 
@@ -896,6 +927,7 @@ extern "C" int v2e_emu_create(const V2eEmuCfg *cfg, V2eEmu **out) {
     ALLOC(d.lp, np * h->state_elem);
     ALLOC(d.base, np * h->state_elem);
     ALLOC(d.rec, np * sizeof(int16_t));
+    ALLOC(d.act_list, np * sizeof(uint32_t));
     if (d.per_pixel_thres) { ALLOC(d.pos_thres, np * 4); ALLOC(d.neg_thres, np * 4); }
     if (d.leak_on) ALLOC(d.noise_rate, np * 4);
     if (d.refr_on) ALLOC(d.tmem, np * 4);
@@ -908,6 +940,7 @@ extern "C" int v2e_emu_create(const V2eEmuCfg *cfg, V2eEmu **out) {
     ALLOC(d.hist_post, slots * d.seg_stride * 4);
     ALLOC(d.segoff, slots * d.seg_stride * 4);
     ALLOC(d.cursor, slots * d.seg_stride * 4);
+    ALLOC(d.act_count, slots * sizeof(uint32_t));
     ALLOC(d.abort_flag, 2 * sizeof(int32_t));
 #undef ALLOC
     if (cudaMallocHost((void **)&h->ctrl_host, (slots + 1) * sizeof(FrameCtrl)) != cudaSuccess ||
@@ -923,7 +956,7 @@ extern "C" int v2e_emu_destroy(V2eEmu *h) {
     if (!h) return V2E_OK;
     EmuDev &d = h->d;
     void *ptrs[] = {d.lp, d.base, d.rec, d.pos_thres, d.neg_thres, d.noise_rate, d.tmem, d.surround,
-                    h->lut_dev, d.ctrl, d.hist_pre, d.hist_post, d.segoff, d.cursor, d.abort_flag};
+                    h->lut_dev, d.ctrl, d.hist_pre, d.hist_post, d.segoff, d.cursor, d.abort_flag, d.act_list, d.act_count};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->ctrl_host) cudaFreeHost(h->ctrl_host);
     if (h->abort_host) cudaFreeHost(h->abort_host);
@@ -992,10 +1025,16 @@ template <typename S, int RNG>
 static int launch_update_r(V2eEmu *h, const FrameParams &p, const void *frame, int dt, const float *lr,
                            const float *sr, int slot, int do_plan, int lp_done, cudaStream_t st) {
     int g = grid_for(h->d);
+    const EmuDev &d = h->d;
+    if (sizeof(S) == 8 && RNG == 1 && dt == V2E_U8 && d.per_pixel_thres && d.leak_on && d.lowpass_on && d.shot_on &&
+        !d.hdr && !d.csdvs && !lp_done) {
+        emu_update_kernel<double, V2E_U8, 1, true><<<g, kThreads, 0, st>>>(h->d, p, frame, lr, sr, slot, do_plan, 0);
+        return V2E_OK;
+    }
     switch (dt) {
-        case V2E_U8: emu_update_kernel<S, V2E_U8, RNG><<<g, kThreads, 0, st>>>(h->d, p, frame, lr, sr, slot, do_plan, lp_done); break;
-        case V2E_F32: emu_update_kernel<S, V2E_F32, RNG><<<g, kThreads, 0, st>>>(h->d, p, frame, lr, sr, slot, do_plan, lp_done); break;
-        case V2E_F64: emu_update_kernel<S, V2E_F64, RNG><<<g, kThreads, 0, st>>>(h->d, p, frame, lr, sr, slot, do_plan, lp_done); break;
+        case V2E_U8: emu_update_kernel<S, V2E_U8, RNG, false><<<g, kThreads, 0, st>>>(h->d, p, frame, lr, sr, slot, do_plan, lp_done); break;
+        case V2E_F32: emu_update_kernel<S, V2E_F32, RNG, false><<<g, kThreads, 0, st>>>(h->d, p, frame, lr, sr, slot, do_plan, lp_done); break;
+        case V2E_F64: emu_update_kernel<S, V2E_F64, RNG, false><<<g, kThreads, 0, st>>>(h->d, p, frame, lr, sr, slot, do_plan, lp_done); break;
         default: return fail(V2E_E_INVALID, "bad frame dtype");
     }
     return V2E_OK;
@@ -1048,7 +1087,7 @@ static int enqueue_count(V2eEmu *h, const FrameParams &p, const void *frame, int
     if (rc) return rc;
     if (d.refr_on) {
         ProfScope ps(h, slot, 1, st);
-        emu_filter_kernel<<<grid_for(d), kThreads, 0, st>>>(d, p, slot, !shot_pending);
+        emu_filter_kernel<<<kListBlocks, kThreads, 0, st>>>(d, p, slot, !shot_pending);
     }
     return V2E_OK;
 }
@@ -1056,8 +1095,8 @@ static int enqueue_count(V2eEmu *h, const FrameParams &p, const void *frame, int
 static int enqueue_emit(V2eEmu *h, const FrameParams &p, int slot, float *events, cudaStream_t st) {
     const EmuDev &d = h->d;
     ProfScope ps(h, slot, 2, st);
-    if (d.state_f64) emu_emit_kernel<double><<<grid_for(d), kThreads, 0, st>>>(d, p, slot, (float4 *)events);
-    else emu_emit_kernel<float><<<grid_for(d), kThreads, 0, st>>>(d, p, slot, (float4 *)events);
+    if (d.state_f64) emu_emit_kernel<double><<<kListBlocks, kThreads, 0, st>>>(d, p, slot, (float4 *)events);
+    else emu_emit_kernel<float><<<kListBlocks, kThreads, 0, st>>>(d, p, slot, (float4 *)events);
     return V2E_OK;
 }
 
@@ -1068,6 +1107,7 @@ static int reset_slots(V2eEmu *h, int first, int count, cudaStream_t st) {
     CU(cudaMemsetAsync((char *)d.hist_post + off, 0, bytes, st));
     CU(cudaMemsetAsync((char *)d.cursor + off, 0, bytes, st));
     CU(cudaMemsetAsync(d.ctrl + first, 0, (size_t)(count + 1) * sizeof(FrameCtrl), st));
+    CU(cudaMemsetAsync(d.act_count + first, 0, (size_t)count * sizeof(uint32_t), st));
     CU(cudaMemsetAsync(d.abort_flag, 0, 2 * sizeof(int32_t), st));
     return V2E_OK;
 }

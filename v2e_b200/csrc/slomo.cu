@@ -100,37 +100,53 @@ __global__ void avgpool2_kernel(const __half *__restrict__ in, __half *__restric
     *(uint4 *)(out + (((long)n * Ho + y) * Wo + x) * C + c8 * 8) = o;
 }
 
-// F.interpolate(scale_factor=2, mode='bilinear', align_corners=False) on NHWC fp16
+// F.interpolate(scale_factor=2, mode='bilinear', align_corners=False) on NHWC fp16.
+// Output rows 2k+1 and 2k+2 both interpolate input rows k and k+1 (weights .75/.25 and .25/.75), same
+// for columns, so one thread loads a 2x2 input patch (8 channels each) and writes the 2x2 output block
+// (2k+1..2k+2, 2m+1..2m+2): one 16-byte load per 16-byte store. k = -1 and k = H-1 are the clamped borders
+// (PyTorch clamps the source index, which makes output rows 0 and 2H-1 copies of input rows 0 and H-1).
 __global__ void upsample2_kernel(const __half *__restrict__ in, __half *__restrict__ out, int N, int H, int W, int C) {
-    const int Ho = H * 2, Wo = W * 2, C8 = C / 8;
+    const int C8 = C / 8, Hb = H + 1, Wb = W + 1;
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long total = (long)N * Ho * Wo * C8;
+    const long total = (long)N * Hb * Wb * C8;
     if (i >= total) return;
     const int c8 = (int)(i % C8);
     long r = i / C8;
-    const int x = (int)(r % Wo); r /= Wo;
-    const int y = (int)(r % Ho);
-    const int n = (int)(r / Ho);
-    float sy = 0.5f * ((float)y + 0.5f) - 0.5f, sx = 0.5f * ((float)x + 0.5f) - 0.5f;
-    if (sy < 0.f) sy = 0.f;
-    if (sx < 0.f) sx = 0.f;
-    const int y0 = (int)sy, x0 = (int)sx;
-    const int y1 = y0 + (y0 < H - 1), x1 = x0 + (x0 < W - 1);
-    const float ly = sy - (float)y0, lx = sx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
+    const int m = (int)(r % Wb) - 1; r /= Wb;
+    const int k = (int)(r % Hb) - 1;
+    const int n = (int)(r / Hb);
+    const int y0 = k < 0 ? 0 : k, y1 = k + 1 > H - 1 ? H - 1 : k + 1;
+    const int x0 = m < 0 ? 0 : m, x1 = m + 1 > W - 1 ? W - 1 : m + 1;
     const __half *base = in + (long)n * H * W * C + c8 * 8;
-    uint4 a = *(const uint4 *)(base + ((long)y0 * W + x0) * C), b = *(const uint4 *)(base + ((long)y0 * W + x1) * C),
-          c = *(const uint4 *)(base + ((long)y1 * W + x0) * C), d = *(const uint4 *)(base + ((long)y1 * W + x1) * C);
+    const uint4 a = *(const uint4 *)(base + ((long)y0 * W + x0) * C), b = *(const uint4 *)(base + ((long)y0 * W + x1) * C),
+                c = *(const uint4 *)(base + ((long)y1 * W + x0) * C), d = *(const uint4 *)(base + ((long)y1 * W + x1) * C);
     const __half2 *ha = (const __half2 *)&a, *hb = (const __half2 *)&b, *hc = (const __half2 *)&c, *hd = (const __half2 *)&d;
-    uint4 o;
-    __half2 *ho = (__half2 *)&o;
+    float2 fa[4], fb[4], fc[4], fd[4];
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        float2 fa = __half22float2(ha[j]), fb = __half22float2(hb[j]), fc = __half22float2(hc[j]), fd = __half22float2(hd[j]);
-        float vx = hy * (hx * fa.x + lx * fb.x) + ly * (hx * fc.x + lx * fd.x);
-        float vy = hy * (hx * fa.y + lx * fb.y) + ly * (hx * fc.y + lx * fd.y);
-        ho[j] = __floats2half2_rn(vx, vy);
+    for (int j = 0; j < 4; j++) { fa[j] = __half22float2(ha[j]); fb[j] = __half22float2(hb[j]); fc[j] = __half22float2(hc[j]); fd[j] = __half22float2(hd[j]); }
+    const int Ho = 2 * H, Wo = 2 * W;
+#pragma unroll
+    for (int dy = 0; dy < 2; dy++) {
+        const int oy = 2 * k + 1 + dy;
+        if (oy < 0 || oy >= Ho) continue;
+        // lambda of the lower row: 0.25 for output row 2k+1, 0.75 for 2k+2 (exactly PyTorch's src - floor(src))
+        const float ly = dy ? 0.75f : 0.25f, hy = 1.f - ly;
+#pragma unroll
+        for (int dx = 0; dx < 2; dx++) {
+            const int ox = 2 * m + 1 + dx;
+            if (ox < 0 || ox >= Wo) continue;
+            const float lx = dx ? 0.75f : 0.25f, hx = 1.f - lx;
+            uint4 o;
+            __half2 *ho = (__half2 *)&o;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                float vx = hy * (hx * fa[j].x + lx * fb[j].x) + ly * (hx * fc[j].x + lx * fd[j].x);
+                float vy = hy * (hx * fa[j].y + lx * fb[j].y) + ly * (hx * fc[j].y + lx * fd[j].y);
+                ho[j] = __floats2half2_rn(vx, vy);
+            }
+            *(uint4 *)(out + (((long)n * Ho + oy) * Wo + ox) * C + c8 * 8) = o;
+        }
     }
-    *(uint4 *)(out + (((long)n * Ho + y) * Wo + x) * C + c8 * 8) = o;
 }
 
 // backWarp.forward (model.py:268-300) for one output pixel: grid_sample(img, bilinear, zeros,
@@ -503,7 +519,7 @@ static int unet_forward(V2eSlomo *h, const UNet &u, const __half *in, float *out
     for (int k = 0; k < 5; k++) {                       // up blocks (model.py:125-155)
         const int lvl = 5 - k;                          // x lives at 1/2^lvl
         const int hi = H >> lvl, wi = W >> lvl, ho = hi * 2, wo = wi * 2;
-        const long n = (long)B * ho * wo * (ui[k] / 8);
+        const long n = (long)B * (hi + 1) * (wi + 1) * (ui[k] / 8);
         upsample2_kernel<<<cdiv(n, 256), 256, 0, st>>>(x, h->up[k], B, hi, wi, ui[k]);
         const __half *skip = k < 4 ? h->s[3 - k] : h->s1;
         if ((rc = conv(h, u, 12 + 2 * k, h->up[k], nullptr, B, ho, wo, h->ua[k], 0, st))) return rc;

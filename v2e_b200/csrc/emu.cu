@@ -65,7 +65,8 @@ struct EmuDev {                         // passed by value to every kernel
     double *surround;
     int16_t *rec;
     uint32_t *act_list;                 // [n_pad] pixel indices with a non-zero record (built by the update kernel)
-    uint32_t *act_count;                // [max_slots]
+    uint32_t *act_count;                // [max_slots][n_blocks]: entries of each update-block's list segment
+    int32_t n_blocks;                   // blocks of the update kernel = list segments of kThreads*kVec pixels
     const float *lut;                   // [256] lin_log
     FrameCtrl *ctrl;                    // [max_slots+1]
     uint32_t *hist_pre, *hist_post, *segoff, *cursor;   // [max_slots][seg_stride]
@@ -381,43 +382,50 @@ emu_update_kernel(EmuDev d, FrameParams p, const void *frame, const float *leak_
     __shared__ double s_inten[256];
     __shared__ uint32_t s_hist[kSegSmem + 2];
     __shared__ int s_max;
-    __shared__ uint32_t s_wbase[kThreads / 32], s_act_total, s_gbase;
-    if (*(volatile int32_t *)d.abort_flag) return;
+    __shared__ uint32_t s_wbase[kThreads / 32], s_act_total;
     const int tid = threadIdx.x;
-    if (tid == 0) s_act_total = 0;
-    s_lut[tid] = (double)d.lut[tid];
-    s_inten[tid] = ((double)tid + 20.0) / 275.0;
-    if (tid < kSegSmem + 2) s_hist[tid] = 0;
-    if (tid == 0) s_max = 0;
-    __syncthreads();
-    FrameCtrl *c = d.ctrl + slot;
-    uint32_t *hist = d.hist_pre + (size_t)slot * d.seg_stride;
     const int i0 = (blockIdx.x * kThreads + tid) * kVec;
-    int local_max = 0;
-    int mags[4] = {0, 0, 0, 0}, pols[4] = {0, 0, 0, 0}, flg[4] = {0, 0, 0, 0};
-    short recs[4] = {0, 0, 0, 0};
+    // 1. every global load is issued before anything waits: abort flag, table entry, frame, state
+    const int32_t abort_v = *(volatile int32_t *)d.abort_flag;
+    const float lut_v = d.lut[tid];
+    double x[4] = {0, 0, 0, 0};
+    S lp[4], base[4];
+    float thp[4], thn[4], nr[4], lr[4], sr[4];
+    double su[4];
     if (i0 < d.n) {
-        double x[4];
         load_frame4<FT>(frame, i0, d.n, x);
-        S lp[4], base[4];
-        float thp[4], thn[4], nr[4], lr[4], sr[4];
-        double su[4];
         ld4((const S *)d.lp, i0, lp);
         ld4((const S *)d.base, i0, base);
         if (f_pp) {
             ld4(d.pos_thres, i0, thp);
             ld4(d.neg_thres, i0, thn);
-        } else {
-#pragma unroll
-            for (int k = 0; k < 4; k++) { thp[k] = (float)d.pos_nom; thn[k] = (float)d.neg_nom; }
         }
         if (f_cs) ld4(d.surround, i0, su);
-        const bool shot_here = f_shot && (RNG == 1 || shot_rand != nullptr);
         if (f_leak) {
             ld4(d.noise_rate, i0, nr);
             if (RNG == 0) load_f32x4_any(leak_randn, i0, d.n, lr);
         }
-        if (RNG == 0 && shot_here) load_f32x4_any(shot_rand, i0, d.n, sr);
+        if (RNG == 0 && f_shot && shot_rand != nullptr) load_f32x4_any(shot_rand, i0, d.n, sr);
+    }
+    // 2. shared-memory tables and counters
+    if (tid == 0) s_act_total = 0;
+    s_lut[tid] = (double)lut_v;
+    s_inten[tid] = ((double)tid + 20.0) / 275.0;
+    if (tid < kSegSmem + 2) s_hist[tid] = 0;
+    if (tid == 0) s_max = 0;
+    if (abort_v) return;                     // block-uniform (set by an earlier frame's plan)
+    __syncthreads();
+    FrameCtrl *c = d.ctrl + slot;
+    uint32_t *hist = d.hist_pre + (size_t)slot * d.seg_stride;
+    int local_max = 0;
+    int mags[4] = {0, 0, 0, 0}, pols[4] = {0, 0, 0, 0}, flg[4] = {0, 0, 0, 0};
+    short recs[4] = {0, 0, 0, 0};
+    if (i0 < d.n) {
+        if (!f_pp) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) { thp[k] = (float)d.pos_nom; thn[k] = (float)d.neg_nom; }
+        }
+        const bool shot_here = f_shot && (RNG == 1 || shot_rand != nullptr);
         if (RNG == 1) {
             const uint2 key = make_uint2((uint32_t)d.seed, (uint32_t)(d.seed >> 32));
             if (f_leak) {
@@ -557,10 +565,10 @@ emu_update_kernel(EmuDev d, FrameParams p, const void *frame, const float *leak_
     if ((tid & 31) == 0 && local_max > 0) atomicMax(&s_max, local_max);
     __syncthreads();
     if (tid == 0 && s_max > 0) atomicMax(&c->max_n, s_max);
-    if (tid == 0 && s_act_total) s_gbase = atomicAdd(&d.act_count[slot], s_act_total);
-    __syncthreads();
+    // this block's list segment is fixed (block b owns entries [b*1024, (b+1)*1024)): no global round trip
+    if (tid == 0) d.act_count[(size_t)slot * d.n_blocks + blockIdx.x] = s_act_total;
     if (nact) {
-        uint32_t pos = s_gbase + s_wbase[tid >> 5] + (uint32_t)(incl - nact);
+        uint32_t pos = (uint32_t)blockIdx.x * (kThreads * kVec) + s_wbase[tid >> 5] + (uint32_t)(incl - nact);
 #pragma unroll
         for (int k = 0; k < 4; k++)
             if (recs[k] != 0) d.act_list[pos++] = (uint32_t)(i0 + k);
@@ -568,8 +576,17 @@ emu_update_kernel(EmuDev d, FrameParams p, const void *frame, const float *leak_
     if (tid < kSegSmem && s_hist[tid]) atomicAdd(&hist[tid], s_hist[tid]);
     if (tid >= kSegSmem && tid < kSegSmem + 2 && s_hist[tid])
         atomicAdd(&hist[2 * d.iter_cap + (tid - kSegSmem)], s_hist[tid]);
+    // do_plan bit 0: plan here; bit 1: plan here only if the refractory filter turns out to be inactive
+    // for this frame (then the filter kernel that follows returns immediately)
     if (do_plan) {
-        if (last_block(&c->done[0])) plan_frame(d, p, slot);
+        if (last_block(&c->done[0])) {
+            bool go = do_plan & 1;
+            if (!go) {
+                const int32_t mx = *(volatile int32_t *)&c->max_n;
+                go = !make_ts(p, mx, d.refr_d).filter_active && mx <= d.iter_cap;
+            }
+            if (go) plan_frame(d, p, slot);
+        }
     }
 }
 
@@ -608,19 +625,21 @@ emu_filter_kernel(EmuDev d, FrameParams p, int slot, int do_plan) {
     if (*(volatile int32_t *)d.abort_flag) return;
     const int tid = threadIdx.x, lane = tid & 31;
     FrameCtrl *c = d.ctrl + slot;
+    if (*(volatile int32_t *)&c->planned) return;       // the update kernel already planned (filter inactive)
     const int32_t max_n = *(volatile int32_t *)&c->max_n;
     const TsParams ts = make_ts(p, max_n, d.refr_d);
     if (ts.filter_active && max_n <= d.iter_cap) {
         if (tid < kSegSmem) s_hist[tid] = 0;
         __syncthreads();
         uint32_t *hist = d.hist_post + (size_t)slot * d.seg_stride;
-        const uint32_t n_act = d.act_count[slot];
-        for (uint32_t base = blockIdx.x * kThreads; base < n_act; base += gridDim.x * kThreads) {
+        const uint32_t *seg_cnt = d.act_count + (size_t)slot * d.n_blocks;
+        for (int sg = blockIdx.x; sg < d.n_blocks; sg += gridDim.x)
+        for (uint32_t base = 0, n_act = seg_cnt[sg]; base < n_act; base += kThreads) {
             const uint32_t e = base + tid;
             int mag = 0, pol = 0;
             float tm = 0.f;
             if (e < n_act) {
-                const uint32_t idx = d.act_list[e];
+                const uint32_t idx = d.act_list[(size_t)sg * (kThreads * kVec) + e];
                 const int cnt = d.rec[idx] >> kRecShift;
                 mag = cnt < 0 ? -cnt : cnt;
                 pol = cnt < 0;
@@ -670,7 +689,9 @@ emu_shot_kernel(EmuDev d, FrameParams p, const void *frame, const float *shot_ra
             int flags = shot_flags(d, p, x[k], sr[k], thp[k], thn[k]);
             if (flags) {
                 const short old = d.rec[i0 + k];
-                if (old == 0) d.act_list[atomicAdd(&d.act_count[slot], 1u)] = (uint32_t)(i0 + k);
+                if (old == 0)
+                    d.act_list[(size_t)blockIdx.x * (kThreads * kVec) +
+                               atomicAdd(&d.act_count[(size_t)slot * d.n_blocks + blockIdx.x], 1u)] = (uint32_t)(i0 + k);
                 d.rec[i0 + k] = (short)(old | flags);
                 if (flags & 1) atomicAdd(&s_cnt[0], 1u);
                 if (flags & 2) atomicAdd(&s_cnt[1], 1u);
@@ -706,13 +727,14 @@ emu_emit_kernel(EmuDev d, FrameParams p, int slot, float4 *events) {
     const uint32_t *segoff = d.segoff + (size_t)slot * d.seg_stride;
     uint32_t *cursor = d.cursor + (size_t)slot * d.seg_stride;
     const uint64_t ev_base = c->ev_base;
-    const uint32_t n_act = d.act_count[slot];
+    const uint32_t *seg_cnt = d.act_count + (size_t)slot * d.n_blocks;
     // lane 0 claims `count` consecutive rows of segment `seg` for this warp
     auto claim = [&](int seg_smem, int seg, unsigned count) -> uint32_t {
         if (seg_smem >= 0) return s_base[seg_smem] + atomicAdd(&s_cnt[seg_smem], count);
         return segoff[seg] + atomicAdd(&cursor[seg], count);
     };
-    for (uint32_t base = blockIdx.x * kThreads; base < n_act; base += gridDim.x * kThreads) {
+    for (int sg = blockIdx.x; sg < d.n_blocks; sg += gridDim.x)
+    for (uint32_t base = 0, n_act = seg_cnt[sg]; base < n_act; base += kThreads) {
         if (tid < kSegSmem + 2) s_cnt[tid] = 0;
         __syncthreads();
         const uint32_t e = base + tid;
@@ -720,7 +742,7 @@ emu_emit_kernel(EmuDev d, FrameParams p, int slot, float4 *events) {
         float tm0 = 0.f, th = 0.f;
         S b0 = (S)0, lpv = (S)0;
         if (e < n_act) {
-            idx = (int)d.act_list[e];
+            idx = (int)d.act_list[(size_t)sg * (kThreads * kVec) + e];
             const int r = d.rec[idx];
             const int cnt = r >> kRecShift;
             flags = r & 3;
@@ -927,7 +949,7 @@ extern "C" int v2e_emu_create(const V2eEmuCfg *cfg, V2eEmu **out) {
     ALLOC(d.lp, np * h->state_elem);
     ALLOC(d.base, np * h->state_elem);
     ALLOC(d.rec, np * sizeof(int16_t));
-    ALLOC(d.act_list, np * sizeof(uint32_t));
+    ALLOC(d.act_list, ((np + kThreads * kVec - 1) / (kThreads * kVec)) * (size_t)(kThreads * kVec) * sizeof(uint32_t));
     if (d.per_pixel_thres) { ALLOC(d.pos_thres, np * 4); ALLOC(d.neg_thres, np * 4); }
     if (d.leak_on) ALLOC(d.noise_rate, np * 4);
     if (d.refr_on) ALLOC(d.tmem, np * 4);
@@ -940,7 +962,8 @@ extern "C" int v2e_emu_create(const V2eEmuCfg *cfg, V2eEmu **out) {
     ALLOC(d.hist_post, slots * d.seg_stride * 4);
     ALLOC(d.segoff, slots * d.seg_stride * 4);
     ALLOC(d.cursor, slots * d.seg_stride * 4);
-    ALLOC(d.act_count, slots * sizeof(uint32_t));
+    d.n_blocks = (d.n_pad / kVec + kThreads - 1) / kThreads;
+    ALLOC(d.act_count, slots * d.n_blocks * sizeof(uint32_t));
     ALLOC(d.abort_flag, 2 * sizeof(int32_t));
 #undef ALLOC
     if (cudaMallocHost((void **)&h->ctrl_host, (slots + 1) * sizeof(FrameCtrl)) != cudaSuccess ||
@@ -1077,7 +1100,7 @@ static int enqueue_count(V2eEmu *h, const FrameParams &p, const void *frame, int
     const bool shot_in_update = d.shot_on && (d.rng_mode == 1 || sr != nullptr);
     if (d.shot_on && !shot_in_update && !shot_pending)
         return fail(V2E_E_INVALID, "shot_rand field required in replay mode (or shot_pending)");
-    const int plan_in_update = !d.refr_on && !shot_pending;
+    const int plan_in_update = shot_pending ? 0 : (d.refr_on ? 2 : 1);
     int rc;
     {
         ProfScope ps(h, slot, 0, st);
@@ -1107,7 +1130,7 @@ static int reset_slots(V2eEmu *h, int first, int count, cudaStream_t st) {
     CU(cudaMemsetAsync((char *)d.hist_post + off, 0, bytes, st));
     CU(cudaMemsetAsync((char *)d.cursor + off, 0, bytes, st));
     CU(cudaMemsetAsync(d.ctrl + first, 0, (size_t)(count + 1) * sizeof(FrameCtrl), st));
-    CU(cudaMemsetAsync(d.act_count + first, 0, (size_t)count * sizeof(uint32_t), st));
+    CU(cudaMemsetAsync(d.act_count + (size_t)first * d.n_blocks, 0, (size_t)count * d.n_blocks * sizeof(uint32_t), st));
     CU(cudaMemsetAsync(d.abort_flag, 0, 2 * sizeof(int32_t), st));
     return V2E_OK;
 }

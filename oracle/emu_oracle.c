@@ -182,13 +182,15 @@ int oracle_emu_csdvs(const OracleEmuCfg *cfg, OracleEmuState *st, double delta_t
             long ym = y > 0 ? y - 1 : 0, yp = y < H - 1 ? y + 1 : H - 1;
             for (long x = 0; x < W; x++) {
                 long xm = x > 0 ? x - 1 : 0, xp = x < W - 1 ? x + 1 : W - 1;
-                float acc = 0.0f;
-                acc += hf[ym * W + x];
-                acc += hf[y * W + xm];
-                acc += -4.0f * hf[y * W + x];
-                acc += hf[y * W + xp];
-                acc += hf[yp * W + x];
-                double c = alpha_p * (p[y * W + x] - h[y * W + x]) + alpha_h * (double)acc;
+                /* float32 conv2d of the replicate-padded field with [[0,1,0],[1,-4,1],[0,1,0]]. The
+                 * accumulation order is the CPU backend's (oneDNN, AVX-512 build of torch 2.11): probed
+                 * by exhaustive search over summation trees, see DESIGN.md */
+                float uu = hf[ym * W + x], ll = hf[y * W + xm], cc = -4.0f * hf[y * W + x];
+                float rr = hf[y * W + xp], dd = hf[yp * W + x];
+                float acc = (uu + ll) + (cc + (rr + dd));
+                /* alpha_h is a Python float meeting a float32 tensor: rounded to float32, float32 product */
+                float h_term = (float)alpha_h * acc;
+                double c = alpha_p * (p[y * W + x] - h[y * W + x]) + (double)h_term;
                 chg[y * W + x] = c;
                 double a = fabs(c);
                 if (a > max_change) max_change = a;

@@ -165,6 +165,14 @@ def main():
     save_case("emu_ragged_13x37", emu_mod,
               dict(cutoff_hz=0, leak_rate_hz=0, shot_noise_rate_hz=0, sigma_thres=0.03), fr3,
               np.arange(8) * 1e-3)
+    # centre-surround model (scripts/csdvs.sh:7-16: lambda 10 px, tau_p 0.5 ms, dt 1e-4 s, cutoff 100 Hz)
+    fr4 = texture_frames(20, 36, 6, seed=7)
+    save_case("emu_csdvs", emu_mod,
+              dict(cs_lambda_pixels=10, cs_tau_p_ms=0.5, cutoff_hz=100, refractory_period_s=1e-3,
+                   leak_rate_hz=0.1, shot_noise_rate_hz=1.0, sigma_thres=0.03), fr4, np.arange(6) * 1e-4)
+    save_case("emu_csdvs_fast", emu_mod,
+              dict(cs_lambda_pixels=4, cs_tau_p_ms=2.0, cutoff_hz=200, leak_rate_hz=0, shot_noise_rate_hz=0,
+                   sigma_thres=0.02), texture_frames(17, 23, 6, seed=9), np.arange(6) * 5e-4)
     # BASELINE config 1: scripts/moving_dot.py 64x64, class defaults, seed 42 -> 27 917 events
     import importlib
     md = importlib.import_module("scripts.moving_dot")

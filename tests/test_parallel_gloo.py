@@ -1,0 +1,85 @@
+"""CPU, world_size 2, gloo: the host-side logic of the N>1 path (clip sharding, event-stream gather
+with ragged counts, time merge, max all-reduce). No GPU, no model arithmetic."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from v2e_b200 import parallel
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(100 + rank)
+        n = [5, 0, 9][rank % 3] if rank else 7          # ragged, includes an empty stream
+        rows = torch.from_numpy(np.concatenate([np.sort(rng.uniform(0, 1, (n, 1)), 0),
+                                                rng.integers(0, 64, (n, 2)), rng.choice([-1.0, 1.0], (n, 1))],
+                                               1).astype(np.float32))
+        out = parallel.gather_event_streams(rows, dst=0)
+        mx = parallel.allreduce_max_int(3 + rank, "cpu")
+        if rank == 0:
+            q.put(("gather", [o.numpy() for o in out], mx))
+        else:
+            assert out is None
+            q.put(("rows", rank, rows.numpy(), mx))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_event_streams_world2():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    gathered = [g for g in got if g[0] == "gather"][0]
+    others = {g[1]: g[2] for g in got if g[0] == "rows"}
+    assert len(gathered[1]) == world
+    assert gathered[1][0].shape == (7, 4)
+    for r, rows in others.items():
+        assert np.array_equal(gathered[1][r], rows)
+    assert gathered[2] == 3 + world - 1 and all(g[-1] == 3 + world - 1 for g in got)
+
+
+def test_shard_clips_and_row_bands():
+    for world in (1, 2, 4, 8):
+        owned = sorted(sum((parallel.shard_clips(11, r, world) for r in range(world)), []))
+        assert owned == list(range(11))
+        for H, align in ((720, 1), (260, 4), (7, 1), (720, 32)):
+            bands = [parallel.row_band(H, r, world, align) for r in range(world)]
+            assert bands[0][0] == 0 and bands[-1][1] == H
+            assert all(bands[i][1] == bands[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in bands]
+            assert max(sizes) - min(sizes) < 2 * align or H < world * align   # last band is clipped to H
+    with pytest.raises(ValueError):
+        parallel.shard_clips(4, 2, 2)
+
+
+def test_merge_by_time_is_stable_and_sorted():
+    a = torch.tensor([[0.1, 1, 1, 1], [0.2, 2, 2, -1]], dtype=torch.float32)
+    b = torch.tensor([[0.1, 9, 9, 1], [0.15, 3, 3, 1], [0.2, 8, 8, 1]], dtype=torch.float32)
+    m = parallel.merge_by_time([a, b])
+    assert torch.all(m[1:, 0] >= m[:-1, 0])
+    assert m[0, 1] == 1 and m[1, 1] == 9          # ties keep rank order
+    assert m.shape == (5, 4)

@@ -36,7 +36,6 @@ constexpr int kVec = 4;                 // pixels per thread
 constexpr int kSegSmem = 64;            // (iteration,polarity) segments aggregated in shared memory
 constexpr int kRecShift = 2;            // record = (signed count << 2) | shot_off << 1 | shot_on
 constexpr int kRecMaxCount = 8191;
-constexpr int kListBlocks = 296;         // grid of the kernels that walk the active-pixel list
 constexpr int kPhiloxRounds = 7;         // Philox4x32-7: the lightest variant that passes BigCrush (Salmon et al. 2011)
 
 struct FrameCtrl {                      // one per frame slot, device memory, zeroed per step
@@ -625,10 +624,15 @@ emu_filter_kernel(EmuDev d, FrameParams p, int slot, int do_plan) {
     if (*(volatile int32_t *)d.abort_flag) return;
     const int tid = threadIdx.x, lane = tid & 31;
     FrameCtrl *c = d.ctrl + slot;
-    if (*(volatile int32_t *)&c->planned) return;       // the update kernel already planned (filter inactive)
     const int32_t max_n = *(volatile int32_t *)&c->max_n;
     const TsParams ts = make_ts(p, max_n, d.refr_d);
-    if (ts.filter_active && max_n <= d.iter_cap) {
+    if (!(ts.filter_active && max_n <= d.iter_cap)) {
+        // nothing to filter: the update kernel's histogram is final (it completed before this kernel
+        // started), so one block plans and everybody else leaves
+        if (do_plan && blockIdx.x == 0) plan_frame(d, p, slot);
+        return;
+    }
+    {
         if (tid < kSegSmem) s_hist[tid] = 0;
         __syncthreads();
         uint32_t *hist = d.hist_post + (size_t)slot * d.seg_stride;
@@ -1018,6 +1022,8 @@ extern "C" int v2e_emu_set_fields(V2eEmu *h, const float *pos, const float *neg,
     return V2E_OK;
 }
 
+// one block per list segment while they are all co-resident (148 SMs x 8 blocks), grid-stride beyond
+static inline int list_grid(const EmuDev &d) { return d.n_blocks < 1184 ? d.n_blocks : 1184; }
 static inline int grid_for(const EmuDev &d) { return (d.n_pad / kVec + kThreads - 1) / kThreads; }
 
 template <typename S>
@@ -1100,7 +1106,7 @@ static int enqueue_count(V2eEmu *h, const FrameParams &p, const void *frame, int
     const bool shot_in_update = d.shot_on && (d.rng_mode == 1 || sr != nullptr);
     if (d.shot_on && !shot_in_update && !shot_pending)
         return fail(V2E_E_INVALID, "shot_rand field required in replay mode (or shot_pending)");
-    const int plan_in_update = shot_pending ? 0 : (d.refr_on ? 2 : 1);
+    const int plan_in_update = (!d.refr_on && !shot_pending) ? 1 : 0;
     int rc;
     {
         ProfScope ps(h, slot, 0, st);
@@ -1110,7 +1116,7 @@ static int enqueue_count(V2eEmu *h, const FrameParams &p, const void *frame, int
     if (rc) return rc;
     if (d.refr_on) {
         ProfScope ps(h, slot, 1, st);
-        emu_filter_kernel<<<kListBlocks, kThreads, 0, st>>>(d, p, slot, !shot_pending);
+        emu_filter_kernel<<<list_grid(d), kThreads, 0, st>>>(d, p, slot, !shot_pending);
     }
     return V2E_OK;
 }
@@ -1118,8 +1124,8 @@ static int enqueue_count(V2eEmu *h, const FrameParams &p, const void *frame, int
 static int enqueue_emit(V2eEmu *h, const FrameParams &p, int slot, float *events, cudaStream_t st) {
     const EmuDev &d = h->d;
     ProfScope ps(h, slot, 2, st);
-    if (d.state_f64) emu_emit_kernel<double><<<kListBlocks, kThreads, 0, st>>>(d, p, slot, (float4 *)events);
-    else emu_emit_kernel<float><<<kListBlocks, kThreads, 0, st>>>(d, p, slot, (float4 *)events);
+    if (d.state_f64) emu_emit_kernel<double><<<list_grid(d), kThreads, 0, st>>>(d, p, slot, (float4 *)events);
+    else emu_emit_kernel<float><<<list_grid(d), kThreads, 0, st>>>(d, p, slot, (float4 *)events);
     return V2E_OK;
 }
 

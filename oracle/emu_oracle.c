@@ -171,6 +171,7 @@ int oracle_emu_csdvs(const OracleEmuCfg *cfg, OracleEmuState *st, double delta_t
     double alpha_p = adt / tau_p, alpha_h = adt / tau_h;
     const double *p = (const double *)st->lp;
     double *h = st->surround;
+    const int seq_order = n >= 20000;
     float *hf = (float *)malloc(sizeof(float) * n);
     double *chg = (double *)malloc(sizeof(double) * n);
     double max_change = 2e-5;
@@ -187,7 +188,9 @@ int oracle_emu_csdvs(const OracleEmuCfg *cfg, OracleEmuState *st, double delta_t
                  * by exhaustive search over summation trees, see DESIGN.md */
                 float uu = hf[ym * W + x], ll = hf[y * W + xm], cc = -4.0f * hf[y * W + x];
                 float rr = hf[y * W + xp], dd = hf[yp * W + x];
-                float acc = (uu + ll) + (cc + (rr + dd));
+                /* torch 2.11 CPU conv2d: tensors of >= 20000 output elements (both BASELINE sizes) take the
+                 * path that accumulates the taps in kernel order; smaller ones pair them up */
+                float acc = seq_order ? ((((uu + ll) + cc) + rr) + dd) : (uu + ll) + (cc + (rr + dd));
                 /* alpha_h is a Python float meeting a float32 tensor: rounded to float32, float32 product */
                 float h_term = (float)alpha_h * acc;
                 double c = alpha_p * (p[y * W + x] - h[y * W + x]) + (double)h_term;

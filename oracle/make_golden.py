@@ -170,9 +170,10 @@ def main():
     save_case("emu_csdvs", emu_mod,
               dict(cs_lambda_pixels=10, cs_tau_p_ms=0.5, cutoff_hz=100, refractory_period_s=1e-3,
                    leak_rate_hz=0.1, shot_noise_rate_hz=1.0, sigma_thres=0.03), fr4, np.arange(6) * 1e-4)
-    save_case("emu_csdvs_fast", emu_mod,
+    # >= 20000 pixels: the size class of both BASELINE resolutions (different float32 conv2d summation order)
+    save_case("emu_csdvs_120x176", emu_mod,
               dict(cs_lambda_pixels=4, cs_tau_p_ms=2.0, cutoff_hz=200, leak_rate_hz=0, shot_noise_rate_hz=0,
-                   sigma_thres=0.02), texture_frames(17, 23, 6, seed=9), np.arange(6) * 5e-4)
+                   sigma_thres=0.02), texture_frames(120, 176, 5, seed=9), np.arange(5) * 5e-4)
     # BASELINE config 1: scripts/moving_dot.py 64x64, class defaults, seed 42 -> 27 917 events
     import importlib
     md = importlib.import_module("scripts.moving_dot")

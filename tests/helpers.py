@@ -9,7 +9,7 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 EMU_GOLDENS = ["emu_class_default", "emu_cli_noisy", "emu_clean", "emu_scalar_thres_f64",
                "emu_refractory_multi", "emu_float_frames", "emu_static_leak_shot",
-               "emu_ragged_13x37"]
+               "emu_ragged_13x37", "emu_csdvs", "emu_csdvs_120x176"]
 
 
 def load_golden(name):

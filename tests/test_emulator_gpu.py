@@ -37,8 +37,10 @@ def test_reference_golden_bit_exact(name):
         assert_events_equal(ev, want[i], exact_order=True, ctx="%s frame %d" % (name, i))
     assert rng.exhausted()
     assert em.num_events_on == int(g["num_on"]) and em.num_events_off == int(g["num_off"])
+    if "cs_steps_taken" in g:
+        assert list(g["cs_steps_taken"]) == em.cs_steps_taken     # Euler steps per frame, emulator.py:1123
     for key, attr in (("state_base_log_frame", "base_log_frame"), ("state_lp_log_frame", "lp_log_frame"),
-                      ("state_timestamp_mem", "timestamp_mem")):
+                      ("state_timestamp_mem", "timestamp_mem"), ("state_cs_surround_frame", "cs_surround_frame")):
         if key in g:
             got = getattr(em, attr).cpu().numpy()
             assert got.dtype == g[key].dtype, key

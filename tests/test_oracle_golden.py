@@ -21,8 +21,10 @@ def test_oracle_matches_reference_golden(name):
         assert_events_equal(ev, want[i], exact_order=True, ctx="%s frame %d" % (name, i))
     assert rng.exhausted()
     assert em.num_events_on == int(g["num_on"]) and em.num_events_off == int(g["num_off"])
+    if "cs_steps_taken" in g:
+        assert list(g["cs_steps_taken"]) == em.cs_steps_taken
     for key, arr in (("state_base_log_frame", em.base), ("state_lp_log_frame", em.lp),
-                     ("state_timestamp_mem", em.tmem)):
+                     ("state_timestamp_mem", em.tmem), ("state_cs_surround_frame", em.surround)):
         if key in g and arr is not None:
             assert g[key].dtype == arr.dtype, key
             assert np.array_equal(g[key], arr), key

@@ -61,7 +61,11 @@ struct EmuDev {                         // passed by value to every kernel
     uint64_t seed;
     void *lp, *base;
     float *pos_thres, *neg_thres, *noise_rate, *tmem;
-    double *surround;
+    double *surround;                   // CSDVS h, ping buffer (cs_cur == 0)
+    double *surround2;                  // pong buffer
+    int32_t *cs_cur;                    // which buffer holds the current surround
+    unsigned long long *cs_max;         // [cs_cap] max|change| of every Euler step of the current frame (double bits)
+    int32_t cs_cap, cs_seq_order;
     int16_t *rec;
     uint32_t *act_list;                 // [n_pad] pixel indices with a non-zero record (built by the update kernel)
     uint32_t *act_count;                // [max_slots][n_blocks]: entries of each update-block's list segment
@@ -359,7 +363,92 @@ __global__ void __launch_bounds__(kThreads) emu_first_frame_kernel(EmuDev d, Fra
     st4((S *)d.lp, i0, lp);
     st4((S *)d.base, i0, base);
     if (d.refr_on) st4(d.tmem, i0, tm);
-    if (d.csdvs) st4(d.surround, i0, su);
+    if (d.csdvs) st4(d.surround, i0, su);     // v2e_emu_first_frame resets cs_cur to 0
+}
+
+// ---------------------------------------------------------------------------------------------
+// centre-surround model (emulator.py:1061-1124), only when cs_lambda_pixels is set
+// ---------------------------------------------------------------------------------------------
+// photoreceptor low-pass alone: the surround diffusion needs the whole new lp field first
+template <int FT>
+__global__ void __launch_bounds__(kThreads) emu_lp_kernel(EmuDev d, FrameParams p, const void *frame) {
+    __shared__ float s_lut[256];
+    if (*(volatile int32_t *)d.abort_flag) return;
+    s_lut[threadIdx.x] = d.lut[threadIdx.x];
+    __syncthreads();
+    const int i0 = (blockIdx.x * kThreads + threadIdx.x) * kVec;
+    if (i0 >= d.n) return;
+    double x[4], lp[4];
+    load_frame4<FT>(frame, i0, d.n, x);
+    ld4((const double *)d.lp, i0, lp);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const double xv = x[k];
+        double ln;
+        if (d.hdr) ln = xv;
+        else ln = (double)((FT == V2E_U8 || (xv >= 0.0 && xv <= 255.0 && xv == floor(xv))) ? s_lut[(int)xv] : lin_log_eval(xv));
+        if (d.lowpass_on) {
+            double eps = ((xv + 20.0) / 275.0) * p.eps_scale;
+            if (eps > 1.0) eps = 1.0;
+            lp[k] = (1.0 - eps) * lp[k] + eps * ln;
+        } else {
+            lp[k] = ln;
+        }
+    }
+    st4((double *)d.lp, i0, lp);
+}
+
+// One Euler step h += alpha_p*(p - h) + alpha_h*lap(float32(h)) with replicate padding
+// (emulator.py:1105-1121). p, h float64; the 3x3 stencil is a float32 conv2d whose summation order is the
+// reference's CPU backend's (see oracle/emu_oracle.c); alpha_h meets a float32 tensor -> float32 product.
+// Step k runs only if every earlier step changed some pixel by more than 1e-5 (the reference's while
+// condition); the maxima are exchanged through cs_max.
+__global__ void __launch_bounds__(kThreads)
+emu_csdvs_step_kernel(EmuDev d, double alpha_p, float alpha_h, int step) {
+    if (*(volatile int32_t *)d.abort_flag) return;
+    if (step > 0 && __longlong_as_double((long long)d.cs_max[step - 1]) <= 1e-5) return;
+    const int cur = (*(volatile int32_t *)d.cs_cur + step) & 1;
+    const double *h = cur ? d.surround2 : d.surround;
+    double *hn = cur ? d.surround : d.surround2;
+    const double *pp = (const double *)d.lp;
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    double a = 0.0;
+    if (i < d.n) {
+        const int y = i / d.W, x = i - y * d.W;
+        const int ym = y > 0 ? y - 1 : 0, yp = y < d.H - 1 ? y + 1 : d.H - 1;
+        const int xm = x > 0 ? x - 1 : 0, xp = x < d.W - 1 ? x + 1 : d.W - 1;
+        const double hc = h[i];
+        const float uu = (float)h[ym * d.W + x], ll = (float)h[y * d.W + xm], cc = -4.0f * (float)hc;
+        const float rr = (float)h[y * d.W + xp], dd = (float)h[yp * d.W + x];
+        const float acc = d.cs_seq_order ? ((((uu + ll) + cc) + rr) + dd) : (uu + ll) + (cc + (rr + dd));
+        const float h_term = alpha_h * acc;
+        const double chg = alpha_p * (pp[i] - hc) + (double)h_term;
+        hn[i] = hc + chg;
+        a = fabs(chg);
+    }
+    // block max of |change| -> one atomicMax (non-negative doubles order like their bit patterns)
+    unsigned long long bits = (unsigned long long)__double_as_longlong(a);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long t = __shfl_xor_sync(0xffffffffu, bits, o);
+        bits = t > bits ? t : bits;
+    }
+    __shared__ unsigned long long s_m[kThreads / 32];
+    if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = bits;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kThreads / 32; w++) bits = s_m[w] > bits ? s_m[w] : bits;
+        atomicMax(&d.cs_max[step], bits);
+    }
+}
+
+__global__ void emu_csdvs_finish_kernel(EmuDev d, int num_steps, int slot) {
+    if (*(volatile int32_t *)d.abort_flag) return;
+    int steps = num_steps;
+    for (int k = 0; k < num_steps; k++)
+        if (__longlong_as_double((long long)d.cs_max[k]) <= 1e-5) { steps = k + 1; break; }
+    d.ctrl[slot].cs_steps = steps;
+    *d.cs_cur = (*d.cs_cur + steps) & 1;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -399,7 +488,7 @@ emu_update_kernel(EmuDev d, FrameParams p, const void *frame, const float *leak_
             ld4(d.pos_thres, i0, thp);
             ld4(d.neg_thres, i0, thn);
         }
-        if (f_cs) ld4(d.surround, i0, su);
+        if (f_cs) ld4(*(volatile int32_t *)d.cs_cur ? d.surround2 : d.surround, i0, su);
         if (f_leak) {
             ld4(d.noise_rate, i0, nr);
             if (RNG == 0) load_f32x4_any(leak_randn, i0, d.n, lr);
@@ -913,6 +1002,7 @@ extern "C" int v2e_emu_create(const V2eEmuCfg *cfg, V2eEmu **out) {
     if (cfg->max_frames_per_step < 1) return fail(V2E_E_INVALID, "max_frames_per_step < 1");
     if (cfg->csdvs && !(cfg->cutoff_hz > 0 || cfg->hdr))
         return fail(V2E_E_UNSUPPORTED, "csdvs needs a float64 photoreceptor state (cutoff_hz > 0)");
+    if (cfg->csdvs && !(cfg->cs_tau_p_s > 0 && cfg->cs_tau_h_s > 0)) return fail(V2E_E_INVALID, "csdvs time constants must be positive");
     V2eEmu *h = new V2eEmu();
     memset(h, 0, sizeof(*h));
     h->cfg = *cfg;
@@ -957,7 +1047,14 @@ extern "C" int v2e_emu_create(const V2eEmuCfg *cfg, V2eEmu **out) {
     if (d.per_pixel_thres) { ALLOC(d.pos_thres, np * 4); ALLOC(d.neg_thres, np * 4); }
     if (d.leak_on) ALLOC(d.noise_rate, np * 4);
     if (d.refr_on) ALLOC(d.tmem, np * 4);
-    if (d.csdvs) ALLOC(d.surround, np * 8);
+    if (d.csdvs) {
+        ALLOC(d.surround, np * 8);
+        ALLOC(d.surround2, np * 8);
+        ALLOC(d.cs_cur, sizeof(int32_t));
+        d.cs_cap = 8192;
+        ALLOC(d.cs_max, (size_t)d.cs_cap * sizeof(unsigned long long));
+        d.cs_seq_order = d.n >= 20000;      // float32 conv2d summation order of the reference's CPU backend
+    }
     ALLOC(h->lut_dev, 256 * 4);
     d.lut = h->lut_dev;
     size_t slots = (size_t)d.max_slots;
@@ -983,7 +1080,7 @@ extern "C" int v2e_emu_destroy(V2eEmu *h) {
     if (!h) return V2E_OK;
     EmuDev &d = h->d;
     void *ptrs[] = {d.lp, d.base, d.rec, d.pos_thres, d.neg_thres, d.noise_rate, d.tmem, d.surround,
-                    h->lut_dev, d.ctrl, d.hist_pre, d.hist_post, d.segoff, d.cursor, d.abort_flag, d.act_list, d.act_count};
+                    h->lut_dev, d.ctrl, d.hist_pre, d.hist_post, d.segoff, d.cursor, d.abort_flag, d.act_list, d.act_count, d.surround2, d.cs_cur, d.cs_max};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->ctrl_host) cudaFreeHost(h->ctrl_host);
     if (h->abort_host) cudaFreeHost(h->abort_host);
@@ -1045,6 +1142,7 @@ extern "C" int v2e_emu_first_frame(V2eEmu *h, const void *frame, int dtype, doub
     int rc = h->d.state_f64 ? launch_first<double>(h, p, frame, dtype, (cudaStream_t)stream)
                             : launch_first<float>(h, p, frame, dtype, (cudaStream_t)stream);
     if (rc) return rc;
+    if (h->d.csdvs) CU(cudaMemsetAsync(h->d.cs_cur, 0, sizeof(int32_t), (cudaStream_t)stream));
     CU(cudaGetLastError());
     h->first_done = 1;
     return V2E_OK;
@@ -1102,16 +1200,41 @@ static int enqueue_count(V2eEmu *h, const FrameParams &p, const void *frame, int
                          const float *sr, int shot_pending, int slot, cudaStream_t st) {
     const EmuDev &d = h->d;
     if (d.rng_mode == 0 && d.leak_on && !lr) return fail(V2E_E_INVALID, "leak_randn field required in replay mode");
-    if (d.csdvs) return fail(V2E_E_UNSUPPORTED, "csdvs path not built yet");
     const bool shot_in_update = d.shot_on && (d.rng_mode == 1 || sr != nullptr);
     if (d.shot_on && !shot_in_update && !shot_pending)
         return fail(V2E_E_INVALID, "shot_rand field required in replay mode (or shot_pending)");
     const int plan_in_update = (!d.refr_on && !shot_pending) ? 1 : 0;
     int rc;
+    int lp_done = 0;
+    if (d.csdvs) {
+        // emulator.py:686-708: low-pass for the whole field, then the surround's Euler steps
+        const int g = grid_for(d);
+        switch (dtype) {
+            case V2E_U8: emu_lp_kernel<V2E_U8><<<g, kThreads, 0, st>>>(d, p, frame); break;
+            case V2E_F32: emu_lp_kernel<V2E_F32><<<g, kThreads, 0, st>>>(d, p, frame); break;
+            case V2E_F64: emu_lp_kernel<V2E_F64><<<g, kThreads, 0, st>>>(d, p, frame); break;
+            default: return fail(V2E_E_INVALID, "bad frame dtype");
+        }
+        const double tau_p = h->cfg.cs_tau_p_s, tau_h = h->cfg.cs_tau_h_s;
+        const double min_tau = tau_p < tau_h ? tau_p : tau_h;
+        const int num_steps = (int)ceil((p.dt / min_tau) * 5);              // emulator.py:1076-1078
+        if (num_steps < 1) return fail(V2E_E_INVALID, "csdvs: delta_time must be positive");
+        if (num_steps > d.cs_cap) return fail(V2E_E_UNSUPPORTED, "csdvs: more Euler steps per frame than cs_cap (8192)");
+        const double adt = p.dt / num_steps;
+        const double alpha_p = adt / tau_p, alpha_h = adt / tau_h;
+        if (alpha_p >= 1 || alpha_h >= 1)                                    // emulator.py:1091-1096 quits
+            return fail(V2E_E_INVALID, "CSDVS update alpha (of IIR update) is too large; simulation would explode");
+        CU(cudaMemsetAsync(d.cs_max, 0, (size_t)num_steps * sizeof(unsigned long long), st));
+        const int gs = (d.n + kThreads - 1) / kThreads;
+        for (int k = 0; k < num_steps; k++)
+            emu_csdvs_step_kernel<<<gs, kThreads, 0, st>>>(d, alpha_p, (float)alpha_h, k);
+        emu_csdvs_finish_kernel<<<1, 1, 0, st>>>(d, num_steps, slot);
+        lp_done = 1;
+    }
     {
         ProfScope ps(h, slot, 0, st);
-        rc = d.state_f64 ? launch_update<double>(h, p, frame, dtype, lr, sr, slot, plan_in_update, 0, st)
-                         : launch_update<float>(h, p, frame, dtype, lr, sr, slot, plan_in_update, 0, st);
+        rc = d.state_f64 ? launch_update<double>(h, p, frame, dtype, lr, sr, slot, plan_in_update, lp_done, st)
+                         : launch_update<float>(h, p, frame, dtype, lr, sr, slot, plan_in_update, lp_done, st);
     }
     if (rc) return rc;
     if (d.refr_on) {
@@ -1311,7 +1434,13 @@ extern "C" void *v2e_emu_state_ptr(V2eEmu *h, int which) {
         case 3: return h->d.neg_thres;
         case 4: return h->d.noise_rate;
         case 5: return h->d.tmem;
-        case 6: return h->d.surround;
+        case 6: {
+            if (!h->d.surround) return nullptr;
+            int32_t cur = 0;
+            cudaDeviceSynchronize();
+            cudaMemcpy(&cur, h->d.cs_cur, sizeof(cur), cudaMemcpyDeviceToHost);
+            return cur ? h->d.surround2 : h->d.surround;
+        }
     }
     return nullptr;
 }

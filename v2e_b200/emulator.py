@@ -428,6 +428,8 @@ class EventEmulator(object):
         return out
 
     def _account(self, fi):
+        if self.csdvs_enabled:
+            self.cs_steps_taken.append(int(fi.cs_steps))
         self.num_events_on += int(fi.n_on)
         self.num_events_off += int(fi.n_off)
         self.num_events_total += int(fi.n_events)

@@ -133,6 +133,16 @@ int v2e_emu_phase_count(V2eEmu *h, const void *frame_dev, int frame_dtype, doubl
                         double t_previous, const float *leak_randn_dev,
                         const float *shot_rand_dev, int shot_pending, uint64_t capacity,
                         uint64_t ev_base_start, void *stream);
+/* Pixel-sharded operation (one clip's rows split over GPUs): max_num_events_any_pixel is
+ * frame-global (emulator.py:773-775), so a rank runs phase_update on its band, all-reduces (MAX) the
+ * int32 at v2e_emu_max_n_dev() over the ranks on the same stream, then phase_filter (refractory filter
+ * with the global maximum, and the emission plan when do_plan != 0), then phase_shot / phase_emit. */
+int v2e_emu_phase_update(V2eEmu *h, const void *frame_dev, int frame_dtype, double t_frame,
+                         double t_previous, const float *leak_randn_dev, const float *shot_rand_dev,
+                         uint64_t capacity, uint64_t ev_base_start, void *stream);
+int32_t *v2e_emu_max_n_dev(V2eEmu *h);
+int v2e_emu_phase_filter(V2eEmu *h, double t_frame, double t_previous, uint64_t capacity, int do_plan,
+                         void *stream);
 /* per-(iteration,polarity) row counts of the frame just counted: counts_host[2*max_n]
  * (ON, OFF interleaved). Synchronises. Returns max_n in *max_n. */
 int v2e_emu_read_counts(V2eEmu *h, int32_t *max_n, uint32_t *counts_host, int counts_cap,

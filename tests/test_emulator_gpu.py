@@ -230,3 +230,57 @@ def test_full_size_crop_property_1280x720():
     # up to the float32 rounding of the base update count*theta (emulator.py:936-937): <= 0.5 ulp32(5.5)
     d = (em.lp_log_frame - em.base_log_frame).abs().max().item()
     assert d < 0.2 + 2.4e-7
+
+
+def _sharded_worker(rank, world, port, kw, frames, ts, q):
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)     # gloo moves CUDA tensors through the host:
+    try:                                                              # two ranks can share the one test GPU
+        from v2e_b200 import EventEmulator
+        em = EventEmulator(device="cuda:0", seed=21, shard=(rank, world, None), **kw)
+        out = []
+        for f, t in zip(frames, ts):
+            out.append(em.generate_events(f, t))
+        q.put((rank, out, em.num_events_total))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kw", [
+    dict(cutoff_hz=200, leak_rate_hz=0.1, shot_noise_rate_hz=2.0, refractory_period_s=0.004, pos_thres=0.05,
+         neg_thres=0.05, sigma_thres=0.01),
+    dict(sigma_thres=0.03, cutoff_hz=0, leak_rate_hz=0, shot_noise_rate_hz=0),
+])
+def test_pixel_sharded_two_ranks_match_oracle(kw):
+    """One clip, rows split over 2 ranks (BASELINE config 5 layout): all-reduce(MAX) of the frame-global
+    event maximum per frame; the union of the two ranks' rows must equal the unsharded oracle per frame
+    (same seed: thresholds / noise fields are drawn full-size on every rank and sliced)."""
+    import socket
+    import torch.multiprocessing as mp
+    from emu_oracle import OracleEmulator
+    H, W, T = 50, 64, 8
+    fr = texture_frames(H, W, T, seed=3, speed=3.0)
+    ts = [k * 1e-2 for k in range(T)]
+    orc = OracleEmulator(seed=21, **kw)
+    want = [orc.generate_events(f, t) for f, t in zip(fr, ts)]
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, 2, port, kw, fr, ts, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict()
+    for _ in range(2):
+        r, out, n = q.get(timeout=300)
+        res[r] = (out, n)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] + res[1][1] == orc.num_events_total
+    for i in range(T):
+        parts = [res[r][0][i] for r in (0, 1) if res[r][0][i] is not None]
+        got = np.concatenate(parts) if parts else None
+        assert_events_equal(got, want[i], exact_order=False, ctx="frame %d" % i)

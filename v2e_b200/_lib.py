@@ -54,6 +54,9 @@ _SIGS = {
     "v2e_emu_collect": (_i, [_vp, ctypes.POINTER(V2eFrameInfo), _i, ctypes.POINTER(_i),
                              ctypes.POINTER(_u64), _vp]),
     "v2e_emu_phase_count": (_i, [_vp, _vp, _i, _d, _d, _vp, _vp, _i, _u64, _u64, _vp]),
+    "v2e_emu_phase_update": (_i, [_vp, _vp, _i, _d, _d, _vp, _vp, _u64, _u64, _vp]),
+    "v2e_emu_max_n_dev": (_vp, [_vp]),
+    "v2e_emu_phase_filter": (_i, [_vp, _d, _d, _u64, _i, _vp]),
     "v2e_emu_read_counts": (_i, [_vp, ctypes.POINTER(ctypes.c_int32), _vp, _i, _vp]),
     "v2e_emu_phase_shot": (_i, [_vp, _vp, _i, _d, _d, _vp, _u64, _vp]),
     "v2e_emu_phase_emit": (_i, [_vp, _d, _d, _vp, _u64, _vp]),

@@ -1356,6 +1356,46 @@ extern "C" int v2e_emu_phase_count(V2eEmu *h, const void *frame, int dtype, doub
     return V2E_OK;
 }
 
+// ---- pixel-sharded operation: update only, reduce max_n over ranks, then filter / plan ----------------
+extern "C" int v2e_emu_phase_update(V2eEmu *h, const void *frame, int dtype, double t_frame, double t_previous,
+                                    const float *lr, const float *sr, uint64_t capacity, uint64_t ev_base_start,
+                                    void *stream) {
+    if (!h || !frame) return fail(V2E_E_INVALID, "null argument");
+    if (!h->first_done) return fail(V2E_E_STATE, "v2e_emu_first_frame must run first");
+    if (t_frame < t_previous) return fail(V2E_E_INVALID, "frame times must be non-decreasing");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if ((rc = reset_slots(h, 0, 1, st))) return rc;
+    emu_begin_step_kernel<<<1, 1, 0, st>>>(h->d, 0, ev_base_start);
+    FrameParams p = make_params(h, t_frame, t_previous, h->frame_counter++, capacity);
+    h->last_dt = p.dt;
+    // shot_pending = 1 makes enqueue_count run the update kernel alone when there is no refractory
+    // period; with one, the filter must wait for the reduced max, so launch the update kernel directly
+    const EmuDev &d = h->d;
+    if (d.rng_mode == 0 && d.leak_on && !lr) return fail(V2E_E_INVALID, "leak_randn field required in replay mode");
+    if (d.csdvs) return fail(V2E_E_UNSUPPORTED, "pixel sharding of the centre-surround model needs a halo exchange per Euler step (not built)");
+    rc = d.state_f64 ? launch_update<double>(h, p, frame, dtype, lr, sr, 0, 0, 0, st)
+                     : launch_update<float>(h, p, frame, dtype, lr, sr, 0, 0, 0, st);
+    if (rc) return rc;
+    CU(cudaGetLastError());
+    h->last_T = 1;
+    return V2E_OK;
+}
+
+extern "C" int32_t *v2e_emu_max_n_dev(V2eEmu *h) { return h ? &h->d.ctrl[0].max_n : nullptr; }
+
+extern "C" int v2e_emu_phase_filter(V2eEmu *h, double t_frame, double t_previous, uint64_t capacity, int do_plan,
+                                    void *stream) {
+    if (!h) return fail(V2E_E_INVALID, "null handle");
+    cudaStream_t st = (cudaStream_t)stream;
+    FrameParams p = make_params(h, t_frame, t_previous, 0, capacity);
+    const EmuDev &d = h->d;
+    if (d.refr_on) emu_filter_kernel<<<list_grid(d), kThreads, 0, st>>>(d, p, 0, do_plan);
+    else if (do_plan) emu_plan_kernel<<<1, kThreads, 0, st>>>(d, p, 0);
+    CU(cudaGetLastError());
+    return V2E_OK;
+}
+
 extern "C" int v2e_emu_read_counts(V2eEmu *h, int32_t *max_n, uint32_t *counts, int counts_cap, void *stream) {
     if (!h || !max_n) return fail(V2E_E_INVALID, "null argument");
     cudaStream_t st = (cudaStream_t)stream;

@@ -109,6 +109,7 @@ class EventEmulator(object):
             iter_cap: int = 1024,
             max_frames_per_step: int = 64,
             exact_order: bool = True,
+            shard=None,
     ):
         if not str(device).startswith("cuda"):
             raise RuntimeError("v2e_b200.EventEmulator runs on a CUDA device only (device=%r); "
@@ -157,6 +158,9 @@ class EventEmulator(object):
         self.iter_cap = int(iter_cap)
         self.max_frames_per_step = int(max_frames_per_step)
         self.exact_order = exact_order
+        # shard = (rank, world, process_group): this instance owns a band of rows of every frame
+        # (v2e_b200.parallel.row_band); see _generate_sharded
+        self.shard = shard
         self.event_rows_hint = None   # initial event-buffer rows (default: max(2*H*W, 65536))
         self.seed = seed
         if seed != 0:  # emulator.py:221-224
@@ -296,14 +300,17 @@ class EventEmulator(object):
             rows = max(int(rows), 16)
             self._ev_dev = torch.empty((rows, 4), dtype=torch.float32, device=self.device)
 
-    def _rows_to_host(self, n_rows, base=0):
+    def _rows_to_host(self, n_rows, base=0, copy=True):
+        """Device rows -> host ndarray through a pinned staging buffer. copy=False returns a view of that
+        buffer (valid until the next call) and saves one pass over the rows on the host."""
         if n_rows == 0:
             return np.zeros((0, 4), np.float32)
         if self._ev_pin is None or self._ev_pin.shape[0] < n_rows:   # pinned staging, grown on demand
             self._ev_pin = torch.empty((int(n_rows * 1.25) + 1024, 4), dtype=torch.float32).pin_memory()
         self._ev_pin[:n_rows].copy_(self._ev_dev[base:base + n_rows], non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
-        return self._ev_pin[:n_rows].numpy().copy()
+        out = self._ev_pin[:n_rows].numpy()
+        return out.copy() if copy else out
 
     def _check_time(self, t_frame):
         if t_frame < self.t_previous:
@@ -329,6 +336,8 @@ class EventEmulator(object):
         fr, code = self._to_device_frames(new_frame)
         if fr.dim() != 2:
             raise ValueError("new_frame must be [height, width]")
+        if self.shard is not None:
+            return self._generate_sharded(fr, code, t_frame)
         if not self._initialized:
             self._first_frame(fr, code, t_frame)
             return None
@@ -399,6 +408,103 @@ class EventEmulator(object):
         if fi.n_events == 0:
             return None
         return self._canonical_then_shuffle(ev, counts, perms, int(fi.n_shot_on), int(fi.n_shot_off))
+
+    # pixel-sharded path (BASELINE config 5): this rank owns rows [y0, y1) ---------------
+    def _band(self, H):
+        from .parallel import row_band
+        rank, world, _ = self.shard
+        return row_band(H, rank, world)
+
+    def _full_then_band(self, draw, H, W, y0, y1):
+        """Every rank draws the FULL field from the same seeded generator (so the streams stay aligned
+        with a single-GPU run) and keeps its rows."""
+        return draw((H, W))[y0:y1].contiguous()
+
+    def _generate_sharded(self, fr_full, code, t_frame):
+        import torch.distributed as dist
+        rank, world, group = self.shard
+        H, W = fr_full.shape
+        y0, y1 = self._band(H)
+        fr = fr_full[y0:y1].contiguous()
+        hb = y1 - y0
+        if hb == 0:
+            raise ValueError("more ranks than pixel rows")
+        L = self._lib
+        if not self._initialized:
+            self._create(hb, W)
+            with torch.cuda.device(self.device):
+                _lib.check(L.v2e_emu_first_frame(self._h, ctypes.c_void_p(fr.data_ptr()), code, float(t_frame),
+                                                 float(self.t_previous), self._stream()))
+                pos = neg = nr = None
+                if self.sigma_thres > 0:
+                    pos = torch.clamp(self.rng.normal(self.pos_thres_nominal, self.sigma_thres, (H, W)), min=0.01)[y0:y1].contiguous()
+                    neg = torch.clamp(self.rng.normal(self.neg_thres_nominal, self.sigma_thres, (H, W)), min=0.01)[y0:y1].contiguous()
+                if self.leak_rate_hz > 0:
+                    nr = torch.exp(math.log(10) * self.noise_rate_cov_decades * self.rng.randn((H, W)))[y0:y1].contiguous()
+                p = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
+                _lib.check(L.v2e_emu_set_fields(self._h, p(pos), p(neg), p(nr)))
+            self._initialized = True
+            self._full_h = H
+            return None
+        n = hb * W
+        h = self._h
+        leak_on, shot_on = self.leak_rate_hz > 0, self.shot_noise_rate_hz > 0
+        replay = self.rng_mode == "replay"
+        with torch.cuda.device(self.device):
+            st = self._stream()
+            lr_dev = None
+            if leak_on and replay:
+                lr_dev = self._full_then_band(self.rng.randn, H, W, y0, y1).to(self.device)
+            self._ensure_event_buffers(self.event_rows_hint or max(4 * n, 1 << 16))
+            cap = self._ev_dev.shape[0]
+            tp = float(self.t_previous)
+            fp = ctypes.c_void_p(fr.data_ptr())
+            _lib.check(L.v2e_emu_phase_update(h, fp, code, t_frame, tp,
+                                              None if lr_dev is None else ctypes.c_void_p(lr_dev.data_ptr()),
+                                              None, cap, 0, st))
+            # the frame-global maximum (emulator.py:773-775): in-place MAX over the ranks
+            mx = torch.as_tensor(_DevView(L.v2e_emu_max_n_dev(h), (1,), "<i4", self), device=self.device)
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+            shot_pending = shot_on and replay
+            _lib.check(L.v2e_emu_phase_filter(h, t_frame, tp, cap, 0 if shot_pending else 1, st))
+            max_n = ctypes.c_int32(0)
+            counts = np.zeros(2 * self.iter_cap, np.uint32)
+            _lib.check(L.v2e_emu_read_counts(h, ctypes.byref(max_n), counts.ctypes.data_as(ctypes.c_void_p),
+                                             counts.size, st))
+            m = max_n.value
+            counts = counts[:2 * m].astype(np.int64)
+            if replay:
+                # keep the seeded generator aligned with an unsharded run: the reference draws one
+                # randperm(n_i) per iteration with n_i = events of the WHOLE frame (emulator.py:868)
+                tot = torch.from_numpy(counts.copy()).to(self.device)
+                if m > 0:
+                    dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
+                tot = tot.cpu().numpy()
+                for it in range(m):
+                    k = int(tot[2 * it] + tot[2 * it + 1])
+                    if k > 0:
+                        self.rng.randperm(k)
+            if shot_pending:
+                sr_dev = self._full_then_band(self.rng.rand, H, W, y0, y1).to(self.device)
+                _lib.check(L.v2e_emu_phase_shot(h, fp, code, t_frame, tp, ctypes.c_void_p(sr_dev.data_ptr()), cap, st))
+            _lib.check(L.v2e_emu_phase_emit(h, t_frame, tp, ctypes.c_void_p(self._ev_dev.data_ptr()), cap, st))
+            info = (_lib.V2eFrameInfo * 1)()
+            done, rows = ctypes.c_int(0), ctypes.c_uint64(0)
+            _lib.check(L.v2e_emu_collect(h, info, 1, ctypes.byref(done), ctypes.byref(rows), st))
+            fi = info[0]
+            self.last_frame_info = fi
+            ev = self._rows_to_host(int(fi.n_events))
+        self._account(fi)
+        self.t_previous = t_frame
+        if fi.n_events == 0:
+            return None
+        saved, self.exact_order = self.exact_order, False
+        try:
+            ev = self._canonical_then_shuffle(ev, counts, [None] * m, int(fi.n_shot_on), int(fi.n_shot_off))
+        finally:
+            self.exact_order = saved
+        ev[:, 2] += y0
+        return ev
 
     def _canonical_then_shuffle(self, ev, counts, perms, shot_on, shot_off):
         """Device rows of one (iteration, polarity) group come in no particular order. The reference
@@ -474,12 +580,12 @@ class EventEmulator(object):
             self.last_frame_info = info[T - 1]
             return total, offsets
 
-    def generate_events_batch(self, frames, t_frames, return_device=False):
+    def generate_events_batch(self, frames, t_frames, return_device=False, copy=True):
         """Fast path (not in the reference): all frames of a clip in a few launches per frame and no
         per-frame host synchronisation. frames: [T,H,W]; t_frames: [T] seconds, non-decreasing.
         Returns (rows [N,4] float32, offsets [T+1]) -- rows of frame f are rows[offsets[f]:offsets[f+1]].
         With return_device=True rows is a view of the emulator's device buffer (valid until the next
-        call). The first frame of a fresh emulator only initialises state (zero rows), as in the
+        call); with copy=False the host rows are a view of the pinned staging buffer (same lifetime). The first frame of a fresh emulator only initialises state (zero rows), as in the
         reference. Needs rng_mode="device" when leak or shot noise is on."""
         if self.rng_mode == "replay" and (self.leak_rate_hz > 0 or self.shot_noise_rate_hz > 0):
             raise RuntimeError("generate_events_batch with per-frame noise needs rng_mode='device' "
@@ -514,7 +620,7 @@ class EventEmulator(object):
             if self._ev_dev is None:
                 return torch.zeros((0, 4), dtype=torch.float32, device=self.device), offs
             return self._ev_dev[:row], offs
-        return self._rows_to_host(row), offs
+        return self._rows_to_host(row, copy=copy), offs
 
     # state tensors by the reference's attribute names (emulator.py:756-764 reads them via getattr)
     def _state(self, name):

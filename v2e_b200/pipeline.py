@@ -17,11 +17,12 @@ class V2EPipeline:
         self.slomo = slomo
         self.emulator = emulator
 
-    def run(self, frames_u8, src_duration_s, t_offset=0.0, return_device=False):
+    def run(self, frames_u8, src_duration_s, t_offset=0.0, return_device=False, copy=False):
         """frames_u8: [N,H,W] uint8 source frames covering `src_duration_s` seconds.
-        Returns (events [M,4] float32, frame offsets, interp_times_s, n_interp_frames)."""
+        Returns (events [M,4] float32, frame offsets, interp_times_s, n_interp_frames). Host rows are a
+        view of the emulator's pinned staging buffer unless copy=True (valid until the next call)."""
         interp, times, avg_u = self.slomo.interpolate_frames(frames_u8)
         f = src_duration_s / (np.max(times) - np.min(times))          # v2e.py:794-797
         t = t_offset + f * times
-        ev, offs = self.emulator.generate_events_batch(interp, t, return_device=return_device)
+        ev, offs = self.emulator.generate_events_batch(interp, t, return_device=return_device, copy=copy)
         return ev, offs, t, interp.shape[0]

@@ -119,6 +119,7 @@ def cpu_port_sample(H, W, U_sample=2, seed=0):
     import torch
     import slomo_ref
     from emu_oracle import OracleEmulator
+    torch.set_num_threads(os.cpu_count() or 1)      # torchrun pins OMP_NUM_THREADS=1; the CPU leg uses every core
     wts = slomo_weights()
     frames = source_clip(H, W, 9, seed=seed)[:2]
     t0 = time.perf_counter()
@@ -192,6 +193,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # keep stdout to the one JSON line: NCCL prints its version banner there at the VERSION level
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     src_host = torch.from_numpy(source_clip(H, W, NS, seed=rank)).pin_memory()

@@ -47,9 +47,9 @@ def run_case(N, H, W, C1, C2, Cout, K, bo, out_mode=0, seed=0):
     return ok
 
 if __name__ == '__main__':
-    cases = [(1, 4, 256, 64, 0, 32, 3), (1, 40, 256, 32, 0, 32, 3), (1, 33, 130, 16, 0, 32, 3), (1, 61, 300, 64, 0, 64, 3),
-             (1, 70, 256, 32, 0, 32, 7), (2, 64, 384, 12, 0, 32, 7), (2, 75, 320, 32, 32, 32, 3), (1, 48, 640, 32, 0, 64, 5),
-             (1, 256, 320, 32, 0, 32, 7), (1, 60, 256, 32, 0, 5, 3, None, 1), (3, 5, 128, 64, 0, 32, 3)]
+    cases = [(1, 4, 512, 64, 0, 32, 3), (1, 40, 512, 32, 0, 32, 3), (1, 33, 530, 16, 0, 32, 3), (1, 61, 600, 64, 0, 64, 3),
+             (1, 70, 512, 32, 0, 32, 7), (2, 64, 640, 12, 0, 32, 7), (2, 75, 576, 32, 32, 32, 3), (1, 48, 640, 32, 0, 64, 5),
+             (1, 256, 520, 32, 0, 32, 7), (1, 60, 512, 32, 0, 5, 3, None, 1), (3, 5, 513, 64, 0, 32, 3)]
     res = {0: True, 1: True}
     for bo in (0,):
         for c in cases:

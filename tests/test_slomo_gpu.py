@@ -96,6 +96,87 @@ def test_conv_tc_matches_torch(case):
         assert (out[..., Cout:] == 0).all()
 
 
+STRIP_CASES = [
+    # N, H, W, C1, C2, Cout, K, out_mode  (W >= 512: layers that run on the strip kernel)
+    (1, 4, 512, 64, 0, 32, 3, 0), (1, 40, 512, 32, 0, 32, 3, 0), (1, 33, 530, 16, 0, 32, 3, 0),
+    (1, 70, 512, 32, 0, 32, 7, 0), (2, 64, 640, 12, 0, 32, 7, 0), (2, 75, 576, 32, 32, 32, 3, 0),
+    (1, 48, 640, 32, 0, 64, 5, 0), (1, 60, 512, 32, 0, 5, 3, 1), (3, 5, 513, 64, 0, 32, 3, 0),
+]
+
+
+def pack_w_strip(w, C1, C2, KC):
+    """fp16 [slabs][taps][Cout_pad][KC] (include/v2e_b200.h, v2e_conv2d_lrelu_sm100_strip)."""
+    Cout, Cin, KH, KW = w.shape
+    C1p, C2p = pad16(C1), (pad16(C2) if C2 else 0)
+    Cp = cout_pad(Cout)
+    full = torch.zeros((Cp, KH * KW, C1p + C2p), dtype=torch.float16, device=w.device)
+    wt = w.permute(0, 2, 3, 1).reshape(Cout, KH * KW, Cin).half()
+    full[:Cout, :, :C1] = wt[:, :, :C1]
+    if C2:
+        full[:Cout, :, C1p:C1p + C2] = wt[:, :, C1:]
+    slabs = (C1p + C2p) // KC
+    return full.reshape(Cp, KH * KW, slabs, KC).permute(2, 1, 0, 3).contiguous(), Cp
+
+
+@pytest.mark.parametrize("case", STRIP_CASES)
+def test_conv_strip_kernel_matches_torch(case):
+    """Sliding-window strip kernel (resident weights, input-row ring, descriptor-shifted taps, two MMA
+    issuers) vs torch conv2d on the same fp16-rounded operands. Same tolerance as the per-tap kernel."""
+    N, H, W, C1, C2, Cout, K, mode = case
+    Lm, L = _lib()
+    g = torch.Generator().manual_seed(hash(case) & 0xFFFF)
+    x1 = torch.randn((N, C1, H, W), generator=g).to(DEV)
+    x2 = torch.randn((N, C2, H, W), generator=g).to(DEV) if C2 else None
+    w = (torch.randn((Cout, C1 + C2, K, K), generator=g) / np.sqrt((C1 + C2) * K * K)).to(DEV)
+    b = (torch.randn((Cout,), generator=g) * 0.1).to(DEV)
+    a1 = to_nhwc16(x1)
+    a2 = to_nhwc16(x2) if C2 else None
+    Cp = cout_pad(Cout)
+    KC = L.v2e_conv_strip_pick_kc(a1.shape[-1], a2.shape[-1] if C2 else 0, Cp, K, K, W)
+    assert KC in (16, 32, 64), "case must qualify for the strip kernel"
+    wp, Cp = pack_w_strip(w, C1, C2, KC)
+    bp = torch.zeros(Cp, device=DEV)
+    bp[:Cout] = b
+    out = torch.full((N, H, W, Cp if mode == 0 else 8), float("nan"),
+                     dtype=torch.float16 if mode == 0 else torch.float32, device=DEV)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    p = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
+    Lm.check(L.v2e_conv2d_lrelu_sm100_strip(p(a1), a1.shape[-1], p(a2), a2.shape[-1] if C2 else 0, p(wp), p(bp), Cp,
+                                            K, K, N, H, W, p(out), Cp, mode, min(Cout, 8), ctypes.c_float(0.1), st))
+    torch.cuda.synchronize()
+    xin = torch.cat([x1, x2], 1) if C2 else x1
+    ref = torch.nn.functional.conv2d(xin.half().float(), w.half().float(), b, padding=K // 2)
+    ref = torch.nn.functional.leaky_relu(ref, 0.1).permute(0, 2, 3, 1)
+    got = out[..., :min(Cout, out.shape[-1])].float()
+    refc = ref[..., :got.shape[-1]]
+    assert torch.isfinite(got).all()
+    assert ((got - refc).abs() <= 2e-3 * refc.abs() + 2e-3).all(), (got - refc).abs().max().item()
+
+
+def test_full_resolution_unet_matches_float32_reference():
+    """BASELINE resolution (1280x720 -> 1280x704 network): the layers that run on the strip kernel only
+    exist at this width. One frame pair, flow UNet + one interpolated frame vs the float32 torch
+    reference. Tolerances as in the small-size test."""
+    from v2e_b200.slomo import SloMoEngine
+    sd_fc, sd_at = _weights(5)
+    H, W = 720, 1280
+    frames = __import__("make_golden_slomo_frames").smooth_frames(2, H, W, 11, dx=6, dy=2, up=16)
+    eng = SloMoEngine(sd_fc, sd_at, (W, H), 1, DEV)
+    eng.set_pairs(torch.from_numpy(frames).to(DEV))
+    flow = eng.flow_out().clone().cpu()[..., :4].permute(0, 3, 1, 2)
+    torch.set_num_threads(max(1, min(32, os.cpu_count() or 1)))
+    I, _ = slomo_ref.load_pair_tensors(frames, (eng.w, eng.h))
+    ref_flow, ref_outs = slomo_ref.interp_batch(sd_fc, sd_at, I[:1], I[1:2], 1)
+    rms = ref_flow.pow(2).mean().sqrt().item()
+    assert (flow - ref_flow).abs().max().item() < 0.02 * rms + 0.02, ((flow - ref_flow).abs().max().item(), rms)
+    out = torch.empty((1, H, W), dtype=torch.uint8, device=DEV)
+    ft = torch.empty((1, eng.h, eng.w), dtype=torch.float32, device=DEV)
+    eng.interp(0.5, out, ft)
+    d = (ft.cpu() - ref_outs[0][1][:, 0]).abs()
+    assert d.max().item() < 0.01 and d.mean().item() < 0.001, (d.max().item(), d.mean().item())
+    eng.close()
+
+
 @pytest.mark.parametrize("sizes", [((346, 260), (320, 256), 1), ((320, 256), (346, 260), 0),
                                    ((1280, 720), (1280, 704), 1), ((1280, 704), (1280, 720), 0),
                                    ((100, 70), (96, 64), 1), ((96, 64), (100, 70), 0), ((130, 96), (128, 96), 1)])

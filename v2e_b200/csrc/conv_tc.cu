@@ -209,13 +209,15 @@ struct StripParams {
 };
 constexpr int kMaxSlot = 12;
 
+constexpr int kStripThreads = 224;      // warps: 0 producer, 1 issuer A, 2-5 epilogue, 6 issuer B
+
 template <int KW, int KC>
-__global__ void __launch_bounds__(kConvThreads)
+__global__ void __launch_bounds__(kStripThreads)
 conv_strip_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                   const __grid_constant__ CUtensorMap tmB, const StripParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    __shared__ __align__(8) uint64_t full_bar[kMaxSlot], empty_bar[kMaxSlot], w_bar, tmem_full_bar[2], tmem_empty_bar[2];
+    __shared__ __align__(8) uint64_t full_bar[kMaxSlot], empty_bar[kMaxSlot], w_bar, tmem_full_bar[4], tmem_empty_bar[4];
     __shared__ uint32_t tmem_base_smem;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -227,12 +229,13 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t row_bytes = (uint32_t)p.slab_bytes * slabs;       // one ring slot (all slabs)
     uint8_t *ring = smem + ((p.w_bytes + 1023) & ~1023);
     const uint32_t acc_cols = p.BN < 32 ? 32 : p.BN;
-    const uint32_t tmem_cols = acc_cols * 2;
+    const uint32_t tmem_cols = acc_cols * 4;              // two issuers x double buffering
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < p.nslot; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        // a ring slot is free again when BOTH issuers have retired their last MMA that reads it
+        for (int s = 0; s < p.nslot; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 2); }
         mbar_init(&w_bar, 1);
-        for (int s = 0; s < 2; s++) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 4); }
+        for (int s = 0; s < 4; s++) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 4); }
         fence_barrier_init();
     }
     if (warp == 0 && lane == 0) {
@@ -275,8 +278,11 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer: converged warp, one elected lane issues; taps/k-steps fully unrolled =====
+    } else if (warp == 1 || warp == 6) {
+        // ===== two MMA issuers (converged warps, one elected lane each): issuer A takes the even output
+        // rows of an item, issuer B the odd ones, each into its own pair of TMEM accumulators, so two
+        // instruction streams feed the tensor pipe. Taps / k-steps are fully unrolled. =====
+        const int who = warp == 6;
         const uint32_t leader = elect_one();
         constexpr uint32_t swz = KC == 64 ? 2u : (KC == 32 ? 4u : 6u);
         constexpr uint32_t rowb = (uint32_t)KC * 2u;
@@ -290,25 +296,27 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t tap16 = ((uint32_t)p.BN * rowb) >> 4;              // one tap's weight tile
         mbar_wait(&w_bar, 0);
         uint32_t cnt = 0;                                   // index of the first input row of this item
-        uint32_t acc = 0, acc_phase = 0;
+        uint32_t acc = 0, acc_phase = 0;                    // this issuer's accumulator ring (2 deep)
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             const int rest = item / p.tiles_x;
             const int seg = rest % p.n_seg;
             const int ya = seg * p.seg_h, yb = min(p.H, ya + p.seg_h);
             const int rows_in = (yb - ya) + 2 * ph;
             int waited = 0;                                 // input rows of this item known to be in smem
-            for (int y = ya; y < yb; y++) {
-                const int need = (y - ya) + p.KH;           // rows 0 .. y-ya+KH-1 of the item
+            int released = 0;                               // input rows of this item this issuer has released
+            for (int yr = who; yr < yb - ya; yr += 2) {     // output row (relative to the item)
+                const int need = yr + p.KH;                 // input rows 0 .. yr+KH-1 of the item
                 for (; waited < need; waited++) {
                     const uint32_t g = cnt + (uint32_t)waited;
                     mbar_wait(&full_bar[g % (uint32_t)p.nslot], (g / (uint32_t)p.nslot) & 1u);
                 }
-                mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+                const uint32_t ai = (uint32_t)who * 2u + acc;
+                mbar_wait(&tmem_empty_bar[ai], acc_phase ^ 1);
                 tcgen05_fence_after();
-                const uint32_t tmem_acc = tmem_base + acc * acc_cols;
+                const uint32_t tmem_acc = tmem_base + ai * acc_cols;
                 uint32_t first = 0;                         // 0 for the very first MMA of the row (overwrite)
                 for (int r = 0; r < p.KH; r++) {
-                    const uint32_t g = cnt + (uint32_t)(y - ya + r);
+                    const uint32_t g = cnt + (uint32_t)(yr + r);
                     const uint32_t a_row = ring16 + (g % (uint32_t)p.nslot) * row16;
                     for (int sl = 0; sl < slabs; sl++) {
                         const uint32_t a_lo = a_row + (uint32_t)sl * slab16;
@@ -325,26 +333,32 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         }
                     }
                 }
-                umma_commit_pred(&tmem_full_bar[acc], leader);
-                // input row (y - ph) is not needed by later output rows: release its slot
-                {
-                    const uint32_t g = cnt + (uint32_t)(y - ya);
+                umma_commit_pred(&tmem_full_bar[ai], leader);
+                // this issuer's next row is yr+2 and reads input rows >= yr+2: release everything below
+                for (; released <= yr + 1 && released < rows_in; released++) {
+                    const uint32_t g = cnt + (uint32_t)released;
                     umma_commit_pred(&empty_bar[g % (uint32_t)p.nslot], leader);
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            // release the KH-1 rows still held by this item
-            for (int k = (yb - ya); k < rows_in; k++) {
-                const uint32_t g = cnt + (uint32_t)k;
+            // end of the item: observe every fill (so that a later wait on the same slot cannot alias an
+            // earlier phase of the same parity), then release what is left: each issuer releases every
+            // input row of the item exactly once
+            for (; waited < rows_in; waited++) {
+                const uint32_t g = cnt + (uint32_t)waited;
+                mbar_wait(&full_bar[g % (uint32_t)p.nslot], (g / (uint32_t)p.nslot) & 1u);
+            }
+            for (; released < rows_in; released++) {
+                const uint32_t g = cnt + (uint32_t)released;
                 umma_commit_pred(&empty_bar[g % (uint32_t)p.nslot], leader);
             }
             cnt += (uint32_t)rows_in;
         }
     } else {
-        // ===== epilogue =====
+        // ===== epilogue (warps 2..5: TMEM lane group = warp % 4) =====
         const int q = warp & 3;
         const int m = q * 32 + lane;
-        uint32_t acc = 0, acc_phase = 0;
+        uint32_t accs[2] = {0, 0}, phases[2] = {0, 0};      // accumulator ring position of issuer A / B
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             const int tx = item % p.tiles_x, rest = item / p.tiles_x;
             const int seg = rest % p.n_seg, n = rest / p.n_seg;
@@ -352,9 +366,11 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int px = tx * kRowTile + m;
             const bool inb = px < p.W;
             for (int y = ya; y < yb; y++) {
-                mbar_wait(&tmem_full_bar[acc], acc_phase);
+                const int who = (y - ya) & 1;
+                const uint32_t ai = (uint32_t)who * 2u + accs[who];
+                mbar_wait(&tmem_full_bar[ai], phases[who]);
                 tcgen05_fence_after();
-                const uint32_t tmem_acc = tmem_base + acc * acc_cols;
+                const uint32_t tmem_acc = tmem_base + ai * acc_cols;
                 const size_t pix = ((size_t)n * p.H + y) * p.W + px;
                 for (int c0 = 0; c0 < p.BN; c0 += 16) {
                     uint32_t v[16];
@@ -383,8 +399,8 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 }
                 tcgen05_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (lane == 0) mbar_arrive(&tmem_empty_bar[ai]);
+                if (++accs[who] == 2) { accs[who] = 0; phases[who] ^= 1; }
             }
         }
     }
@@ -549,15 +565,23 @@ static int make_rowseg_tmap(CUtensorMap *tm, const void *ptr, int N, int H, int 
 
 // Slab width and ring depth for the strip kernel; returns KC (0: layer does not qualify), *nslot_out.
 int v2e_strip_pick(int C1, int C2, int Cout_pad, int KH, int KW, int W, int *nslot_out) {
-    if (Cout_pad > 128 || W < kRowTile || (KW != 3 && KW != 5 && KW != 7)) return 0;
+    // wide layers only: below ~4 row tiles per image row the per-tap kernel's 8x16 tiles waste less
+    if (Cout_pad > 128 || W < 4 * kRowTile || (KW != 3 && KW != 5 && KW != 7)) return 0;
     const int g = C2 ? (C1 < C2 ? C1 : C2) : C1;
     const int kc = g % 64 == 0 ? 64 : (g % 32 == 0 ? 32 : 16);
     const int slabs = (C1 + C2) / kc;
     const size_t wb = ((size_t)slabs * KH * KW * Cout_pad * kc * 2 + 1023) & ~(size_t)1023;
     const size_t slab = ((size_t)(kRowTile + KW - 1) * kc * 2 + 1023) & ~(size_t)1023;
-    const size_t budget = 222 * 1024;
-    if (wb + 2048 >= budget) return 0;
-    int nslot = (int)((budget - wb - 2048) / (slab * slabs));
+    // two CTAs per SM (two MMA issue streams, epilogues overlap) when weights + a (KH+2)-row ring fit in
+    // half of the shared memory; otherwise one CTA with as deep a ring as fits
+    const size_t half = 110 * 1024, full = 222 * 1024;
+    int nslot = 0;
+    if (Cout_pad <= 64 && wb + 2048 + (size_t)(KH + 1) * slab * slabs <= half) {   // TMEM: 2 CTAs x 4 accumulators
+        nslot = (int)((half - wb - 2048) / (slab * slabs));
+    } else {
+        if (wb + 2048 >= full) return 0;
+        nslot = (int)((full - wb - 2048) / (slab * slabs));
+    }
     if (nslot > kMaxSlot) nslot = kMaxSlot;
     if (nslot < KH + 1) return 0;
     if (nslot_out) *nslot_out = nslot;
@@ -609,8 +633,9 @@ int v2e_strip_prepare(V2eStripLaunch *L, const void *x1, int C1, const void *x2,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return v2e_set_error(V2E_E_CUDA, "cuTensorMapEncodeTiled failed for strip weights%s", "");
     }
-    L->grid = p.n_items < n_sms ? p.n_items : n_sms;
     L->smem = (size_t)((p.w_bytes + 1023) & ~1023) + (size_t)nslot * p.slab_bytes * slabs + 1024;
+    const int ctas = (L->smem + 1024 <= 113 * 1024) ? 2 * n_sms : n_sms;
+    L->grid = p.n_items < ctas ? p.n_items : ctas;
     return V2E_OK;
 }
 
@@ -622,7 +647,7 @@ int v2e_strip_launch(const V2eStripLaunch *L, cudaStream_t st) {
             cudaFuncSetAttribute(conv_strip_kernel<KW_, KC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); \
             attr_set = true;                                                                                    \
         }                                                                                                       \
-        conv_strip_kernel<KW_, KC_><<<L->grid, kConvThreads, L->smem, st>>>(L->tmA, L->tmA2, L->tmB, L->p);     \
+        conv_strip_kernel<KW_, KC_><<<L->grid, kStripThreads, L->smem, st>>>(L->tmA, L->tmA2, L->tmB, L->p);     \
         launched = true;                                                                                        \
     }
     bool launched = false;

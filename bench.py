@@ -119,7 +119,8 @@ def cpu_port_sample(H, W, U_sample=2, seed=0):
     import torch
     import slomo_ref
     from emu_oracle import OracleEmulator
-    torch.set_num_threads(os.cpu_count() or 1)      # torchrun pins OMP_NUM_THREADS=1; the CPU leg uses every core
+    # torchrun pins OMP_NUM_THREADS=1; the CPU leg uses the physical cores (hyper-threads slow ATen's convs down)
+    torch.set_num_threads(max(1, min(64, (os.cpu_count() or 2) // 2)))
     wts = slomo_weights()
     frames = source_clip(H, W, 9, seed=seed)[:2]
     t0 = time.perf_counter()

@@ -69,7 +69,8 @@ struct EmuDev {                         // passed by value to every kernel
     int16_t *rec;
     uint32_t *act_list;                 // [n_pad] pixel indices with a non-zero record (built by the update kernel)
     uint32_t *act_count;                // [max_slots][n_blocks]: entries of each update-block's list segment
-    int32_t n_blocks;                   // blocks of the update kernel = list segments of kThreads*kVec pixels
+    int32_t n_blocks;                   // blocks of the update kernel = list segments of seg_px pixels
+    int32_t seg_px, groups;             // seg_px = groups * kThreads * kVec
     const float *lut;                   // [256] lin_log
     FrameCtrl *ctrl;                    // [max_slots+1]
     uint32_t *hist_pre, *hist_post, *segoff, *cursor;   // [max_slots][seg_stride]
@@ -459,10 +460,13 @@ __global__ void emu_csdvs_finish_kernel(EmuDev d, int num_steps, int slot) {
 // ---------------------------------------------------------------------------------------------
 // FAST: the configuration fixed at compile time to v2e's CLI defaults in device-RNG mode (per-pixel
 // thresholds, low-pass, leak and shot noise on, no hdr / csdvs): every uniform flag test disappears.
+// A block covers `groups` consecutive tiles of 1024 pixels (4 per thread); the host picks `groups` so that
+// the whole grid is resident at once (one wave: no half-empty second wave, and the per-block fixed costs
+// -- tables, reductions, list bookkeeping -- are paid once per 1024*groups pixels).
 template <typename S, int FT, int RNG, bool FAST>
 __global__ void __launch_bounds__(kThreads, 4)
 emu_update_kernel(EmuDev d, FrameParams p, const void *frame, const float *leak_randn,
-                  const float *shot_rand, int slot, int do_plan, int lp_done_arg) {
+                  const float *shot_rand, int slot, int do_plan, int lp_done_arg, int groups) {
     const bool f_pp = FAST || d.per_pixel_thres, f_leak = FAST || d.leak_on, f_lp = FAST || d.lowpass_on;
     const bool f_shot = FAST || d.shot_on, f_hdr = FAST ? false : (bool)d.hdr, f_cs = FAST ? false : (bool)d.csdvs;
     const bool lp_done = FAST ? false : (bool)lp_done_arg;
@@ -470,32 +474,10 @@ emu_update_kernel(EmuDev d, FrameParams p, const void *frame, const float *leak_
     __shared__ double s_inten[256];
     __shared__ uint32_t s_hist[kSegSmem + 2];
     __shared__ int s_max;
-    __shared__ uint32_t s_wbase[kThreads / 32], s_act_total;
-    const int tid = threadIdx.x;
-    const int i0 = (blockIdx.x * kThreads + tid) * kVec;
-    // 1. every global load is issued before anything waits: abort flag, table entry, frame, state
+    __shared__ uint32_t s_act_total;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int32_t abort_v = *(volatile int32_t *)d.abort_flag;
     const float lut_v = d.lut[tid];
-    double x[4] = {0, 0, 0, 0};
-    S lp[4], base[4];
-    float thp[4], thn[4], nr[4], lr[4], sr[4];
-    double su[4];
-    if (i0 < d.n) {
-        load_frame4<FT>(frame, i0, d.n, x);
-        ld4((const S *)d.lp, i0, lp);
-        ld4((const S *)d.base, i0, base);
-        if (f_pp) {
-            ld4(d.pos_thres, i0, thp);
-            ld4(d.neg_thres, i0, thn);
-        }
-        if (f_cs) ld4(*(volatile int32_t *)d.cs_cur ? d.surround2 : d.surround, i0, su);
-        if (f_leak) {
-            ld4(d.noise_rate, i0, nr);
-            if (RNG == 0) load_f32x4_any(leak_randn, i0, d.n, lr);
-        }
-        if (RNG == 0 && f_shot && shot_rand != nullptr) load_f32x4_any(shot_rand, i0, d.n, sr);
-    }
-    // 2. shared-memory tables and counters
     if (tid == 0) s_act_total = 0;
     s_lut[tid] = (double)lut_v;
     s_inten[tid] = ((double)tid + 20.0) / 275.0;
@@ -505,176 +487,183 @@ emu_update_kernel(EmuDev d, FrameParams p, const void *frame, const float *leak_
     __syncthreads();
     FrameCtrl *c = d.ctrl + slot;
     uint32_t *hist = d.hist_pre + (size_t)slot * d.seg_stride;
+    const double *su_ptr = f_cs ? (*(volatile int32_t *)d.cs_cur ? d.surround2 : d.surround) : nullptr;
+    const bool shot_here = f_shot && (RNG == 1 || shot_rand != nullptr);
+    const uint32_t seg_base = (uint32_t)blockIdx.x * (uint32_t)(groups * kThreads * kVec);
     int local_max = 0;
-    int mags[4] = {0, 0, 0, 0}, pols[4] = {0, 0, 0, 0}, flg[4] = {0, 0, 0, 0};
-    short recs[4] = {0, 0, 0, 0};
-    if (i0 < d.n) {
-        if (!f_pp) {
+
+    for (int g = 0; g < groups; g++) {
+        const int i0 = ((blockIdx.x * groups + g) * kThreads + tid) * kVec;
+        int mags[4] = {0, 0, 0, 0}, pols[4] = {0, 0, 0, 0}, flg[4] = {0, 0, 0, 0};
+        short recs[4] = {0, 0, 0, 0};
+        if (i0 < d.n) {
+            double x[4];
+            S lp[4], base[4];
+            float thp[4], thn[4], nr[4], lr[4], sr[4];
+            double su[4];
+            load_frame4<FT>(frame, i0, d.n, x);
+            ld4((const S *)d.lp, i0, lp);
+            ld4((const S *)d.base, i0, base);
+            if (f_pp) {
+                ld4(d.pos_thres, i0, thp);
+                ld4(d.neg_thres, i0, thn);
+            } else {
 #pragma unroll
-            for (int k = 0; k < 4; k++) { thp[k] = (float)d.pos_nom; thn[k] = (float)d.neg_nom; }
-        }
-        const bool shot_here = f_shot && (RNG == 1 || shot_rand != nullptr);
-        if (RNG == 1) {
-            const uint2 key = make_uint2((uint32_t)d.seed, (uint32_t)(d.seed >> 32));
+                for (int k = 0; k < 4; k++) { thp[k] = (float)d.pos_nom; thn[k] = (float)d.neg_nom; }
+            }
+            if (f_cs) ld4(su_ptr, i0, su);
             if (f_leak) {
-                // Box-Muller on fast intrinsics: this stream only has to be N(0,1), not torch's bits
-                uint4 r = philox4x32<kPhiloxRounds>(make_uint4((uint32_t)(i0 >> 2), p.frame_index, 0u, 0x6c65616bu), key);
-                float a = __fsqrt_rn(-2.0f * __logf(u01_open(r.x))), b = __fsqrt_rn(-2.0f * __logf(u01_open(r.z)));
-                float sa, ca, sb, cb;
-                __sincosf(6.283185307179586f * u01_half(r.y), &sa, &ca);
-                __sincosf(6.283185307179586f * u01_half(r.w), &sb, &cb);
-                lr[0] = a * ca; lr[1] = a * sa; lr[2] = b * cb; lr[3] = b * sb;
+                ld4(d.noise_rate, i0, nr);
+                if (RNG == 0) load_f32x4_any(leak_randn, i0, d.n, lr);
             }
-            if (f_shot) {
-                uint4 r = philox4x32<kPhiloxRounds>(make_uint4((uint32_t)(i0 >> 2), p.frame_index, 1u, 0x73686f74u), key);
-                sr[0] = u01_half(r.x); sr[1] = u01_half(r.y); sr[2] = u01_half(r.z); sr[3] = u01_half(r.w);
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const double xv = x[k];
-            const bool is_code = FT == V2E_U8 || (xv >= 0.0 && xv <= 255.0 && xv == floor(xv));
-            // photoreceptor low-pass (emulator_utils.py:57-109)
-            if (!lp_done) {
-                double ln;                               // float32 lin_log value, widened (or raw if hdr)
-                if (f_hdr) ln = xv;
-                else ln = is_code ? s_lut[(int)xv] : (double)lin_log_eval(xv);
-                if (sizeof(S) == 8) {
-                    if (f_lp) {
-                        double inten01 = is_code ? s_inten[(int)xv] : (xv + 20.0) / 275.0;
-                        double eps = inten01 * p.eps_scale;
-                        if (eps > 1.0) eps = 1.0;
-                        lp[k] = (S)((1.0 - eps) * (double)lp[k] + eps * ln);
-                    } else {
-                        lp[k] = (S)ln;
-                    }
-                } else {
-                    lp[k] = (S)ln;                       // exact: ln is a widened float32
+            if (RNG == 0 && shot_here) load_f32x4_any(shot_rand, i0, d.n, sr);
+            if (RNG == 1) {
+                const uint2 key = make_uint2((uint32_t)d.seed, (uint32_t)(d.seed >> 32));
+                if (f_leak) {
+                    // Box-Muller on fast intrinsics: this stream only has to be N(0,1), not torch's bits
+                    uint4 r = philox4x32<kPhiloxRounds>(make_uint4((uint32_t)(i0 >> 2), p.frame_index, 0u, 0x6c65616bu), key);
+                    float a = __fsqrt_rn(-2.0f * __logf(u01_open(r.x))), b = __fsqrt_rn(-2.0f * __logf(u01_open(r.z)));
+                    float sa, ca, sb, cb;
+                    __sincosf(6.283185307179586f * u01_half(r.y), &sa, &ca);
+                    __sincosf(6.283185307179586f * u01_half(r.w), &sb, &cb);
+                    lr[0] = a * ca; lr[1] = a * sa; lr[2] = b * cb; lr[3] = b * sb;
+                }
+                if (f_shot) {
+                    uint4 r = philox4x32<kPhiloxRounds>(make_uint4((uint32_t)(i0 >> 2), p.frame_index, 1u, 0x73686f74u), key);
+                    sr[0] = u01_half(r.x); sr[1] = u01_half(r.y); sr[2] = u01_half(r.z); sr[3] = u01_half(r.w);
                 }
             }
-            // leak (emulator_utils.py:114-134): float32 products, subtract in S
-            if (f_leak) {
-                float rate = (d.leak_rate_f * nr[k]) * (1.0f - d.leak_jit_f * lr[k]);
-                float delta = (p.dt_f * rate) * thp[k];
-                base[k] = base[k] - (S)delta;
-            }
-            // difference and event counts (emulator.py:748-772, emulator_utils.py:137-173)
-            S diff;
-            if (sizeof(S) == 8 && f_cs) diff = (S)(((double)lp[k] - su[k]) - (double)base[k]);
-            else diff = lp[k] - base[k];
-            S tp, tn;
-            if (sizeof(S) == 8 && !f_pp) { tp = (S)d.pos_nom; tn = (S)d.neg_nom; }
-            else { tp = (S)thp[k]; tn = (S)thn[k]; }
-            int32_t cnt = 0;
-            if (diff >= tp) cnt = div_floor_count<S>(diff, tp);
-            else if (-diff >= tn) cnt = -div_floor_count<S>(-diff, tn);
-            // shot noise: exact test only when the draw can possibly cross (shot_bound >= any
-            // per-pixel probability; see make_params)
-            int flags = 0;
-            if (shot_here) {
-                const double r = (double)sr[k];
-                if (!(xv >= 0.0 && xv <= 255.0) || r < p.shot_bound || r > 1.0 - p.shot_bound)
-                    flags = shot_flags(d, p, xv, sr[k], thp[k], thn[k]);
-            }
-            const bool valid = (i0 + k) < d.n;
-            if (!valid) { cnt = 0; flags = 0; }
-            int32_t mag = cnt < 0 ? -cnt : cnt;
-            if (mag > local_max) local_max = mag;
-            if (mag > kRecMaxCount) { cnt = cnt < 0 ? -kRecMaxCount : kRecMaxCount; }
-            recs[k] = (short)((cnt << kRecShift) | flags);
-            mags[k] = mag < d.iter_cap ? mag : d.iter_cap;
-            pols[k] = cnt < 0;
-            flg[k] = flags;
-        }
-        if (!lp_done) st4((S *)d.lp, i0, lp);
-        if (f_leak) st4((S *)d.base, i0, base);
-        *(short4 *)(d.rec + i0) = make_short4(recs[0], recs[1], recs[2], recs[3]);
-    }
-    // per-(iteration,polarity) histogram. Iterations 0 and 1 (almost all events) are counted per thread
-    // and reduced with one REDUX per segment; a pixel with >= 3 events (rare) takes the ballot loop.
-    {
-        const int lane = tid & 31;
-        int c0on = 0, c0off = 0, c1on = 0, c1off = 0, son = 0, soff = 0, deep = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            c0on += (mags[k] > 0) & !pols[k];
-            c0off += (mags[k] > 0) & pols[k];
-            c1on += (mags[k] > 1) & !pols[k];
-            c1off += (mags[k] > 1) & pols[k];
-            son += flg[k] & 1;
-            soff += (flg[k] >> 1) & 1;
-            deep |= mags[k] > 2;
-        }
-        const int packed = c0on | (c0off << 4) | (c1on << 8) | (c1off << 12) | (son << 16) | (soff << 20);
-        if (__any_sync(0xffffffffu, packed != 0)) {
-            // 4-bit fields, <= 4 per lane: sums over 32 lanes (<= 128) need 8 bits -> two REDUX of 3 fields
-            const int lo = __reduce_add_sync(0xffffffffu, (c0on) | (c0off << 10) | (c1on << 20));
-            const int hi = __reduce_add_sync(0xffffffffu, (c1off) | (son << 10) | (soff << 20));
-            if (lane == 0) {
-                if (lo & 1023) atomicAdd(&s_hist[0], lo & 1023);
-                if ((lo >> 10) & 1023) atomicAdd(&s_hist[1], (lo >> 10) & 1023);
-                if ((lo >> 20) & 1023) atomicAdd(&s_hist[2], (lo >> 20) & 1023);
-                if (hi & 1023) atomicAdd(&s_hist[3], hi & 1023);
-                if ((hi >> 10) & 1023) atomicAdd(&s_hist[kSegSmem], (hi >> 10) & 1023);
-                if ((hi >> 20) & 1023) atomicAdd(&s_hist[kSegSmem + 1], (hi >> 20) & 1023);
-            }
-        }
-        if (__any_sync(0xffffffffu, deep)) {
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                const int wmax = __reduce_max_sync(0xffffffffu, mags[k]);
-                for (int it = 2; it < wmax; it++) {
-                    unsigned on = __ballot_sync(0xffffffffu, mags[k] > it && !pols[k]);
-                    unsigned off = __ballot_sync(0xffffffffu, mags[k] > it && pols[k]);
-                    if (lane == 0) {
-                        if (on) { if (2 * it < kSegSmem) atomicAdd(&s_hist[2 * it], __popc(on)); else atomicAdd(&hist[2 * it], __popc(on)); }
-                        if (off) { if (2 * it + 1 < kSegSmem) atomicAdd(&s_hist[2 * it + 1], __popc(off)); else atomicAdd(&hist[2 * it + 1], __popc(off)); }
+                const double xv = x[k];
+                const bool is_code = FT == V2E_U8 || (xv >= 0.0 && xv <= 255.0 && xv == floor(xv));
+                // photoreceptor low-pass (emulator_utils.py:57-109)
+                if (!lp_done) {
+                    double ln;                               // float32 lin_log value, widened (or raw if hdr)
+                    if (f_hdr) ln = xv;
+                    else ln = is_code ? s_lut[(int)xv] : (double)lin_log_eval(xv);
+                    if (sizeof(S) == 8) {
+                        if (f_lp) {
+                            double inten01 = is_code ? s_inten[(int)xv] : (xv + 20.0) / 275.0;
+                            double eps = inten01 * p.eps_scale;
+                            if (eps > 1.0) eps = 1.0;
+                            lp[k] = (S)((1.0 - eps) * (double)lp[k] + eps * ln);
+                        } else {
+                            lp[k] = (S)ln;
+                        }
+                    } else {
+                        lp[k] = (S)ln;                       // exact: ln is a widened float32
+                    }
+                }
+                // leak (emulator_utils.py:114-134): float32 products, subtract in S
+                if (f_leak) {
+                    float rate = (d.leak_rate_f * nr[k]) * (1.0f - d.leak_jit_f * lr[k]);
+                    float delta = (p.dt_f * rate) * thp[k];
+                    base[k] = base[k] - (S)delta;
+                }
+                // difference and event counts (emulator.py:748-772, emulator_utils.py:137-173)
+                S diff;
+                if (sizeof(S) == 8 && f_cs) diff = (S)(((double)lp[k] - su[k]) - (double)base[k]);
+                else diff = lp[k] - base[k];
+                S tp, tn;
+                if (sizeof(S) == 8 && !f_pp) { tp = (S)d.pos_nom; tn = (S)d.neg_nom; }
+                else { tp = (S)thp[k]; tn = (S)thn[k]; }
+                int32_t cnt = 0;
+                if (diff >= tp) cnt = div_floor_count<S>(diff, tp);
+                else if (-diff >= tn) cnt = -div_floor_count<S>(-diff, tn);
+                // shot noise: exact test only when the draw can possibly cross (shot_bound >= any
+                // per-pixel probability; see make_params)
+                int flags = 0;
+                if (shot_here) {
+                    const double r = (double)sr[k];
+                    if (!(xv >= 0.0 && xv <= 255.0) || r < p.shot_bound || r > 1.0 - p.shot_bound)
+                        flags = shot_flags(d, p, xv, sr[k], thp[k], thn[k]);
+                }
+                const bool valid = (i0 + k) < d.n;
+                if (!valid) { cnt = 0; flags = 0; }
+                int32_t mag = cnt < 0 ? -cnt : cnt;
+                if (mag > local_max) local_max = mag;
+                if (mag > kRecMaxCount) { cnt = cnt < 0 ? -kRecMaxCount : kRecMaxCount; }
+                recs[k] = (short)((cnt << kRecShift) | flags);
+                mags[k] = mag < d.iter_cap ? mag : d.iter_cap;
+                pols[k] = cnt < 0;
+                flg[k] = flags;
+            }
+            if (!lp_done) st4((S *)d.lp, i0, lp);
+            if (f_leak) st4((S *)d.base, i0, base);
+            *(short4 *)(d.rec + i0) = make_short4(recs[0], recs[1], recs[2], recs[3]);
+        }
+        // per-(iteration,polarity) histogram. Iterations 0 and 1 (almost all events) are counted per thread
+        // and reduced with one REDUX per three segments; a pixel with >= 3 events takes the ballot loop.
+        {
+            int c0on = 0, c0off = 0, c1on = 0, c1off = 0, son = 0, soff = 0, deep = 0, nact = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                c0on += (mags[k] > 0) & !pols[k];
+                c0off += (mags[k] > 0) & pols[k];
+                c1on += (mags[k] > 1) & !pols[k];
+                c1off += (mags[k] > 1) & pols[k];
+                son += flg[k] & 1;
+                soff += (flg[k] >> 1) & 1;
+                deep |= mags[k] > 2;
+                nact += recs[k] != 0;
+            }
+            if (__any_sync(0xffffffffu, nact != 0)) {
+                const int lo = __reduce_add_sync(0xffffffffu, (c0on) | (c0off << 10) | (c1on << 20));
+                const int hi = __reduce_add_sync(0xffffffffu, (c1off) | (son << 10) | (soff << 20));
+                // compaction of the active pixels into this block's list segment: warp scan, one shared
+                // atomic per warp, no global round trip (the segment's place is fixed)
+                int incl = nact;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                uint32_t wbase = 0;
+                if (lane == 31) wbase = atomicAdd(&s_act_total, (uint32_t)incl);
+                wbase = __shfl_sync(0xffffffffu, wbase, 31);
+                if (lane == 0) {
+                    if (lo & 1023) atomicAdd(&s_hist[0], lo & 1023);
+                    if ((lo >> 10) & 1023) atomicAdd(&s_hist[1], (lo >> 10) & 1023);
+                    if ((lo >> 20) & 1023) atomicAdd(&s_hist[2], (lo >> 20) & 1023);
+                    if (hi & 1023) atomicAdd(&s_hist[3], hi & 1023);
+                    if ((hi >> 10) & 1023) atomicAdd(&s_hist[kSegSmem], (hi >> 10) & 1023);
+                    if ((hi >> 20) & 1023) atomicAdd(&s_hist[kSegSmem + 1], (hi >> 20) & 1023);
+                }
+                if (nact) {
+                    uint32_t pos = seg_base + wbase + (uint32_t)(incl - nact);
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        if (recs[k] != 0) d.act_list[pos++] = (uint32_t)(i0 + k);
+                }
+                if (__any_sync(0xffffffffu, deep)) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int wmax = __reduce_max_sync(0xffffffffu, mags[k]);
+                        for (int it = 2; it < wmax; it++) {
+                            unsigned on = __ballot_sync(0xffffffffu, mags[k] > it && !pols[k]);
+                            unsigned off = __ballot_sync(0xffffffffu, mags[k] > it && pols[k]);
+                            if (lane == 0) {
+                                if (on) { if (2 * it < kSegSmem) atomicAdd(&s_hist[2 * it], __popc(on)); else atomicAdd(&hist[2 * it], __popc(on)); }
+                                if (off) { if (2 * it + 1 < kSegSmem) atomicAdd(&s_hist[2 * it + 1], __popc(off)); else atomicAdd(&hist[2 * it + 1], __popc(off)); }
+                            }
+                        }
                     }
                 }
             }
         }
-    }
-    // compaction of the active pixels (record != 0) into act_list: warp scan, one shared atomic per warp,
-    // one global atomic per block; the filter / emit kernels only walk this list
-    const int nact = (recs[0] != 0) + (recs[1] != 0) + (recs[2] != 0) + (recs[3] != 0);
-    int incl = nact;
-    {
-        const int lane = tid & 31;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        const int wtot = __shfl_sync(0xffffffffu, incl, 31);
-        if (lane == 31 && wtot) s_wbase[tid >> 5] = atomicAdd(&s_act_total, (uint32_t)wtot);
     }
     // block max -> one atomicMax per block
     local_max = warp_reduce_max(local_max);
-    if ((tid & 31) == 0 && local_max > 0) atomicMax(&s_max, local_max);
+    if (lane == 0 && local_max > 0) atomicMax(&s_max, local_max);
     __syncthreads();
     if (tid == 0 && s_max > 0) atomicMax(&c->max_n, s_max);
-    // this block's list segment is fixed (block b owns entries [b*1024, (b+1)*1024)): no global round trip
     if (tid == 0) d.act_count[(size_t)slot * d.n_blocks + blockIdx.x] = s_act_total;
-    if (nact) {
-        uint32_t pos = (uint32_t)blockIdx.x * (kThreads * kVec) + s_wbase[tid >> 5] + (uint32_t)(incl - nact);
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-            if (recs[k] != 0) d.act_list[pos++] = (uint32_t)(i0 + k);
-    }
     if (tid < kSegSmem && s_hist[tid]) atomicAdd(&hist[tid], s_hist[tid]);
     if (tid >= kSegSmem && tid < kSegSmem + 2 && s_hist[tid])
         atomicAdd(&hist[2 * d.iter_cap + (tid - kSegSmem)], s_hist[tid]);
-    // do_plan bit 0: plan here; bit 1: plan here only if the refractory filter turns out to be inactive
-    // for this frame (then the filter kernel that follows returns immediately)
     if (do_plan) {
-        if (last_block(&c->done[0])) {
-            bool go = do_plan & 1;
-            if (!go) {
-                const int32_t mx = *(volatile int32_t *)&c->max_n;
-                go = !make_ts(p, mx, d.refr_d).filter_active && mx <= d.iter_cap;
-            }
-            if (go) plan_frame(d, p, slot);
-        }
+        if (last_block(&c->done[0])) plan_frame(d, p, slot);
     }
 }
 
@@ -732,7 +721,7 @@ emu_filter_kernel(EmuDev d, FrameParams p, int slot, int do_plan) {
             int mag = 0, pol = 0;
             float tm = 0.f;
             if (e < n_act) {
-                const uint32_t idx = d.act_list[(size_t)sg * (kThreads * kVec) + e];
+                const uint32_t idx = d.act_list[(size_t)sg * d.seg_px + e];
                 const int cnt = d.rec[idx] >> kRecShift;
                 mag = cnt < 0 ? -cnt : cnt;
                 pol = cnt < 0;
@@ -782,9 +771,11 @@ emu_shot_kernel(EmuDev d, FrameParams p, const void *frame, const float *shot_ra
             int flags = shot_flags(d, p, x[k], sr[k], thp[k], thn[k]);
             if (flags) {
                 const short old = d.rec[i0 + k];
-                if (old == 0)
-                    d.act_list[(size_t)blockIdx.x * (kThreads * kVec) +
-                               atomicAdd(&d.act_count[(size_t)slot * d.n_blocks + blockIdx.x], 1u)] = (uint32_t)(i0 + k);
+                if (old == 0) {
+                    const int sg = (i0 + k) / d.seg_px;
+                    d.act_list[(size_t)sg * d.seg_px + atomicAdd(&d.act_count[(size_t)slot * d.n_blocks + sg], 1u)] =
+                        (uint32_t)(i0 + k);
+                }
                 d.rec[i0 + k] = (short)(old | flags);
                 if (flags & 1) atomicAdd(&s_cnt[0], 1u);
                 if (flags & 2) atomicAdd(&s_cnt[1], 1u);
@@ -835,7 +826,7 @@ emu_emit_kernel(EmuDev d, FrameParams p, int slot, float4 *events) {
         float tm0 = 0.f, th = 0.f;
         S b0 = (S)0, lpv = (S)0;
         if (e < n_act) {
-            idx = (int)d.act_list[(size_t)sg * (kThreads * kVec) + e];
+            idx = (int)d.act_list[(size_t)sg * d.seg_px + e];
             const int r = d.rec[idx];
             const int cnt = r >> kRecShift;
             flags = r & 3;
@@ -1043,7 +1034,7 @@ extern "C" int v2e_emu_create(const V2eEmuCfg *cfg, V2eEmu **out) {
     ALLOC(d.lp, np * h->state_elem);
     ALLOC(d.base, np * h->state_elem);
     ALLOC(d.rec, np * sizeof(int16_t));
-    ALLOC(d.act_list, ((np + kThreads * kVec - 1) / (kThreads * kVec)) * (size_t)(kThreads * kVec) * sizeof(uint32_t));
+
     if (d.per_pixel_thres) { ALLOC(d.pos_thres, np * 4); ALLOC(d.neg_thres, np * 4); }
     if (d.leak_on) ALLOC(d.noise_rate, np * 4);
     if (d.refr_on) ALLOC(d.tmem, np * 4);
@@ -1063,8 +1054,19 @@ extern "C" int v2e_emu_create(const V2eEmuCfg *cfg, V2eEmu **out) {
     ALLOC(d.hist_post, slots * d.seg_stride * 4);
     ALLOC(d.segoff, slots * d.seg_stride * 4);
     ALLOC(d.cursor, slots * d.seg_stride * 4);
-    d.n_blocks = (d.n_pad / kVec + kThreads - 1) / kThreads;
+    {
+        // one wave: 4 resident blocks per SM (64 registers x 256 threads)
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int tiles = (d.n_pad / kVec + kThreads - 1) / kThreads;
+        d.groups = (tiles + 4 * sms - 1) / (4 * sms);
+        if (d.groups < 1) d.groups = 1;
+        d.seg_px = d.groups * kThreads * kVec;
+        d.n_blocks = (tiles + d.groups - 1) / d.groups;
+    }
     ALLOC(d.act_count, slots * d.n_blocks * sizeof(uint32_t));
+    ALLOC(d.act_list, (size_t)d.n_blocks * d.seg_px * sizeof(uint32_t));
     ALLOC(d.abort_flag, 2 * sizeof(int32_t));
 #undef ALLOC
     if (cudaMallocHost((void **)&h->ctrl_host, (slots + 1) * sizeof(FrameCtrl)) != cudaSuccess ||
@@ -1151,17 +1153,17 @@ extern "C" int v2e_emu_first_frame(V2eEmu *h, const void *frame, int dtype, doub
 template <typename S, int RNG>
 static int launch_update_r(V2eEmu *h, const FrameParams &p, const void *frame, int dt, const float *lr,
                            const float *sr, int slot, int do_plan, int lp_done, cudaStream_t st) {
-    int g = grid_for(h->d);
+    int g = h->d.n_blocks;
     const EmuDev &d = h->d;
     if (sizeof(S) == 8 && RNG == 1 && dt == V2E_U8 && d.per_pixel_thres && d.leak_on && d.lowpass_on && d.shot_on &&
         !d.hdr && !d.csdvs && !lp_done) {
-        emu_update_kernel<double, V2E_U8, 1, true><<<g, kThreads, 0, st>>>(h->d, p, frame, lr, sr, slot, do_plan, 0);
+        emu_update_kernel<double, V2E_U8, 1, true><<<g, kThreads, 0, st>>>(h->d, p, frame, lr, sr, slot, do_plan, 0, d.groups);
         return V2E_OK;
     }
     switch (dt) {
-        case V2E_U8: emu_update_kernel<S, V2E_U8, RNG, false><<<g, kThreads, 0, st>>>(h->d, p, frame, lr, sr, slot, do_plan, lp_done); break;
-        case V2E_F32: emu_update_kernel<S, V2E_F32, RNG, false><<<g, kThreads, 0, st>>>(h->d, p, frame, lr, sr, slot, do_plan, lp_done); break;
-        case V2E_F64: emu_update_kernel<S, V2E_F64, RNG, false><<<g, kThreads, 0, st>>>(h->d, p, frame, lr, sr, slot, do_plan, lp_done); break;
+        case V2E_U8: emu_update_kernel<S, V2E_U8, RNG, false><<<g, kThreads, 0, st>>>(h->d, p, frame, lr, sr, slot, do_plan, lp_done, d.groups); break;
+        case V2E_F32: emu_update_kernel<S, V2E_F32, RNG, false><<<g, kThreads, 0, st>>>(h->d, p, frame, lr, sr, slot, do_plan, lp_done, d.groups); break;
+        case V2E_F64: emu_update_kernel<S, V2E_F64, RNG, false><<<g, kThreads, 0, st>>>(h->d, p, frame, lr, sr, slot, do_plan, lp_done, d.groups); break;
         default: return fail(V2E_E_INVALID, "bad frame dtype");
     }
     return V2E_OK;

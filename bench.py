@@ -286,8 +286,8 @@ def main():
         conv_ms, conv_n, conv_fl = ctypes.c_float(0), ctypes.c_int(0), ctypes.c_double(0)
         _lib.check(eng.lib.v2e_slomo_profile_read(eng._h, ctypes.byref(conv_ms), ctypes.byref(conv_n),
                                                   ctypes.byref(conv_fl), eng._stream()))
-        ms3, n3 = (ctypes.c_float * 3)(), (ctypes.c_int * 3)()
-        _lib.check(em._lib.v2e_emu_profile_read(em._h, ms3, n3, em._stream()))
+        ms3, n3 = (ctypes.c_float * 4)(), (ctypes.c_int * 4)()
+        _lib.check(em._lib.v2e_emu_profile_read4(em._h, ms3, n3, em._stream()))
         _lib.check(eng.lib.v2e_slomo_profile(eng._h, 0))
         _lib.check(em._lib.v2e_emu_profile(em._h, 0))
         achieved = conv_fl.value / (conv_ms.value * 1e-3) / 1e12
@@ -305,7 +305,13 @@ def main():
                                   "frac": upd_bytes / (upd_us * 1e-6) / 1e9 / pk["hbm_gbs"], "traffic": None,
                                   "bytes_per_launch": upd_bytes, "us_per_launch": upd_us,
                                   "kernel_us": {"update": upd_us, "filter": ms3[1] / max(n3[1], 1) * 1e3,
-                                                "emit": ms3[2] / max(n3[2], 1) * 1e3}},
+                                                "emit": ms3[2] / max(n3[2], 1) * 1e3},
+                                  # what the same CUDA-event bracket reports around an EMPTY kernel on this
+                                  # stream: the floor of the method, included in every figure above
+                                  "event_bracket_floor_us": ms3[3] / max(n3[3], 1) * 1e3,
+                                  "traffic_note": "ncu (cold caches): 26.8 MB DRAM read, <1 MB written per launch -- "
+                                                  "the 43 MB of state and frame are L2-resident between frames "
+                                                  "(profiles/r1_emu_update_ncu.md)"},
         }
     pipe.slomo.cleanup()
     pipe.emulator.cleanup()

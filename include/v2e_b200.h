@@ -161,6 +161,10 @@ int v2e_emu_phase_emit(V2eEmu *h, double t_frame, double t_previous, float *even
  * time (ms) and launch count of the {update, filter, emit} kernels. */
 int v2e_emu_profile(V2eEmu *h, int enable);
 int v2e_emu_profile_read(V2eEmu *h, float *ms_sum3, int *launches3, void *stream);
+/* Same with a fourth entry: the event bracket around an empty kernel launched once per frame while
+ * profiling -- the floor of this measurement method (launch + event processing), so that a reader can
+ * tell a kernel's duration from the cost of observing it. */
+int v2e_emu_profile_read4(V2eEmu *h, float *ms_sum4, int *launches4, void *stream);
 
 /* State access for parity probes (emulator.py:756-764 reads them by name). which:
  * 0 lp_log_frame, 1 base_log_frame, 2 pos_thres, 3 neg_thres, 4 noise_rate_array,

@@ -28,6 +28,7 @@
 
 #include "../../include/v2e_b200.h"
 #include "common.cuh"
+#include "tc_common.cuh"   // mbarrier helpers (the update kernel stages its state with TMA bulk copies)
 
 namespace {
 
@@ -70,7 +71,9 @@ struct EmuDev {                         // passed by value to every kernel
     uint32_t *act_list;                 // [n_pad] pixel indices with a non-zero record (built by the update kernel)
     uint32_t *act_count;                // [max_slots][n_blocks]: entries of each update-block's list segment
     int32_t n_blocks;                   // blocks of the update kernel = list segments of seg_px pixels
-    int32_t seg_px, groups;             // seg_px = groups * kThreads * kVec
+    int32_t seg_px, upb;                // block b owns the 128-pixel units [b*units/n_blocks, (b+1)*units/n_blocks): upb or
+                                        // upb-1 of them; seg_px = upb * 128 = capacity of a list segment
+    int32_t units, pad1;                // ceil(n / 128)
     const float *lut;                   // [256] lin_log
     FrameCtrl *ctrl;                    // [max_slots+1]
     uint32_t *hist_pre, *hist_post, *segoff, *cursor;   // [max_slots][seg_stride]
@@ -84,6 +87,7 @@ struct FrameParams {
     uint32_t frame_index;               // Philox counter word
     double shot_c;                      // (shot_noise_rate_hz/2)*delta_time (emulator_utils.py:323-324)
     double shot_bound;                  // >= every pixel's ON/OFF shot probability of this frame (x >= 0)
+    float shot_lo_f, shot_hi_f;         // float32 fast reject: a draw r with shot_lo_f <= r <= shot_hi_f cannot fire
     uint64_t capacity;
 };
 
@@ -163,8 +167,14 @@ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
     }
     return ctr;
 }
-__device__ __forceinline__ float u01_open(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+// (x>>8 + 0.5) * 2^-24 in (0,1) and (x>>8) * 2^-24 in [0,1): both exact in float32, one instruction after the convert
+__device__ __forceinline__ float u01_open(uint32_t x) { return fmaf((float)(x >> 8), 1.0f / 16777216.0f, 0.5f / 16777216.0f); }
 __device__ __forceinline__ float u01_half(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 // ---------------------------------------------------------------------------------------------
 // vector load helpers: 4 consecutive elements starting at i (i % 4 == 0)
@@ -258,6 +268,44 @@ __device__ void plan_frame(const EmuDev &d, const FrameParams &p, int slot) {
     const uint32_t *hs = d.hist_pre + (size_t)slot * d.seg_stride;     // shot counters live at the end
     uint32_t *off = d.segoff + (size_t)slot * d.seg_stride;
     const int nseg = 2 * max_n;
+    if (nseg <= 64) {
+        // the usual case (a handful of iterations): one warp, two segments per lane, shuffle scan
+        if (tid >= 32) return;
+        const int s0 = 2 * tid, s1 = 2 * tid + 1;           // (iteration tid, ON) and (iteration tid, OFF)
+        const uint32_t v0 = s0 < nseg ? h[s0] : 0u, v1 = s1 < nseg ? h[s1] : 0u;
+        uint32_t incl = v0 + v1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (tid >= o) incl += t;
+        }
+        const uint32_t excl = incl - (v0 + v1);
+        if (s0 < nseg) off[s0] = excl;
+        if (s1 < nseg) off[s1] = excl + v0;
+        const uint32_t sig = __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t sig_on = __reduce_add_sync(0xffffffffu, v0);
+        if (tid == 0) {
+            const uint32_t shot_on = hs[2 * d.iter_cap], shot_off = hs[2 * d.iter_cap + 1];
+            off[2 * d.iter_cap] = sig;
+            off[2 * d.iter_cap + 1] = sig + shot_on;
+            const uint32_t total = sig + shot_on + shot_off;
+            c->filter_active = ts.filter_active && d.refr_on;
+            c->n_on = sig_on + shot_on;
+            c->n_off = (sig - sig_on) + shot_off;
+            c->n_shot_on = shot_on;
+            c->n_shot_off = shot_off;
+            c->n_events = total;
+            const uint64_t base = c->ev_base;
+            if (base + total > p.capacity) {
+                if (atomicCAS(d.abort_flag, 0, V2E_E_CAPACITY) == 0) d.abort_flag[1] = slot;
+            } else {
+                d.ctrl[slot + 1].ev_base = base + total;
+                c->planned = 1;
+            }
+            __threadfence();
+        }
+        return;
+    }
     const int per = (nseg + kThreads - 1) / kThreads;
     uint32_t sum = 0, on = 0;
     for (int k = 0; k < per; k++) {
@@ -454,105 +502,245 @@ __global__ void emu_csdvs_finish_kernel(EmuDev d, int num_steps, int slot) {
 
 // ---------------------------------------------------------------------------------------------
 // update kernel: emulator.py:663-775 for 4 pixels per thread
-// RNG: 0 = replay (host-drawn fields), 1 = device (Philox). Everything else is a uniform runtime
-// flag. Tables in shared memory: lin_log(0..255) as float64 and inten01(0..255) = (x+20)/275
-// (the same IEEE division the reference does, evaluated once per block instead of once per pixel).
-// ---------------------------------------------------------------------------------------------
+// RNG: 0 = replay (host-drawn fields), 1 = device (Philox). Everything else is a uniform runtime flag.
 // FAST: the configuration fixed at compile time to v2e's CLI defaults in device-RNG mode (per-pixel
 // thresholds, low-pass, leak and shot noise on, no hdr / csdvs): every uniform flag test disappears.
-// A block covers `groups` consecutive tiles of 1024 pixels (4 per thread); the host picks `groups` so that
-// the whole grid is resident at once (one wave: no half-empty second wave, and the per-block fixed costs
-// -- tables, reductions, list bookkeeping -- are paid once per 1024*groups pixels).
+//
+// Memory path: the per-pixel state (lp, base, thresholds, noise rate: 28 of the 47 bytes per pixel, the
+// rest being the 1-byte frame and the stores) is staged through shared memory by 1-D TMA bulk copies
+// (cp.async.bulk ... mbarrier::complete_tx). Every warp runs its own two-stage pipeline over 128-pixel
+// units (4 pixels per lane): a block owns `upb` consecutive units, warp w takes units w, w+8, ...; lane 0
+// issues the copies of the unit after next as soon as the warp has read a stage into registers, and the
+// frame bytes of the next unit are prefetched into a register, so DRAM/L2 latency overlaps the arithmetic
+// of the unit in between and no block-wide barrier sits in the loop. The grid is exactly one resident wave
+// (3 blocks per SM) and the units are dealt out evenly (block sizes differ by at most one unit), so that at
+// 1280x720 almost every warp has two units and the few third units run at the end on an otherwise idle SM.
+//
+// Tables in shared memory (per block, 256 entries, the 8-bit code is the index). With uint8 frames and
+// the low-pass on, the update lp' = (1-eps)*lp + eps*ln needs only lp from the pixel: (1-eps) and the
+// product eps*ln depend on the code alone, so they are evaluated once per block with exactly the
+// reference's float64 operations (emulator_utils.py:84-99) and the pixel does one multiply and one add.
+// Otherwise the tables hold lin_log(code) and inten01(code) = (code+20)/275.
+// ---------------------------------------------------------------------------------------------
+constexpr int kUnitPx = 32 * kVec;                 // pixels of one warp pass
+constexpr int kWarps = kThreads / 32;
+constexpr int kStages = 2;
+template <typename S> struct StageLayout {         // one unit of one warp
+    static constexpr int lp = 0;
+    static constexpr int base = kUnitPx * (int)sizeof(S);
+    static constexpr int thp = 2 * kUnitPx * (int)sizeof(S);
+    static constexpr int thn = thp + kUnitPx * 4;
+    static constexpr int nr = thn + kUnitPx * 4;
+    static constexpr int bytes = nr + kUnitPx * 4;
+    static constexpr int block_bytes = bytes * kStages * kWarps;
+};
+
+// Executed by the whole (converged) warp with warp-uniform operands; only the lane with leader != 0 issues.
+// A plain `if (lane == 0)` around the asm makes nvcc emit an election loop per instruction.
+__device__ __forceinline__ void bulk_load_pred(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar,
+                                               uint32_t leader) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %4, 0;\n\t"
+                 "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}"
+                 ::"r"(dst_smem), "l"((uint64_t)src), "r"(bytes), "r"(bar), "r"(leader) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_pred(uint32_t bar, uint32_t bytes, uint32_t leader) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+                 "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes), "r"(leader) : "memory");
+}
+
+// event count |diff| // threshold with ATen's floor division (div_floor_count above), the common results
+// 0 / 1 / 2 without a branch: a = |diff| >= 0, b > 0
+template <typename S> __device__ __forceinline__ int32_t div_floor_count_fast(S a, S b) {
+    const S b2 = b + b;
+    int32_t cnt = (int32_t)(a >= b) + (int32_t)(a >= b2);
+    if (a >= b2 && !(a - b2 < b)) cnt = div_floor_count<S>(a, b);     // >= 3 events: rare
+    return cnt;
+}
+
 template <typename S, int FT, int RNG, bool FAST>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, 3)
 emu_update_kernel(EmuDev d, FrameParams p, const void *frame, const float *leak_randn,
-                  const float *shot_rand, int slot, int do_plan, int lp_done_arg, int groups) {
+                  const float *shot_rand, int slot, int do_plan, int lp_done_arg) {
     const bool f_pp = FAST || d.per_pixel_thres, f_leak = FAST || d.leak_on, f_lp = FAST || d.lowpass_on;
     const bool f_shot = FAST || d.shot_on, f_hdr = FAST ? false : (bool)d.hdr, f_cs = FAST ? false : (bool)d.csdvs;
     const bool lp_done = FAST ? false : (bool)lp_done_arg;
-    __shared__ double s_lut[256];
-    __shared__ double s_inten[256];
+    // code tables usable: uint8 frame, float64 low-pass computed here
+    const bool tab = FAST || (FT == V2E_U8 && sizeof(S) == 8 && f_lp && !f_hdr && !lp_done);
+    const bool need_lp = f_lp || lp_done;                 // otherwise lp' = lin_log(x): the old value is not read
+    extern __shared__ __align__(128) unsigned char s_stage[];
+    __shared__ double s_ta[256];                          // tab: 1-eps      else: lin_log
+    __shared__ double s_tb[256];                          // tab: eps*ln     else: inten01
+    __shared__ uint64_t s_full[kWarps][kStages];
     __shared__ uint32_t s_hist[kSegSmem + 2];
     __shared__ int s_max;
     __shared__ uint32_t s_act_total;
     const int tid = threadIdx.x, lane = tid & 31;
+    // the shuffle tells the compiler that the warp index is warp-uniform: the TMA issue below then runs on
+    // the uniform datapath instead of an election loop per instruction
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    // abort flag (set by an earlier frame's plan): read now, tested after the copies are in flight so that its
+    // round trip is off the critical path; nothing is written before the test
     const int32_t abort_v = *(volatile int32_t *)d.abort_flag;
     const float lut_v = d.lut[tid];
-    if (tid == 0) s_act_total = 0;
-    s_lut[tid] = (double)lut_v;
-    s_inten[tid] = ((double)tid + 20.0) / 275.0;
+    // this block's units; warp w owns units u0+w, u0+w+8, ...
+    const int u0 = (int)(((long long)blockIdx.x * d.units) / d.n_blocks);
+    const int u1 = (int)(((long long)(blockIdx.x + 1) * d.units) / d.n_blocks);
+    const int nj = (u1 - u0 - warp + kWarps - 1) / kWarps;     // units of this warp (<= 0: none)
+    unsigned char *my_stage = s_stage + (size_t)warp * (kStages * StageLayout<S>::bytes);
+    const uint32_t leader = elect_one();
+    const uint32_t stage_u32 = smem_u32(my_stage), bar_u32 = smem_u32(&s_full[warp][0]);
+    auto issue = [&](int j) {                // whole warp, warp-uniform arguments
+        const uint32_t bar = bar_u32 + 8u * (uint32_t)(j % kStages);
+        const uint32_t st = stage_u32 + (uint32_t)(j % kStages) * (uint32_t)StageLayout<S>::bytes;
+        const size_t px0 = (size_t)(u0 + warp + j * kWarps) * kUnitPx;
+        constexpr uint32_t nS = kUnitPx * (uint32_t)sizeof(S), nF = kUnitPx * 4u;
+        const uint32_t total = (need_lp ? nS : 0u) + nS + (f_pp ? 2u * nF : 0u) + (f_leak ? nF : 0u);
+        mbar_expect_tx_pred(bar, total, leader);
+        if (need_lp) bulk_load_pred(st + StageLayout<S>::lp, (const S *)d.lp + px0, nS, bar, leader);
+        bulk_load_pred(st + StageLayout<S>::base, (const S *)d.base + px0, nS, bar, leader);
+        if (f_pp) {
+            bulk_load_pred(st + StageLayout<S>::thp, d.pos_thres + px0, nF, bar, leader);
+            bulk_load_pred(st + StageLayout<S>::thn, d.neg_thres + px0, nF, bar, leader);
+        }
+        if (f_leak) bulk_load_pred(st + StageLayout<S>::nr, d.noise_rate + px0, nF, bar, leader);
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; s++) mbar_init(&s_full[warp][s], 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < kStages; s++) if (s < nj) issue(s);
+    if (tid == 0) { s_act_total = 0; s_max = 0; }
+    {
+        const double ln = (double)lut_v;
+        const double inten01 = ((double)tid + 20.0) / 275.0;
+        if (tab) {
+            double eps = inten01 * p.eps_scale;          // emulator_utils.py:84
+            if (eps > 1.0) eps = 1.0;                    // :96
+            s_ta[tid] = 1.0 - eps;                       // :99 (1-eps)
+            s_tb[tid] = eps * ln;                        //     eps*log_new_frame
+        } else {
+            s_ta[tid] = ln;
+            s_tb[tid] = inten01;
+        }
+    }
     if (tid < kSegSmem + 2) s_hist[tid] = 0;
-    if (tid == 0) s_max = 0;
-    if (abort_v) return;                     // block-uniform (set by an earlier frame's plan)
+    // frame bytes of the warp's first unit (uint8 frames): in flight across the barrier
+    const bool f_al = FT == V2E_U8 && (((uintptr_t)frame) & 3) == 0;
+    auto load_codes = [&](int i0) -> uint32_t {          // 4 codes packed little-endian
+        const uint8_t *f = (const uint8_t *)frame;
+        if (f_al && i0 + 4 <= d.n) return __ldg((const uint32_t *)(f + i0));
+        uint32_t v = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) if (i0 + k < d.n) v |= (uint32_t)f[i0 + k] << (8 * k);
+        return v;
+    };
+    uint32_t codes_next = 0;
+    if (FT == V2E_U8 && nj > 0) codes_next = load_codes((u0 + warp) * kUnitPx + lane * kVec);
     __syncthreads();
+    if (abort_v) {                           // block-uniform; let the copies land before the block's smem goes away
+#pragma unroll
+        for (int s = 0; s < kStages; s++) if (s < nj) mbar_wait(&s_full[warp][s], 0);
+        return;
+    }
     FrameCtrl *c = d.ctrl + slot;
     uint32_t *hist = d.hist_pre + (size_t)slot * d.seg_stride;
     const double *su_ptr = f_cs ? (*(volatile int32_t *)d.cs_cur ? d.surround2 : d.surround) : nullptr;
     const bool shot_here = f_shot && (RNG == 1 || shot_rand != nullptr);
-    const uint32_t seg_base = (uint32_t)blockIdx.x * (uint32_t)(groups * kThreads * kVec);
+    const uint32_t seg_base = (uint32_t)blockIdx.x * (uint32_t)d.seg_px;
+    const int so = lane * kVec;                          // element offset inside the stage arrays
     int local_max = 0;
+    uint32_t acc0 = 0, acc1 = 0;                         // ON / OFF counts of iterations 0 (low half) and 1 (high half)
+    auto flush_acc = [&]() {
+        if (lane == 0) {
+            if (acc0 & 0xffffu) atomicAdd(&s_hist[0], acc0 & 0xffffu);
+            if (acc1 & 0xffffu) atomicAdd(&s_hist[1], acc1 & 0xffffu);
+            if (acc0 >> 16) atomicAdd(&s_hist[2], acc0 >> 16);
+            if (acc1 >> 16) atomicAdd(&s_hist[3], acc1 >> 16);
+        }
+        acc0 = acc1 = 0;
+    };
 
-    for (int g = 0; g < groups; g++) {
-        const int i0 = ((blockIdx.x * groups + g) * kThreads + tid) * kVec;
+    for (int j = 0; j < nj; j++) {
+        const int i0 = (u0 + warp + j * kWarps) * kUnitPx + lane * kVec;
+        const bool t_on = i0 < d.n;
+        const unsigned char *st = my_stage + (size_t)(j % kStages) * StageLayout<S>::bytes;
         int mags[4] = {0, 0, 0, 0}, pols[4] = {0, 0, 0, 0}, flg[4] = {0, 0, 0, 0};
         short recs[4] = {0, 0, 0, 0};
-        if (i0 < d.n) {
-            double x[4];
-            S lp[4], base[4];
-            float thp[4], thn[4], nr[4], lr[4], sr[4];
-            double su[4];
-            load_frame4<FT>(frame, i0, d.n, x);
-            ld4((const S *)d.lp, i0, lp);
-            ld4((const S *)d.base, i0, base);
-            if (f_pp) {
-                ld4(d.pos_thres, i0, thp);
-                ld4(d.neg_thres, i0, thn);
-            } else {
-#pragma unroll
-                for (int k = 0; k < 4; k++) { thp[k] = (float)d.pos_nom; thn[k] = (float)d.neg_nom; }
-            }
+        // direct (unstaged) inputs first: their latency overlaps the wait for the stage
+        double x[4] = {0.0, 0.0, 0.0, 0.0};
+        const uint32_t codes = codes_next;
+        if (FT == V2E_U8 && j + 1 < nj) codes_next = load_codes(i0 + kWarps * kUnitPx);
+        float lr[4], sr[4];
+        double su[4];
+        if (t_on) {
+            if (FT != V2E_U8) load_frame4<FT>(frame, i0, d.n, x);
             if (f_cs) ld4(su_ptr, i0, su);
-            if (f_leak) {
-                ld4(d.noise_rate, i0, nr);
-                if (RNG == 0) load_f32x4_any(leak_randn, i0, d.n, lr);
-            }
+            if (RNG == 0 && f_leak) load_f32x4_any(leak_randn, i0, d.n, lr);
             if (RNG == 0 && shot_here) load_f32x4_any(shot_rand, i0, d.n, sr);
-            if (RNG == 1) {
-                const uint2 key = make_uint2((uint32_t)d.seed, (uint32_t)(d.seed >> 32));
-                if (f_leak) {
-                    // Box-Muller on fast intrinsics: this stream only has to be N(0,1), not torch's bits
-                    uint4 r = philox4x32<kPhiloxRounds>(make_uint4((uint32_t)(i0 >> 2), p.frame_index, 0u, 0x6c65616bu), key);
-                    float a = __fsqrt_rn(-2.0f * __logf(u01_open(r.x))), b = __fsqrt_rn(-2.0f * __logf(u01_open(r.z)));
-                    float sa, ca, sb, cb;
-                    __sincosf(6.283185307179586f * u01_half(r.y), &sa, &ca);
-                    __sincosf(6.283185307179586f * u01_half(r.w), &sb, &cb);
-                    lr[0] = a * ca; lr[1] = a * sa; lr[2] = b * cb; lr[3] = b * sb;
-                }
-                if (f_shot) {
-                    uint4 r = philox4x32<kPhiloxRounds>(make_uint4((uint32_t)(i0 >> 2), p.frame_index, 1u, 0x73686f74u), key);
-                    sr[0] = u01_half(r.x); sr[1] = u01_half(r.y); sr[2] = u01_half(r.z); sr[3] = u01_half(r.w);
-                }
+        }
+        if (RNG == 1) {
+            const uint2 key = make_uint2((uint32_t)d.seed, (uint32_t)(d.seed >> 32));
+            if (f_leak) {
+                // Box-Muller on fast intrinsics: this stream only has to be N(0,1), not torch's bits
+                uint4 r = philox4x32<kPhiloxRounds>(make_uint4((uint32_t)(i0 >> 2), p.frame_index, 0u, 0x6c65616bu), key);
+                float a = sqrt_approx(-2.0f * __logf(u01_open(r.x))), b = sqrt_approx(-2.0f * __logf(u01_open(r.z)));
+                float sa, ca, sb, cb;
+                __sincosf(6.283185307179586f * u01_half(r.y), &sa, &ca);
+                __sincosf(6.283185307179586f * u01_half(r.w), &sb, &cb);
+                lr[0] = a * ca; lr[1] = a * sa; lr[2] = b * cb; lr[3] = b * sb;
             }
+            if (f_shot) {
+                uint4 r = philox4x32<kPhiloxRounds>(make_uint4((uint32_t)(i0 >> 2), p.frame_index, 1u, 0x73686f74u), key);
+                sr[0] = u01_half(r.x); sr[1] = u01_half(r.y); sr[2] = u01_half(r.z); sr[3] = u01_half(r.w);
+            }
+        }
+        // staged state -> registers
+        S lp[4], base[4];
+        float thp[4], thn[4], nr[4];
+        mbar_wait(&s_full[warp][j % kStages], (uint32_t)((j / kStages) & 1));
+        if (need_lp) ld4((const S *)(st + StageLayout<S>::lp), so, lp);
+        ld4((const S *)(st + StageLayout<S>::base), so, base);
+        if (f_pp) {
+            ld4((const float *)(st + StageLayout<S>::thp), so, thp);
+            ld4((const float *)(st + StageLayout<S>::thn), so, thn);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) { thp[k] = (float)d.pos_nom; thn[k] = (float)d.neg_nom; }
+        }
+        if (f_leak) ld4((const float *)(st + StageLayout<S>::nr), so, nr);
+        __syncwarp();                                      // the stage has been read by the whole warp
+        if (j + kStages < nj) issue(j + kStages);
+        // packed counters of this thread's 4 pixels: byte 0 ON events of iteration 0, byte 1 OFF of
+        // iteration 0, byte 2 ON of iteration 1, byte 3 OFF of iteration 1 (<= 4 each, <= 128 per warp)
+        uint32_t pk = 0;
+        int nact = 0, deep = 0;
+        if (t_on) {
+            bool shot_maybe = false;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                const double xv = x[k];
+                const int code_u8 = (int)((codes >> (8 * k)) & 0xffu);
+                const double xv = (FT == V2E_U8) ? 0.0 : x[k];
                 const bool is_code = FT == V2E_U8 || (xv >= 0.0 && xv <= 255.0 && xv == floor(xv));
+                const int code = (FT == V2E_U8) ? code_u8 : (is_code ? (int)xv : 0);
                 // photoreceptor low-pass (emulator_utils.py:57-109)
                 if (!lp_done) {
-                    double ln;                               // float32 lin_log value, widened (or raw if hdr)
-                    if (f_hdr) ln = xv;
-                    else ln = is_code ? s_lut[(int)xv] : (double)lin_log_eval(xv);
-                    if (sizeof(S) == 8) {
-                        if (f_lp) {
-                            double inten01 = is_code ? s_inten[(int)xv] : (xv + 20.0) / 275.0;
+                    if (tab) {
+                        lp[k] = (S)(s_ta[code] * (double)lp[k] + s_tb[code]);
+                    } else {
+                        double ln;                           // float32 lin_log value, widened (or raw if hdr)
+                        if (f_hdr) ln = xv;
+                        else ln = is_code ? s_ta[code] : (double)lin_log_eval(xv);
+                        if (sizeof(S) == 8 && f_lp) {
+                            double inten01 = is_code ? s_tb[code] : (xv + 20.0) / 275.0;
                             double eps = inten01 * p.eps_scale;
                             if (eps > 1.0) eps = 1.0;
                             lp[k] = (S)((1.0 - eps) * (double)lp[k] + eps * ln);
                         } else {
-                            lp[k] = (S)ln;
+                            lp[k] = (S)ln;                   // float32 state: exact, ln is a widened float32
                         }
-                    } else {
-                        lp[k] = (S)ln;                       // exact: ln is a widened float32
                     }
                 }
                 // leak (emulator_utils.py:114-134): float32 products, subtract in S
@@ -568,91 +756,112 @@ emu_update_kernel(EmuDev d, FrameParams p, const void *frame, const float *leak_
                 S tp, tn;
                 if (sizeof(S) == 8 && !f_pp) { tp = (S)d.pos_nom; tn = (S)d.neg_nom; }
                 else { tp = (S)thp[k]; tn = (S)thn[k]; }
-                int32_t cnt = 0;
-                if (diff >= tp) cnt = div_floor_count<S>(diff, tp);
-                else if (-diff >= tn) cnt = -div_floor_count<S>(-diff, tn);
-                // shot noise: exact test only when the draw can possibly cross (shot_bound >= any
-                // per-pixel probability; see make_params)
-                int flags = 0;
-                if (shot_here) {
-                    const double r = (double)sr[k];
-                    if (!(xv >= 0.0 && xv <= 255.0) || r < p.shot_bound || r > 1.0 - p.shot_bound)
-                        flags = shot_flags(d, p, xv, sr[k], thp[k], thn[k]);
+                // ON iff diff >= tp, OFF iff -diff >= tn (thresholds > 0): one magnitude, one threshold.
+                // Results 0 / 1 / 2 of ATen's floor division without a branch (see div_floor_count)
+                const bool neg = diff < (S)0;
+                const S a = neg ? -diff : diff, b = neg ? tn : tp, b2 = b + b;
+                const int ge1 = a >= b, ge2 = a >= b2;
+                int32_t mag = ge1 + ge2;
+                if (ge2 && !(a - b2 < b)) {                  // >= 3 events: rare
+                    mag = div_floor_count<S>(a, b);
+                    local_max = max(local_max, mag);         // before the clamps: the plan reports > iter_cap
+                    if (mag > kRecMaxCount) mag = kRecMaxCount;
+                    deep = 1;
                 }
-                const bool valid = (i0 + k) < d.n;
-                if (!valid) { cnt = 0; flags = 0; }
-                int32_t mag = cnt < 0 ? -cnt : cnt;
-                if (mag > local_max) local_max = mag;
-                if (mag > kRecMaxCount) { cnt = cnt < 0 ? -kRecMaxCount : kRecMaxCount; }
-                recs[k] = (short)((cnt << kRecShift) | flags);
-                mags[k] = mag < d.iter_cap ? mag : d.iter_cap;
-                pols[k] = cnt < 0;
-                flg[k] = flags;
+                // shot noise: the exact test (below) only when the draw can possibly cross. shot_lo_f /
+                // shot_hi_f are float32 bounds rounded outwards from shot_bound >= any per-pixel probability
+                if (shot_here) {
+                    const float r = sr[k];
+                    shot_maybe |= (FT != V2E_U8 && !(xv >= 0.0 && xv <= 255.0)) || r < p.shot_lo_f || r > p.shot_hi_f;
+                }
+                recs[k] = (short)((neg ? -mag : mag) << kRecShift);
+                mags[k] = mag;
+                pols[k] = neg;
+            }
+            if (i0 + 4 > d.n) {                            // the frame's last, partial quad
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (i0 + k >= d.n) { recs[k] = 0; mags[k] = 0; }
+            }
+            if (shot_maybe) {                              // rare
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const double xv = (FT == V2E_U8) ? (double)((codes >> (8 * k)) & 0xffu) : x[k];
+                    const float r = sr[k];
+                    if ((i0 + k) < d.n &&
+                        ((FT != V2E_U8 && !(xv >= 0.0 && xv <= 255.0)) || r < p.shot_lo_f || r > p.shot_hi_f)) {
+                        const int flags = shot_flags(d, p, xv, r, thp[k], thn[k]);
+                        flg[k] = flags;
+                        recs[k] = (short)(recs[k] | flags);
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                local_max = max(local_max, mags[k]);
+                mags[k] = min(mags[k], d.iter_cap);
+                const uint32_t m = (uint32_t)(mags[k] > 0) | ((uint32_t)(mags[k] > 1) << 16);
+                pk += m << (pols[k] ? 8 : 0);
+                nact += recs[k] != 0;
             }
             if (!lp_done) st4((S *)d.lp, i0, lp);
             if (f_leak) st4((S *)d.base, i0, base);
             *(short4 *)(d.rec + i0) = make_short4(recs[0], recs[1], recs[2], recs[3]);
         }
-        // per-(iteration,polarity) histogram. Iterations 0 and 1 (almost all events) are counted per thread
-        // and reduced with one REDUX per three segments; a pixel with >= 3 events takes the ballot loop.
-        {
-            int c0on = 0, c0off = 0, c1on = 0, c1off = 0, son = 0, soff = 0, deep = 0, nact = 0;
+        // per-(iteration,polarity) histogram. Iterations 0 and 1 (almost all events) are counted per thread,
+        // reduced with one REDUX and accumulated in (warp-uniform) registers until the warp's last unit; a
+        // pixel with >= 3 events takes the ballot loop, shot-noise flags their own (rare) path.
+        if (__any_sync(0xffffffffu, nact != 0)) {
+            const uint32_t wsum = __reduce_add_sync(0xffffffffu, pk);
+            acc0 += wsum & 0x00ff00ffu;                     // ON:  iteration 0 | iteration 1 << 16
+            acc1 += (wsum >> 8) & 0x00ff00ffu;              // OFF: iteration 0 | iteration 1 << 16
+            if ((j & 255) == 255) flush_acc();              // 16-bit fields, <= 128 per unit
+            // compaction of the active pixels into this block's list segment: warp scan, one shared
+            // atomic per warp, no global round trip (the segment's place is fixed)
+            int incl = nact;
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                c0on += (mags[k] > 0) & !pols[k];
-                c0off += (mags[k] > 0) & pols[k];
-                c1on += (mags[k] > 1) & !pols[k];
-                c1off += (mags[k] > 1) & pols[k];
-                son += flg[k] & 1;
-                soff += (flg[k] >> 1) & 1;
-                deep |= mags[k] > 2;
-                nact += recs[k] != 0;
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
             }
-            if (__any_sync(0xffffffffu, nact != 0)) {
-                const int lo = __reduce_add_sync(0xffffffffu, (c0on) | (c0off << 10) | (c1on << 20));
-                const int hi = __reduce_add_sync(0xffffffffu, (c1off) | (son << 10) | (soff << 20));
-                // compaction of the active pixels into this block's list segment: warp scan, one shared
-                // atomic per warp, no global round trip (the segment's place is fixed)
-                int incl = nact;
+            uint32_t wbase = 0;
+            if (lane == 31) wbase = atomicAdd(&s_act_total, (uint32_t)incl);
+            wbase = __shfl_sync(0xffffffffu, wbase, 31);
+            if (nact) {
+                uint32_t pos = seg_base + wbase + (uint32_t)(incl - nact);
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    int t = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += t;
-                }
-                uint32_t wbase = 0;
-                if (lane == 31) wbase = atomicAdd(&s_act_total, (uint32_t)incl);
-                wbase = __shfl_sync(0xffffffffu, wbase, 31);
+                for (int k = 0; k < 4; k++)
+                    if (recs[k] != 0) d.act_list[pos++] = (uint32_t)(i0 + k);
+            }
+            const unsigned shot_any = __ballot_sync(0xffffffffu, (flg[0] | flg[1] | flg[2] | flg[3]) != 0);
+            if (shot_any) {
+                int son = 0, soff = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) { son += flg[k] & 1; soff += (flg[k] >> 1) & 1; }
+                son = __reduce_add_sync(0xffffffffu, son);
+                soff = __reduce_add_sync(0xffffffffu, soff);
                 if (lane == 0) {
-                    if (lo & 1023) atomicAdd(&s_hist[0], lo & 1023);
-                    if ((lo >> 10) & 1023) atomicAdd(&s_hist[1], (lo >> 10) & 1023);
-                    if ((lo >> 20) & 1023) atomicAdd(&s_hist[2], (lo >> 20) & 1023);
-                    if (hi & 1023) atomicAdd(&s_hist[3], hi & 1023);
-                    if ((hi >> 10) & 1023) atomicAdd(&s_hist[kSegSmem], (hi >> 10) & 1023);
-                    if ((hi >> 20) & 1023) atomicAdd(&s_hist[kSegSmem + 1], (hi >> 20) & 1023);
+                    if (son) atomicAdd(&s_hist[kSegSmem], (uint32_t)son);
+                    if (soff) atomicAdd(&s_hist[kSegSmem + 1], (uint32_t)soff);
                 }
-                if (nact) {
-                    uint32_t pos = seg_base + wbase + (uint32_t)(incl - nact);
+            }
+            if (__any_sync(0xffffffffu, deep)) {
 #pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        if (recs[k] != 0) d.act_list[pos++] = (uint32_t)(i0 + k);
-                }
-                if (__any_sync(0xffffffffu, deep)) {
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const int wmax = __reduce_max_sync(0xffffffffu, mags[k]);
-                        for (int it = 2; it < wmax; it++) {
-                            unsigned on = __ballot_sync(0xffffffffu, mags[k] > it && !pols[k]);
-                            unsigned off = __ballot_sync(0xffffffffu, mags[k] > it && pols[k]);
-                            if (lane == 0) {
-                                if (on) { if (2 * it < kSegSmem) atomicAdd(&s_hist[2 * it], __popc(on)); else atomicAdd(&hist[2 * it], __popc(on)); }
-                                if (off) { if (2 * it + 1 < kSegSmem) atomicAdd(&s_hist[2 * it + 1], __popc(off)); else atomicAdd(&hist[2 * it + 1], __popc(off)); }
-                            }
+                for (int k = 0; k < 4; k++) {
+                    const int wmax = __reduce_max_sync(0xffffffffu, mags[k]);
+                    for (int it = 2; it < wmax; it++) {
+                        unsigned on = __ballot_sync(0xffffffffu, mags[k] > it && !pols[k]);
+                        unsigned off = __ballot_sync(0xffffffffu, mags[k] > it && pols[k]);
+                        if (lane == 0) {
+                            if (on) { if (2 * it < kSegSmem) atomicAdd(&s_hist[2 * it], __popc(on)); else atomicAdd(&hist[2 * it], __popc(on)); }
+                            if (off) { if (2 * it + 1 < kSegSmem) atomicAdd(&s_hist[2 * it + 1], __popc(off)); else atomicAdd(&hist[2 * it + 1], __popc(off)); }
                         }
                     }
                 }
             }
         }
     }
+    flush_acc();
     // block max -> one atomicMax per block
     local_max = warp_reduce_max(local_max);
     if (lane == 0 && local_max > 0) atomicMax(&s_max, local_max);
@@ -772,7 +981,8 @@ emu_shot_kernel(EmuDev d, FrameParams p, const void *frame, const float *shot_ra
             if (flags) {
                 const short old = d.rec[i0 + k];
                 if (old == 0) {
-                    const int sg = (i0 + k) / d.seg_px;
+                    // the update block that owns this pixel's unit: largest b with b*units/n_blocks <= unit
+                    const int sg = (int)((((long long)((i0 + k) / kUnitPx) + 1) * d.n_blocks - 1) / d.units);
                     d.act_list[(size_t)sg * d.seg_px + atomicAdd(&d.act_count[(size_t)slot * d.n_blocks + sg], 1u)] =
                         (uint32_t)(i0 + k);
                 }
@@ -908,6 +1118,9 @@ emu_emit_kernel(EmuDev d, FrameParams p, int slot, float4 *events) {
     }
 }
 
+// measurement floor: what an event bracket reports around a kernel that does nothing (v2e_emu_profile_read4)
+__global__ void emu_null_kernel() {}
+
 __global__ void emu_begin_step_kernel(EmuDev d, int slot, uint64_t ev_base) {
     d.ctrl[slot].ev_base = ev_base;
 }
@@ -921,6 +1134,7 @@ __global__ void __launch_bounds__(kThreads) emu_plan_kernel(EmuDev d, FrameParam
 // =============================================================================================
 // host side
 // =============================================================================================
+constexpr int kProfKinds = 4;            // update, filter, emit, null kernel (bracket floor)
 struct V2eEmu {
     V2eEmuCfg cfg;
     EmuDev d;
@@ -933,7 +1147,7 @@ struct V2eEmu {
     int profile;                // 1: bracket every kernel of v2e_emu_step with CUDA events
     cudaEvent_t *ev;            // [max_slots][3 kinds][2]
     int prof_frames;
-    unsigned char *prof_used;   // [max_slots][3]
+    unsigned char *prof_used;   // [max_slots][kProfKinds]
     float *lut_dev;
     FrameCtrl *ctrl_host;       // pinned
     int32_t *abort_host;        // pinned [2]
@@ -980,6 +1194,13 @@ static FrameParams make_params(const V2eEmu *h, double t_frame, double t_prev, u
             pre_max = nom / h->min_thres;
         }
         p.shot_bound = fabs(p.shot_c) * inten_max * pre_max * 1.0001 + 1e-300;
+        // rounded outwards: (double)r < shot_bound implies r < shot_lo_f, (double)r > 1-shot_bound implies r > shot_hi_f
+        float lo = (float)p.shot_bound;
+        if ((double)lo < p.shot_bound) lo = nextafterf(lo, INFINITY);
+        float hi = (float)(1.0 - p.shot_bound);
+        if ((double)hi > 1.0 - p.shot_bound) hi = nextafterf(hi, -INFINITY);
+        p.shot_lo_f = lo;
+        p.shot_hi_f = hi;
     }
     p.capacity = capacity;
     return p;
@@ -1024,7 +1245,9 @@ extern "C" int v2e_emu_create(const V2eEmuCfg *cfg, V2eEmu **out) {
     d.seed = cfg->seed;
     h->state_elem = d.state_f64 ? 8 : 4;
     h->min_thres = 0.01;
-    size_t np = (size_t)d.n_pad;
+    d.units = (d.n + kUnitPx - 1) / kUnitPx;
+    // state arrays are staged in whole 128-pixel units by the update kernel's bulk copies
+    size_t np = (size_t)d.units * kUnitPx;
 #define ALLOC(ptr, bytes)                                                     \
     do {                                                                      \
         cudaError_t e_ = cudaMalloc((void **)&(ptr), (bytes));                \
@@ -1055,15 +1278,16 @@ extern "C" int v2e_emu_create(const V2eEmuCfg *cfg, V2eEmu **out) {
     ALLOC(d.segoff, slots * d.seg_stride * 4);
     ALLOC(d.cursor, slots * d.seg_stride * 4);
     {
-        // one wave: 4 resident blocks per SM (64 registers x 256 threads)
+        // one wave of the update kernel: 3 resident blocks per SM (2 stages x 28 KB of shared memory each),
+        // every block the same number of 128-pixel units
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const int tiles = (d.n_pad / kVec + kThreads - 1) / kThreads;
-        d.groups = (tiles + 4 * sms - 1) / (4 * sms);
-        if (d.groups < 1) d.groups = 1;
-        d.seg_px = d.groups * kThreads * kVec;
-        d.n_blocks = (tiles + d.groups - 1) / d.groups;
+        d.n_blocks = 3 * sms;
+        if (d.n_blocks > (d.units + 3) / 4) d.n_blocks = (d.units + 3) / 4;     // small frames: >= 4 units per block
+        if (d.n_blocks < 1) d.n_blocks = 1;
+        d.upb = (d.units + d.n_blocks - 1) / d.n_blocks;
+        d.seg_px = d.upb * kUnitPx;
     }
     ALLOC(d.act_count, slots * d.n_blocks * sizeof(uint32_t));
     ALLOC(d.act_list, (size_t)d.n_blocks * d.seg_px * sizeof(uint32_t));
@@ -1087,7 +1311,7 @@ extern "C" int v2e_emu_destroy(V2eEmu *h) {
     if (h->ctrl_host) cudaFreeHost(h->ctrl_host);
     if (h->abort_host) cudaFreeHost(h->abort_host);
     if (h->ev) {
-        for (int i = 0; i < d.max_slots * 6; i++) cudaEventDestroy(h->ev[i]);
+        for (int i = 0; i < d.max_slots * kProfKinds * 2; i++) cudaEventDestroy(h->ev[i]);
         delete[] h->ev;
         delete[] h->prof_used;
     }
@@ -1155,15 +1379,27 @@ static int launch_update_r(V2eEmu *h, const FrameParams &p, const void *frame, i
                            const float *sr, int slot, int do_plan, int lp_done, cudaStream_t st) {
     int g = h->d.n_blocks;
     const EmuDev &d = h->d;
+    const size_t sm = (size_t)StageLayout<S>::block_bytes;
+    {
+        // opt in to > 48 KB of dynamic shared memory once per instantiation
+        static bool done = false;
+        if (!done) {
+            CU(cudaFuncSetAttribute(emu_update_kernel<double, V2E_U8, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StageLayout<double>::block_bytes));
+            CU(cudaFuncSetAttribute(emu_update_kernel<S, V2E_U8, RNG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            CU(cudaFuncSetAttribute(emu_update_kernel<S, V2E_F32, RNG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            CU(cudaFuncSetAttribute(emu_update_kernel<S, V2E_F64, RNG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            done = true;
+        }
+    }
     if (sizeof(S) == 8 && RNG == 1 && dt == V2E_U8 && d.per_pixel_thres && d.leak_on && d.lowpass_on && d.shot_on &&
         !d.hdr && !d.csdvs && !lp_done) {
-        emu_update_kernel<double, V2E_U8, 1, true><<<g, kThreads, 0, st>>>(h->d, p, frame, lr, sr, slot, do_plan, 0, d.groups);
+        emu_update_kernel<double, V2E_U8, 1, true><<<g, kThreads, sm, st>>>(h->d, p, frame, lr, sr, slot, do_plan, 0);
         return V2E_OK;
     }
     switch (dt) {
-        case V2E_U8: emu_update_kernel<S, V2E_U8, RNG, false><<<g, kThreads, 0, st>>>(h->d, p, frame, lr, sr, slot, do_plan, lp_done, d.groups); break;
-        case V2E_F32: emu_update_kernel<S, V2E_F32, RNG, false><<<g, kThreads, 0, st>>>(h->d, p, frame, lr, sr, slot, do_plan, lp_done, d.groups); break;
-        case V2E_F64: emu_update_kernel<S, V2E_F64, RNG, false><<<g, kThreads, 0, st>>>(h->d, p, frame, lr, sr, slot, do_plan, lp_done, d.groups); break;
+        case V2E_U8: emu_update_kernel<S, V2E_U8, RNG, false><<<g, kThreads, sm, st>>>(h->d, p, frame, lr, sr, slot, do_plan, lp_done); break;
+        case V2E_F32: emu_update_kernel<S, V2E_F32, RNG, false><<<g, kThreads, sm, st>>>(h->d, p, frame, lr, sr, slot, do_plan, lp_done); break;
+        case V2E_F64: emu_update_kernel<S, V2E_F64, RNG, false><<<g, kThreads, sm, st>>>(h->d, p, frame, lr, sr, slot, do_plan, lp_done); break;
         default: return fail(V2E_E_INVALID, "bad frame dtype");
     }
     return V2E_OK;
@@ -1190,9 +1426,9 @@ static int launch_shot(V2eEmu *h, const FrameParams &p, const void *frame, int d
 struct ProfScope {
     V2eEmu *h; int slot, kind; cudaStream_t st;
     ProfScope(V2eEmu *h_, int slot_, int kind_, cudaStream_t st_) : h(h_), slot(slot_), kind(kind_), st(st_) {
-        if (h->profile) { cudaEventRecord(h->ev[(slot * 3 + kind) * 2], st); h->prof_used[slot * 3 + kind] = 1; }
+        if (h->profile) { cudaEventRecord(h->ev[(slot * kProfKinds + kind) * 2], st); h->prof_used[slot * kProfKinds + kind] = 1; }
     }
-    ~ProfScope() { if (h->profile) cudaEventRecord(h->ev[(slot * 3 + kind) * 2 + 1], st); }
+    ~ProfScope() { if (h->profile) cudaEventRecord(h->ev[(slot * kProfKinds + kind) * 2 + 1], st); }
 };
 
 static size_t frame_elem(int dt) { return dt == V2E_U8 ? 1 : (dt == V2E_F32 ? 4 : 8); }
@@ -1253,6 +1489,11 @@ static int enqueue_emit(V2eEmu *h, const FrameParams &p, int slot, float *events
     else emu_emit_kernel<float><<<list_grid(d), kThreads, 0, st>>>(d, p, slot, (float4 *)events);
     return V2E_OK;
 }
+static void enqueue_null_bracket(V2eEmu *h, int slot, cudaStream_t st) {
+    if (!h->profile) return;
+    ProfScope ps(h, slot, 3, st);
+    emu_null_kernel<<<1, 32, 0, st>>>();
+}
 
 static int reset_slots(V2eEmu *h, int first, int count, cudaStream_t st) {
     EmuDev &d = h->d;
@@ -1286,7 +1527,7 @@ extern "C" int v2e_emu_step(V2eEmu *h, const void *frames, int dtype, int T, con
     } else {
         if ((rc = reset_slots(h, first, T - first, st))) return rc;
     }
-    if (h->profile) { memset(h->prof_used, 0, (size_t)d.max_slots * 3); h->prof_frames = T - first; }
+    if (h->profile) { memset(h->prof_used, 0, (size_t)d.max_slots * kProfKinds); h->prof_frames = T - first; }
     if (!resume_emit) {
         h->step_base = h->frame_counter;
         h->frame_counter += (uint32_t)T;
@@ -1305,6 +1546,7 @@ extern "C" int v2e_emu_step(V2eEmu *h, const void *frames, int dtype, int T, con
             if ((rc = enqueue_count(h, p, frame, dtype, lr, sr, 0, f, st))) return rc;
         }
         if ((rc = enqueue_emit(h, p, f, events, st))) return rc;
+        enqueue_null_bracket(h, f, st);
     }
     CU(cudaGetLastError());
     h->last_T = T;
@@ -1441,28 +1683,34 @@ extern "C" int v2e_emu_phase_emit(V2eEmu *h, double t_frame, double t_previous, 
 extern "C" int v2e_emu_profile(V2eEmu *h, int enable) {
     if (!h) return fail(V2E_E_INVALID, "null handle");
     if (enable && !h->ev) {
-        int n = h->d.max_slots * 3 * 2;
+        int n = h->d.max_slots * kProfKinds * 2;
         h->ev = new cudaEvent_t[n];
         for (int i = 0; i < n; i++) CU(cudaEventCreate(&h->ev[i]));
-        h->prof_used = new unsigned char[h->d.max_slots * 3]();
+        h->prof_used = new unsigned char[h->d.max_slots * kProfKinds]();
     }
     h->profile = enable ? 1 : 0;
     return V2E_OK;
 }
 
-extern "C" int v2e_emu_profile_read(V2eEmu *h, float *ms_sum3, int *launches3, void *stream) {
-    if (!h || !h->ev || !ms_sum3 || !launches3) return fail(V2E_E_INVALID, "profiling not enabled");
+static int profile_read_n(V2eEmu *h, float *ms_sum, int *launches, int kinds, void *stream) {
+    if (!h || !h->ev || !ms_sum || !launches) return fail(V2E_E_INVALID, "profiling not enabled");
     CU(cudaStreamSynchronize((cudaStream_t)stream));
-    for (int k = 0; k < 3; k++) { ms_sum3[k] = 0.f; launches3[k] = 0; }
+    for (int k = 0; k < kinds; k++) { ms_sum[k] = 0.f; launches[k] = 0; }
     for (int s = 0; s < h->d.max_slots; s++)
-        for (int k = 0; k < 3; k++)
-            if (h->prof_used[s * 3 + k]) {
+        for (int k = 0; k < kinds; k++)
+            if (h->prof_used[s * kProfKinds + k]) {
                 float ms = 0.f;
-                CU(cudaEventElapsedTime(&ms, h->ev[(s * 3 + k) * 2], h->ev[(s * 3 + k) * 2 + 1]));
-                ms_sum3[k] += ms;
-                launches3[k] += 1;
+                CU(cudaEventElapsedTime(&ms, h->ev[(s * kProfKinds + k) * 2], h->ev[(s * kProfKinds + k) * 2 + 1]));
+                ms_sum[k] += ms;
+                launches[k] += 1;
             }
     return V2E_OK;
+}
+extern "C" int v2e_emu_profile_read(V2eEmu *h, float *ms_sum3, int *launches3, void *stream) {
+    return profile_read_n(h, ms_sum3, launches3, 3, stream);
+}
+extern "C" int v2e_emu_profile_read4(V2eEmu *h, float *ms_sum4, int *launches4, void *stream) {
+    return profile_read_n(h, ms_sum4, launches4, 4, stream);
 }
 
 extern "C" int v2e_emu_state_is_f64(V2eEmu *h) { return h ? h->d.state_f64 : 0; }

@@ -26,6 +26,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include "../../include/v2e_b200.h"
 #include "tc_common.cuh"
@@ -199,6 +200,8 @@ struct StripParams {
     int KC, BN;
     int tiles_x, seg_h, n_seg, n_items;
     int nslot;
+    int variant;                   // 0: per-tap MMAs (first strip kernel), 1: row-stacked (strip2)
+    int acc_slots, tmem_cols;      // strip2: accumulator ring (slots of BN columns), TMEM allocation
     int slab_bytes;                // bytes of one row buffer of one slab (1024-aligned)
     int w_bytes;                   // all weights: slabs*taps*BN*KC*2
     int w_rows_per_load, w_loads;
@@ -411,6 +414,238 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Strip kernel, row-stacked form ("strip2"): the same column-strip walk, but the MMA is turned round so
+// that ONE fetch of an input row feeds every output row it contributes to.
+//
+// With N = Cout = 16..64 a per-tap MMA (M=128, N=Cout, K=16) spends 32 cycles fetching its 128-row A
+// operand for 8..32 cycles of tensor work: the first strip kernel was bound by the A fetch (ncu: operand
+// fetch 48 %, tensor pipe 35 %). But input row i at horizontal shift s is the A operand of KH different
+// (output row, filter row) pairs: out[i+ph-r] += W[r][s] . in[i][x+s]. So the weights of one filter COLUMN
+// s are stacked into one B operand [W[KH-1][s]; ...; W[0][s]] (N = KH*Cout rows, e.g. 224 for the 7x7
+// layers) and the accumulators of consecutive output rows sit side by side in a TMEM ring (R slots of
+// Cout columns): one MMA (M=128, N=KH*Cout, K=16) adds input row i into all KH live output rows at once.
+// A is fetched once per KH*Cout output channels instead of once per Cout; MMAs per row drop by KH (98 ->
+// 14 for conv2), so one issuer warp is enough.
+//
+//   warp 0     : TMA producer. Weights once per CTA, tile (slab, r, s) placed at [(slab*KW + s)*KH + (KH-1-r)]
+//                so that the r-stack of a column is contiguous; then one box per (input row, channel slab)
+//                into a small ring (each entry is consumed by one burst of MMAs and released).
+//   warp 1     : MMA issuer. Per input row: wait for the accumulator slot of the output row that starts
+//                here, then for every slab / shift / k-step one MMA per contiguous slot range (the ring
+//                wrap and N <= 256 split a stack into at most a few ranges). Accumulate flag always on:
+//                a slot is zeroed by the epilogue when it is drained. After the row's last MMA the output
+//                row that received its last contribution (filter row KH-1) is committed to the epilogue.
+//   warps 2..5 : epilogue: tcgen05.ld, bias, LeakyReLU, store; tcgen05.st zeros; release the slot.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxAcc = 32;
+constexpr int kStrip2Threads = 192;
+
+template <int KW, int KC>
+__global__ void __launch_bounds__(kStrip2Threads)
+conv_strip2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                   const __grid_constant__ CUtensorMap tmB, const StripParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t full_bar[kMaxSlot], empty_bar[kMaxSlot], w_bar, acc_full[kMaxAcc], acc_empty[kMaxAcc];
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Ctot = p.C1 + p.C2;
+    const int slabs = Ctot / KC;
+    const int KH = p.KH;
+    constexpr int PW = kRowTile + KW - 1;
+    const int ph = KH / 2, pw = KW / 2;
+    uint8_t *ring = smem + ((p.w_bytes + 1023) & ~1023);
+    const int R = p.acc_slots;
+    const uint32_t BN = (uint32_t)p.BN;
+    const uint32_t tile_bytes = BN * (uint32_t)KC * 2u;        // one (slab, r, s) weight tile
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.nslot; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&w_bar, 1);
+        for (int s = 0; s < R; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA);
+        if (p.C2) prefetch_tmap(&tmA2);
+        prefetch_tmap(&tmB);
+    }
+    if (warp == 1) {
+        tmem_alloc(&tmem_base_smem, (uint32_t)p.tmem_cols);
+        tmem_relinquish();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            mbar_expect_tx(&w_bar, (uint32_t)p.w_bytes);
+            for (int sl = 0; sl < slabs; sl++)
+                for (int r = 0; r < KH; r++)
+                    for (int s = 0; s < KW; s++)
+                        tma_load_2d(smem + (size_t)((sl * KW + s) * KH + (KH - 1 - r)) * tile_bytes, &tmB, &w_bar, 0,
+                                    ((sl * KH + r) * KW + s) * (int)BN);
+            uint32_t cnt = 0;                                   // ring entries filled so far (all items)
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                const int tx = item % p.tiles_x, rest = item / p.tiles_x;
+                const int seg = rest % p.n_seg, n = rest / p.n_seg;
+                const int ya = seg * p.seg_h, yb = min(p.H, ya + p.seg_h);
+                const int x0 = tx * kRowTile;
+                for (int i = ya - ph; i < yb + ph; i++) {
+                    for (int sl = 0; sl < slabs; sl++, cnt++) {
+                        const int e = (int)(cnt % (uint32_t)p.nslot);
+                        const uint32_t phase = (cnt / (uint32_t)p.nslot) & 1u;
+                        mbar_wait(&empty_bar[e], phase ^ 1);
+                        mbar_expect_tx(&full_bar[e], (uint32_t)(PW * KC * 2));
+                        uint8_t *dst = ring + (size_t)e * p.slab_bytes;
+                        const int c = sl * KC;
+                        if (c < p.C1) tma_load_4d(dst, &tmA, &full_bar[e], c, x0 - pw, i, n);
+                        else tma_load_4d(dst, &tmA2, &full_bar[e], c - p.C1, x0 - pw, i, n);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (converged warp, one elected lane) =====
+        const uint32_t leader = elect_one();
+        constexpr uint32_t swz = KC == 64 ? 2u : (KC == 32 ? 4u : 6u);
+        constexpr uint32_t rowb = (uint32_t)KC * 2u;
+        constexpr uint32_t sbo = 8u * rowb;
+        constexpr int ksteps = KC / 16;
+        const uint64_t dhi = make_smem_desc(0, swz, sbo);
+        const uint32_t lo_flags = (uint32_t)(dhi & 0xFFFF0000u);
+        const uint32_t w16 = (smem_u32(smem) >> 4) | lo_flags, ring16 = (smem_u32(ring) >> 4) | lo_flags;
+        const uint32_t slab16 = (uint32_t)p.slab_bytes >> 4, tile16 = tile_bytes >> 4;
+        const int nb_max = 256 / (int)BN;
+        mbar_wait(&w_bar, 0);
+        uint32_t cnt = 0;                                   // ring entries consumed so far
+        uint32_t orow = 0;                                  // output rows started before this item
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            const int rest = item / p.tiles_x;
+            const int seg = rest % p.n_seg;
+            const int ya = seg * p.seg_h, yb = min(p.H, ya + p.seg_h);
+            const int rows_out = yb - ya, rows_in = rows_out + 2 * ph;
+            for (int ii = 0; ii < rows_in; ii++) {
+                // input row ii of the item feeds output rows yl..yh (relative), filter row r = ii - yr
+                const int yl = max(0, ii - 2 * ph), yh = min(rows_out - 1, ii);
+                if (ii < rows_out) {                        // output row ii starts here: its slot must be drained
+                    const uint32_t g = orow + (uint32_t)ii;
+                    mbar_wait(&acc_empty[g % (uint32_t)R], (g / (uint32_t)R) & 1u);
+                    tcgen05_fence_after();
+                }
+                // contiguous slot ranges of the stack (ring wrap, N <= 256)
+                uint32_t rd[4], rb[4], ri[4];
+                int nr = 0;
+                for (int yr = yl; yr <= yh && nr < 4;) {
+                    const int slot = (int)((orow + (uint32_t)yr) % (uint32_t)R);
+                    int nb = yh - yr + 1;
+                    nb = min(nb, min(R - slot, nb_max));
+                    rd[nr] = tmem_base + (uint32_t)slot * BN;
+                    rb[nr] = (uint32_t)(yr - ii + KH - 1) * tile16;
+                    ri[nr] = make_idesc_f16(kBM, nb * (int)BN);
+                    nr++;
+                    yr += nb;
+                }
+                for (int sl = 0; sl < slabs; sl++, cnt++) {
+                    const uint32_t e = cnt % (uint32_t)p.nslot;
+                    mbar_wait(&full_bar[e], (cnt / (uint32_t)p.nslot) & 1u);
+                    tcgen05_fence_after();
+                    const uint32_t a_lo = ring16 + e * slab16;
+                    const uint32_t b_sl = w16 + (uint32_t)(sl * KW * KH) * tile16;
+#pragma unroll
+                    for (int s = 0; s < KW; s++) {
+#pragma unroll
+                        for (int j = 0; j < ksteps; j++) {
+                            const uint64_t adesc = desc_with_lo(dhi, a_lo + (uint32_t)(s * (rowb >> 4) + 2 * j));
+                            const uint32_t b_lo = b_sl + (uint32_t)(s * KH) * tile16 + (uint32_t)(2 * j);
+#pragma unroll
+                            for (int k = 0; k < 4; k++)
+                                if (k < nr)
+                                    umma_f16_pred(rd[k], adesc, desc_with_lo(dhi, b_lo + rb[k]), ri[k], 1u, leader);
+                        }
+                    }
+                    umma_commit_pred(&empty_bar[e], leader);            // entry free once these MMAs retire
+                }
+                if (ii >= 2 * ph) {                         // output row ii-2ph just got its last filter row
+                    const uint32_t g = orow + (uint32_t)(ii - 2 * ph);
+                    umma_commit_pred(&acc_full[g % (uint32_t)R], leader);
+                }
+            }
+            orow += (uint32_t)rows_out;
+        }
+    } else {
+        // ===== epilogue (warps 2..5: TMEM lane group = warp % 4) =====
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        // all slots start zeroed and released
+        for (int s = 0; s < R; s++)
+            for (uint32_t c0 = 0; c0 < BN; c0 += 16) tmem_st_zero_32x32b_x16(tmem_base + lane_addr + (uint32_t)s * BN + c0);
+        tmem_st_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0)
+            for (int s = 0; s < R; s++) mbar_arrive(&acc_empty[s]);
+        uint32_t orow = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            const int tx = item % p.tiles_x, rest = item / p.tiles_x;
+            const int seg = rest % p.n_seg, n = rest / p.n_seg;
+            const int ya = seg * p.seg_h, yb = min(p.H, ya + p.seg_h);
+            const int px = tx * kRowTile + m;
+            const bool inb = px < p.W;
+            for (int y = ya; y < yb; y++) {
+                const uint32_t g = orow + (uint32_t)(y - ya);
+                const uint32_t slot = g % (uint32_t)R;
+                mbar_wait(&acc_full[slot], (g / (uint32_t)R) & 1u);
+                tcgen05_fence_after();
+                const uint32_t tmem_acc = tmem_base + lane_addr + slot * BN;
+                const size_t pix = ((size_t)n * p.H + y) * p.W + px;
+                for (uint32_t c0 = 0; c0 < BN; c0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld_32x32b_x16(tmem_acc + c0, v);
+                    tmem_ld_wait();
+                    tmem_st_zero_32x32b_x16(tmem_acc + c0);
+                    float f[16];
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        float x = __uint_as_float(v[j]) + __ldg(p.bias + c0 + j);
+                        f[j] = x > 0.f ? x : x * p.slope;
+                    }
+                    if (inb) {
+                        if (p.out_mode == 0) {
+                            __half2 h[8];
+#pragma unroll
+                            for (int j = 0; j < 8; j++) h[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+                            uint4 *dst = (uint4 *)((__half *)p.out + pix * p.out_cstride + c0);
+                            dst[0] = *(uint4 *)&h[0];
+                            dst[1] = *(uint4 *)&h[4];
+                        } else if (c0 == 0) {
+                            float4 *dst = (float4 *)((float *)p.out + pix * 8);
+                            dst[0] = make_float4(f[0], f[1], f[2], f[3]);
+                            dst[1] = make_float4(f[4], f[5], f[6], f[7]);
+                        }
+                    }
+                }
+                tmem_st_wait();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[slot]);
+            }
+            orow += (uint32_t)(yb - ya);
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    }
+}
+
 }  // namespace
 
 // =============================================================================================
@@ -563,13 +798,56 @@ static int make_rowseg_tmap(CUtensorMap *tm, const void *ptr, int N, int H, int 
     return V2E_OK;
 }
 
-// Slab width and ring depth for the strip kernel; returns KC (0: layer does not qualify), *nslot_out.
+// strip2 configuration of a layer: ring entries (one slab of one input row each), accumulator slots, TMEM
+// columns, CTAs per SM. Returns 0 when the layer does not fit (weights resident + >= 3 ring entries,
+// R >= KH+1 slots of BN columns).
+static int strip2_config(int C1, int C2, int Cout_pad, int KH, int KW, int kc, int *nslot, int *acc_slots,
+                         int *tmem_cols, int *ctas_per_sm) {
+    if (Cout_pad > 64) return 0;
+    const int slabs = (C1 + C2) / kc;
+    const size_t wb = ((size_t)slabs * KH * KW * Cout_pad * kc * 2 + 1023) & ~(size_t)1023;
+    const size_t slab = ((size_t)(kRowTile + KW - 1) * kc * 2 + 1023) & ~(size_t)1023;
+    const size_t half = 110 * 1024, full = 222 * 1024;
+    int two = 0;
+    if (wb + 2048 + 4 * slab <= half && (KH + 1) * Cout_pad <= 256) two = 1;
+    const size_t budget = two ? half : full;
+    if (wb + 2048 + 3 * slab > budget) return 0;
+    int ns = (int)((budget - wb - 2048) / slab);
+    if (ns > kMaxSlot) ns = kMaxSlot;
+    const int tmem_budget = two ? 256 : 512;
+    int R = tmem_budget / Cout_pad;
+    if (R > kMaxAcc) R = kMaxAcc;
+    if (R < KH + 1) return 0;
+    int cols = 32;
+    while (cols < R * Cout_pad) cols <<= 1;
+    *nslot = ns; *acc_slots = R; *tmem_cols = cols; *ctas_per_sm = two ? 2 : 1;
+    return 1;
+}
+
+static int strip_variant_forced() {
+    static int v = -2;
+    if (v == -2) {
+        const char *e = getenv("V2E_STRIP_VARIANT");       // A/B measurements: 0 = per-tap MMAs, 1 = row-stacked
+        v = e ? atoi(e) : -1;
+    }
+    return v;
+}
+
+// Slab width and ring depth for the strip kernels; returns KC (0: layer does not qualify), *nslot_out.
 int v2e_strip_pick(int C1, int C2, int Cout_pad, int KH, int KW, int W, int *nslot_out) {
     // wide layers only: below ~4 row tiles per image row the per-tap kernel's 8x16 tiles waste less
     if (Cout_pad > 128 || W < 4 * kRowTile || (KW != 3 && KW != 5 && KW != 7)) return 0;
     const int g = C2 ? (C1 < C2 ? C1 : C2) : C1;
     const int kc = g % 64 == 0 ? 64 : (g % 32 == 0 ? 32 : 16);
     const int slabs = (C1 + C2) / kc;
+    {
+        int ns, R, cols, cps;
+        if (strip_variant_forced() != 0 && strip2_config(C1, C2, Cout_pad, KH, KW, kc, &ns, &R, &cols, &cps)) {
+            if (nslot_out) *nslot_out = ns;
+            return kc;
+        }
+        if (strip_variant_forced() == 1) return 0;
+    }
     const size_t wb = ((size_t)slabs * KH * KW * Cout_pad * kc * 2 + 1023) & ~(size_t)1023;
     const size_t slab = ((size_t)(kRowTile + KW - 1) * kc * 2 + 1023) & ~(size_t)1023;
     // two CTAs per SM (two MMA issue streams, epilogues overlap) when weights + a (KH+2)-row ring fit in
@@ -608,12 +886,20 @@ int v2e_strip_prepare(V2eStripLaunch *L, const void *x1, int C1, const void *x2,
     p.n_seg = (H + seg_h - 1) / seg_h;
     p.n_items = strips * p.n_seg;
     p.nslot = nslot;
+    int ctas_per_sm = 0;
+    {
+        int ns, R, cols, cps;
+        if (strip_variant_forced() != 0 && strip2_config(C1, C2, Cout_pad, KH, KW, KC, &ns, &R, &cols, &cps)) {
+            p.variant = 1; p.nslot = ns; p.acc_slots = R; p.tmem_cols = cols; ctas_per_sm = cps;
+        }
+    }
     const int slabs = (C1 + C2) / KC, taps = KH * KW;
     p.slab_bytes = (int)(((size_t)(kRowTile + KW - 1) * KC * 2 + 1023) & ~(size_t)1023);
     p.w_bytes = slabs * taps * Cout_pad * KC * 2;
     int rows_total = slabs * taps * Cout_pad;
     int rpl = 256;                                           // rows per weight load: largest divisor <= 256, multiple of 8
     while ((rows_total % rpl) || (rpl % 8)) rpl--;
+    if (p.variant == 1) rpl = Cout_pad;                      // strip2 places every (slab, r, s) tile itself
     p.w_rows_per_load = rpl;
     p.w_loads = rows_total / rpl;
     p.out_cstride = out_cstride; p.out_mode = out_mode; p.co_real = co_real; p.slope = slope;
@@ -633,8 +919,9 @@ int v2e_strip_prepare(V2eStripLaunch *L, const void *x1, int C1, const void *x2,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return v2e_set_error(V2E_E_CUDA, "cuTensorMapEncodeTiled failed for strip weights%s", "");
     }
-    L->smem = (size_t)((p.w_bytes + 1023) & ~1023) + (size_t)nslot * p.slab_bytes * slabs + 1024;
-    const int ctas = (L->smem + 1024 <= 113 * 1024) ? 2 * n_sms : n_sms;
+    if (p.variant == 1) L->smem = (size_t)((p.w_bytes + 1023) & ~1023) + (size_t)p.nslot * p.slab_bytes + 1024;
+    else L->smem = (size_t)((p.w_bytes + 1023) & ~1023) + (size_t)nslot * p.slab_bytes * slabs + 1024;
+    const int ctas = p.variant == 1 ? ctas_per_sm * n_sms : ((L->smem + 1024 <= 113 * 1024) ? 2 * n_sms : n_sms);
     L->grid = p.n_items < ctas ? p.n_items : ctas;
     return V2E_OK;
 }
@@ -647,7 +934,15 @@ int v2e_strip_launch(const V2eStripLaunch *L, cudaStream_t st) {
             cudaFuncSetAttribute(conv_strip_kernel<KW_, KC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); \
             attr_set = true;                                                                                    \
         }                                                                                                       \
-        conv_strip_kernel<KW_, KC_><<<L->grid, kStripThreads, L->smem, st>>>(L->tmA, L->tmA2, L->tmB, L->p);     \
+        static bool attr2_set = false;                                                                          \
+        if (!attr2_set) {                                                                                       \
+            cudaFuncSetAttribute(conv_strip2_kernel<KW_, KC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); \
+            attr2_set = true;                                                                                   \
+        }                                                                                                       \
+        if (L->p.variant == 1)                                                                                  \
+            conv_strip2_kernel<KW_, KC_><<<L->grid, kStrip2Threads, L->smem, st>>>(L->tmA, L->tmA2, L->tmB, L->p); \
+        else                                                                                                    \
+            conv_strip_kernel<KW_, KC_><<<L->grid, kStripThreads, L->smem, st>>>(L->tmA, L->tmA2, L->tmB, L->p);  \
         launched = true;                                                                                        \
     }
     bool launched = false;

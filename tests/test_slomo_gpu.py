@@ -101,6 +101,9 @@ STRIP_CASES = [
     (1, 4, 512, 64, 0, 32, 3, 0), (1, 40, 512, 32, 0, 32, 3, 0), (1, 33, 530, 16, 0, 32, 3, 0),
     (1, 70, 512, 32, 0, 32, 7, 0), (2, 64, 640, 12, 0, 32, 7, 0), (2, 75, 576, 32, 32, 32, 3, 0),
     (1, 48, 640, 32, 0, 64, 5, 0), (1, 60, 512, 32, 0, 5, 3, 1), (3, 5, 513, 64, 0, 32, 3, 0),
+    # output channels split over two CTA classes (weights of a slice resident), 2-slab inputs, short items
+    (1, 37, 640, 64, 0, 64, 5, 0), (1, 20, 640, 128, 0, 64, 3, 0), (2, 24, 512, 64, 64, 64, 3, 0),
+    (1, 2, 512, 32, 0, 32, 7, 0), (1, 1, 640, 16, 0, 32, 3, 0),
 ]
 
 
@@ -120,8 +123,8 @@ def pack_w_strip(w, C1, C2, KC):
 
 @pytest.mark.parametrize("case", STRIP_CASES)
 def test_conv_strip_kernel_matches_torch(case):
-    """Sliding-window strip kernel (resident weights, input-row ring, descriptor-shifted taps, two MMA
-    issuers) vs torch conv2d on the same fp16-rounded operands. Same tolerance as the per-tap kernel."""
+    """Strip kernels (resident weights, input-row ring, descriptor-shifted taps; row-stacked MMAs into a TMEM
+    accumulator ring) vs torch conv2d on the same fp16-rounded operands. Same tolerance as the per-tap kernel."""
     N, H, W, C1, C2, Cout, K, mode = case
     Lm, L = _lib()
     g = torch.Generator().manual_seed(hash(case) & 0xFFFF)

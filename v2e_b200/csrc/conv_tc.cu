@@ -202,6 +202,8 @@ struct StripParams {
     int nslot;
     int variant;                   // 0: per-tap MMAs (first strip kernel), 1: row-stacked (strip2)
     int acc_slots, tmem_cols;      // strip2: accumulator ring (slots of BN columns), TMEM allocation
+    int n_split, cout_pad;         // strip2: output channels split over n_split CTA classes of BN = cout_pad / n_split
+                                   // (layers whose whole weight tensor does not fit in shared memory)
     int slab_bytes;                // bytes of one row buffer of one slab (1024-aligned)
     int w_bytes;                   // all weights: slabs*taps*BN*KC*2
     int w_rows_per_load, w_loads;
@@ -460,6 +462,9 @@ conv_strip2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int R = p.acc_slots;
     const uint32_t BN = (uint32_t)p.BN;
     const uint32_t tile_bytes = BN * (uint32_t)KC * 2u;        // one (slab, r, s) weight tile
+    // CTA class: which slice of the output channels this CTA computes (weights resident per slice)
+    const int split = (int)blockIdx.x % p.n_split, co_off = split * (int)BN;
+    const int item0 = (int)blockIdx.x / p.n_split, item_step = (int)gridDim.x / p.n_split;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.nslot; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -489,9 +494,9 @@ conv_strip2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 for (int r = 0; r < KH; r++)
                     for (int s = 0; s < KW; s++)
                         tma_load_2d(smem + (size_t)((sl * KW + s) * KH + (KH - 1 - r)) * tile_bytes, &tmB, &w_bar, 0,
-                                    ((sl * KH + r) * KW + s) * (int)BN);
+                                    ((sl * KH + r) * KW + s) * p.cout_pad + co_off);
             uint32_t cnt = 0;                                   // ring entries filled so far (all items)
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            for (int item = item0; item < p.n_items; item += item_step) {
                 const int tx = item % p.tiles_x, rest = item / p.tiles_x;
                 const int seg = rest % p.n_seg, n = rest / p.n_seg;
                 const int ya = seg * p.seg_h, yb = min(p.H, ya + p.seg_h);
@@ -525,7 +530,7 @@ conv_strip2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         mbar_wait(&w_bar, 0);
         uint32_t cnt = 0;                                   // ring entries consumed so far
         uint32_t orow = 0;                                  // output rows started before this item
-        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        for (int item = item0; item < p.n_items; item += item_step) {
             const int rest = item / p.tiles_x;
             const int seg = rest % p.n_seg;
             const int ya = seg * p.seg_h, yb = min(p.H, ya + p.seg_h);
@@ -592,7 +597,7 @@ conv_strip2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (lane == 0)
             for (int s = 0; s < R; s++) mbar_arrive(&acc_empty[s]);
         uint32_t orow = 0;
-        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        for (int item = item0; item < p.n_items; item += item_step) {
             const int tx = item % p.tiles_x, rest = item / p.tiles_x;
             const int seg = rest % p.n_seg, n = rest / p.n_seg;
             const int ya = seg * p.seg_h, yb = min(p.H, ya + p.seg_h);
@@ -613,7 +618,7 @@ conv_strip2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     float f[16];
 #pragma unroll
                     for (int j = 0; j < 16; j++) {
-                        float x = __uint_as_float(v[j]) + __ldg(p.bias + c0 + j);
+                        float x = __uint_as_float(v[j]) + __ldg(p.bias + co_off + c0 + j);
                         f[j] = x > 0.f ? x : x * p.slope;
                     }
                     if (inb) {
@@ -621,7 +626,7 @@ conv_strip2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                             __half2 h[8];
 #pragma unroll
                             for (int j = 0; j < 8; j++) h[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
-                            uint4 *dst = (uint4 *)((__half *)p.out + pix * p.out_cstride + c0);
+                            uint4 *dst = (uint4 *)((__half *)p.out + pix * p.out_cstride + co_off + c0);
                             dst[0] = *(uint4 *)&h[0];
                             dst[1] = *(uint4 *)&h[4];
                         } else if (c0 == 0) {
@@ -802,26 +807,31 @@ static int make_rowseg_tmap(CUtensorMap *tm, const void *ptr, int N, int H, int 
 // columns, CTAs per SM. Returns 0 when the layer does not fit (weights resident + >= 3 ring entries,
 // R >= KH+1 slots of BN columns).
 static int strip2_config(int C1, int C2, int Cout_pad, int KH, int KW, int kc, int *nslot, int *acc_slots,
-                         int *tmem_cols, int *ctas_per_sm) {
+                         int *tmem_cols, int *ctas_per_sm, int *n_split) {
     if (Cout_pad > 64) return 0;
     const int slabs = (C1 + C2) / kc;
-    const size_t wb = ((size_t)slabs * KH * KW * Cout_pad * kc * 2 + 1023) & ~(size_t)1023;
     const size_t slab = ((size_t)(kRowTile + KW - 1) * kc * 2 + 1023) & ~(size_t)1023;
     const size_t half = 110 * 1024, full = 222 * 1024;
-    int two = 0;
-    if (wb + 2048 + 4 * slab <= half && (KH + 1) * Cout_pad <= 256) two = 1;
-    const size_t budget = two ? half : full;
-    if (wb + 2048 + 3 * slab > budget) return 0;
-    int ns = (int)((budget - wb - 2048) / slab);
-    if (ns > kMaxSlot) ns = kMaxSlot;
-    const int tmem_budget = two ? 256 : 512;
-    int R = tmem_budget / Cout_pad;
-    if (R > kMaxAcc) R = kMaxAcc;
-    if (R < KH + 1) return 0;
-    int cols = 32;
-    while (cols < R * Cout_pad) cols <<= 1;
-    *nslot = ns; *acc_slots = R; *tmem_cols = cols; *ctas_per_sm = two ? 2 : 1;
-    return 1;
+    for (int split = 1; split <= 2; split++) {
+        const int bn = Cout_pad / split;
+        if (bn < 16 || bn % 16) break;
+        const size_t wb = ((size_t)slabs * KH * KW * bn * kc * 2 + 1023) & ~(size_t)1023;
+        int two = 0;
+        if (wb + 2048 + 4 * slab <= half && (KH + 1) * bn <= 256) two = 1;
+        const size_t budget = two ? half : full;
+        if (wb + 2048 + 3 * slab > budget) continue;
+        int ns = (int)((budget - wb - 2048) / slab);
+        if (ns > kMaxSlot) ns = kMaxSlot;
+        const int tmem_budget = two ? 256 : 512;
+        int R = tmem_budget / bn;
+        if (R > kMaxAcc) R = kMaxAcc;
+        if (R < KH + 1) continue;
+        int cols = 32;
+        while (cols < R * bn) cols <<= 1;
+        *nslot = ns; *acc_slots = R; *tmem_cols = cols; *ctas_per_sm = two ? 2 : 1; *n_split = split;
+        return 1;
+    }
+    return 0;
 }
 
 static int strip_variant_forced() {
@@ -841,8 +851,8 @@ int v2e_strip_pick(int C1, int C2, int Cout_pad, int KH, int KW, int W, int *nsl
     const int kc = g % 64 == 0 ? 64 : (g % 32 == 0 ? 32 : 16);
     const int slabs = (C1 + C2) / kc;
     {
-        int ns, R, cols, cps;
-        if (strip_variant_forced() != 0 && strip2_config(C1, C2, Cout_pad, KH, KW, kc, &ns, &R, &cols, &cps)) {
+        int ns, R, cols, cps, nsp;
+        if (strip_variant_forced() != 0 && strip2_config(C1, C2, Cout_pad, KH, KW, kc, &ns, &R, &cols, &cps, &nsp)) {
             if (nslot_out) *nslot_out = ns;
             return kc;
         }
@@ -888,18 +898,20 @@ int v2e_strip_prepare(V2eStripLaunch *L, const void *x1, int C1, const void *x2,
     p.nslot = nslot;
     int ctas_per_sm = 0;
     {
-        int ns, R, cols, cps;
-        if (strip_variant_forced() != 0 && strip2_config(C1, C2, Cout_pad, KH, KW, KC, &ns, &R, &cols, &cps)) {
+        int ns, R, cols, cps, nsp;
+        p.n_split = 1; p.cout_pad = Cout_pad;
+        if (strip_variant_forced() != 0 && strip2_config(C1, C2, Cout_pad, KH, KW, KC, &ns, &R, &cols, &cps, &nsp)) {
             p.variant = 1; p.nslot = ns; p.acc_slots = R; p.tmem_cols = cols; ctas_per_sm = cps;
+            p.n_split = nsp; p.BN = Cout_pad / nsp;
         }
     }
     const int slabs = (C1 + C2) / KC, taps = KH * KW;
     p.slab_bytes = (int)(((size_t)(kRowTile + KW - 1) * KC * 2 + 1023) & ~(size_t)1023);
-    p.w_bytes = slabs * taps * Cout_pad * KC * 2;
+    p.w_bytes = slabs * taps * p.BN * KC * 2;          // resident per CTA (strip2: its slice of the output channels)
     int rows_total = slabs * taps * Cout_pad;
     int rpl = 256;                                           // rows per weight load: largest divisor <= 256, multiple of 8
     while ((rows_total % rpl) || (rpl % 8)) rpl--;
-    if (p.variant == 1) rpl = Cout_pad;                      // strip2 places every (slab, r, s) tile itself
+    if (p.variant == 1) rpl = p.BN;                          // strip2 places every (slab, r, s) tile itself
     p.w_rows_per_load = rpl;
     p.w_loads = rows_total / rpl;
     p.out_cstride = out_cstride; p.out_mode = out_mode; p.co_real = co_real; p.slope = slope;
@@ -923,6 +935,12 @@ int v2e_strip_prepare(V2eStripLaunch *L, const void *x1, int C1, const void *x2,
     else L->smem = (size_t)((p.w_bytes + 1023) & ~1023) + (size_t)nslot * p.slab_bytes * slabs + 1024;
     const int ctas = p.variant == 1 ? ctas_per_sm * n_sms : ((L->smem + 1024 <= 113 * 1024) ? 2 * n_sms : n_sms);
     L->grid = p.n_items < ctas ? p.n_items : ctas;
+    if (p.variant == 1 && p.n_split > 1) {                   // every CTA class walks all items
+        int per = ctas / p.n_split;
+        if (per > p.n_items) per = p.n_items;
+        if (per < 1) per = 1;
+        L->grid = per * p.n_split;
+    }
     return V2E_OK;
 }
 

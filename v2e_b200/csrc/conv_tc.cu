@@ -26,6 +26,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <vector>
 #include <stdlib.h>
 
 #include "../../include/v2e_b200.h"
@@ -202,6 +203,7 @@ struct StripParams {
     int nslot;
     int variant;                   // 0: per-tap MMAs (first strip kernel), 1: row-stacked (strip2)
     int acc_slots, tmem_cols;      // strip2: accumulator ring (slots of BN columns), TMEM allocation
+    long long *dbg;                // STRIP2_DEBUG builds: per-CTA issuer wait cycles
     int n_split, cout_pad;         // strip2: output channels split over n_split CTA classes of BN = cout_pad / n_split
                                    // (layers whose whole weight tensor does not fit in shared memory)
     int slab_bytes;                // bytes of one row buffer of one slab (1024-aligned)
@@ -441,7 +443,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 //   warps 2..5 : epilogue: tcgen05.ld, bias, LeakyReLU, store; tcgen05.st zeros; release the slot.
 // ---------------------------------------------------------------------------------------------
 constexpr int kMaxAcc = 32;
-constexpr int kStrip2Threads = 192;
+constexpr int kStrip2Threads = 320;      // warps: 0 producer, 1 issuer, 2..9 epilogue
 
 template <int KW, int KC>
 __global__ void __launch_bounds__(kStrip2Threads)
@@ -469,7 +471,7 @@ conv_strip2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.nslot; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(&w_bar, 1);
-        for (int s = 0; s < R; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+        for (int s = 0; s < R; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], BN >= 32 ? 8u : 4u); }
         fence_barrier_init();
     }
     if (warp == 0 && lane == 0) {
@@ -530,6 +532,9 @@ conv_strip2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         mbar_wait(&w_bar, 0);
         uint32_t cnt = 0;                                   // ring entries consumed so far
         uint32_t orow = 0;                                  // output rows started before this item
+#ifdef STRIP2_DEBUG
+        long long t_acc = 0, t_full = 0, t_all = clock64();
+#endif
         for (int item = item0; item < p.n_items; item += item_step) {
             const int rest = item / p.tiles_x;
             const int seg = rest % p.n_seg;
@@ -540,7 +545,13 @@ conv_strip2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 const int yl = max(0, ii - 2 * ph), yh = min(rows_out - 1, ii);
                 if (ii < rows_out) {                        // output row ii starts here: its slot must be drained
                     const uint32_t g = orow + (uint32_t)ii;
+#ifdef STRIP2_DEBUG
+                    long long t0 = clock64();
+#endif
                     mbar_wait(&acc_empty[g % (uint32_t)R], (g / (uint32_t)R) & 1u);
+#ifdef STRIP2_DEBUG
+                    t_acc += clock64() - t0;
+#endif
                     tcgen05_fence_after();
                 }
                 // contiguous slot ranges of the stack (ring wrap, N <= 256)
@@ -558,7 +569,13 @@ conv_strip2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 }
                 for (int sl = 0; sl < slabs; sl++, cnt++) {
                     const uint32_t e = cnt % (uint32_t)p.nslot;
+#ifdef STRIP2_DEBUG
+                    long long t1 = clock64();
+#endif
                     mbar_wait(&full_bar[e], (cnt / (uint32_t)p.nslot) & 1u);
+#ifdef STRIP2_DEBUG
+                    t_full += clock64() - t1;
+#endif
                     tcgen05_fence_after();
                     const uint32_t a_lo = ring16 + e * slab16;
                     const uint32_t b_sl = w16 + (uint32_t)(sl * KW * KH) * tile16;
@@ -583,65 +600,99 @@ conv_strip2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             }
             orow += (uint32_t)rows_out;
         }
+#ifdef STRIP2_DEBUG
+        if (lane == 0 && p.dbg) {
+            p.dbg[blockIdx.x * 4 + 0] = t_acc; p.dbg[blockIdx.x * 4 + 1] = t_full;
+            p.dbg[blockIdx.x * 4 + 2] = clock64() - t_all; p.dbg[blockIdx.x * 4 + 3] = orow;
+        }
+#endif
     } else {
-        // ===== epilogue (warps 2..5: TMEM lane group = warp % 4) =====
+        // ===== epilogue (warps 2..9). A warp reads TMEM lanes (warp % 4)*32..+31 = 32 pixels of the row; the two
+        // warps that share a lane group split the BN columns (BN = 16: the second group idles). One warp per
+        // scheduler cannot hide the ld -> math -> store chain within a row period of the stacked MMAs, so the
+        // epilogue is spread over eight warps and kept short: bias in registers, one tcgen05.ld per row, the
+        // output pointer advanced instead of recomputed. =====
         const int q = warp & 3;
+        const int grp = (warp - 2) >> 2;                      // 0: warps 2..5, 1: warps 6..9
         const int m = q * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        // all slots start zeroed and released
-        for (int s = 0; s < R; s++)
-            for (uint32_t c0 = 0; c0 < BN; c0 += 16) tmem_st_zero_32x32b_x16(tmem_base + lane_addr + (uint32_t)s * BN + c0);
-        tmem_st_wait();
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0)
-            for (int s = 0; s < R; s++) mbar_arrive(&acc_empty[s]);
-        uint32_t orow = 0;
-        for (int item = item0; item < p.n_items; item += item_step) {
-            const int tx = item % p.tiles_x, rest = item / p.tiles_x;
-            const int seg = rest % p.n_seg, n = rest / p.n_seg;
-            const int ya = seg * p.seg_h, yb = min(p.H, ya + p.seg_h);
-            const int px = tx * kRowTile + m;
-            const bool inb = px < p.W;
-            for (int y = ya; y < yb; y++) {
-                const uint32_t g = orow + (uint32_t)(y - ya);
-                const uint32_t slot = g % (uint32_t)R;
-                mbar_wait(&acc_full[slot], (g / (uint32_t)R) & 1u);
-                tcgen05_fence_after();
-                const uint32_t tmem_acc = tmem_base + lane_addr + slot * BN;
-                const size_t pix = ((size_t)n * p.H + y) * p.W + px;
-                for (uint32_t c0 = 0; c0 < BN; c0 += 16) {
-                    uint32_t v[16];
-                    tmem_ld_32x32b_x16(tmem_acc + c0, v);
-                    tmem_ld_wait();
-                    tmem_st_zero_32x32b_x16(tmem_acc + c0);
-                    float f[16];
+        const uint32_t ncol = BN >= 32 ? BN / 2 : BN;         // columns of this warp: 8 (never), 16 or 32
+        const uint32_t col0 = (uint32_t)grp * ncol;
+        if (grp == 0 || BN >= 32) {
+            // all slots start zeroed and released
+            for (int s = 0; s < R; s++)
+                for (uint32_t c0 = 0; c0 < ncol; c0 += 16)
+                    tmem_st_zero_32x32b_x16(tmem_base + lane_addr + (uint32_t)s * BN + col0 + c0);
+            tmem_st_wait();
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0)
+                for (int s = 0; s < R; s++) mbar_arrive(&acc_empty[s]);
+            float bias_r[32];
 #pragma unroll
-                    for (int j = 0; j < 16; j++) {
-                        float x = __uint_as_float(v[j]) + __ldg(p.bias + co_off + c0 + j);
-                        f[j] = x > 0.f ? x : x * p.slope;
-                    }
+            for (int j = 0; j < 32; j++) bias_r[j] = (uint32_t)j < ncol ? __ldg(p.bias + co_off + col0 + j) : 0.f;
+            const float slope = p.slope;
+            uint32_t orow = 0;
+            for (int item = item0; item < p.n_items; item += item_step) {
+                const int tx = item % p.tiles_x, rest = item / p.tiles_x;
+                const int seg = rest % p.n_seg, n = rest / p.n_seg;
+                const int ya = seg * p.seg_h, yb = min(p.H, ya + p.seg_h);
+                const int px = tx * kRowTile + m;
+                const bool inb = px < p.W;
+                const size_t pix0 = ((size_t)n * p.H + ya) * p.W + px;
+                __half *o16 = (__half *)p.out + pix0 * p.out_cstride + co_off + col0;
+                float *o32 = (float *)p.out + pix0 * 8;
+                const size_t step16 = (size_t)p.W * p.out_cstride, step32 = (size_t)p.W * 8;
+                uint32_t g = orow, slot = g % (uint32_t)R, par = (g / (uint32_t)R) & 1u;
+                for (int y = ya; y < yb; y++) {
+                    mbar_wait(&acc_full[slot], par);
+                    tcgen05_fence_after();
+                    const uint32_t tmem_acc = tmem_base + lane_addr + slot * BN + col0;
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x16(tmem_acc, v);
+                    if (ncol == 32) tmem_ld_32x32b_x16(tmem_acc + 16, v + 16);
+                    tmem_ld_wait();
+                    tmem_st_zero_32x32b_x16(tmem_acc);
+                    if (ncol == 32) tmem_st_zero_32x32b_x16(tmem_acc + 16);
                     if (inb) {
                         if (p.out_mode == 0) {
-                            __half2 h[8];
 #pragma unroll
-                            for (int j = 0; j < 8; j++) h[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
-                            uint4 *dst = (uint4 *)((__half *)p.out + pix * p.out_cstride + co_off + c0);
-                            dst[0] = *(uint4 *)&h[0];
-                            dst[1] = *(uint4 *)&h[4];
-                        } else if (c0 == 0) {
-                            float4 *dst = (float4 *)((float *)p.out + pix * 8);
+                            for (int c0 = 0; c0 < 32; c0 += 16) {
+                                if ((uint32_t)c0 < ncol) {
+                                    __half2 h[8];
+#pragma unroll
+                                    for (int j = 0; j < 8; j++) {
+                                        const float x0 = __uint_as_float(v[c0 + 2 * j]) + bias_r[c0 + 2 * j];
+                                        const float x1 = __uint_as_float(v[c0 + 2 * j + 1]) + bias_r[c0 + 2 * j + 1];
+                                        h[j] = __floats2half2_rn(fmaxf(x0, x0 * slope), fmaxf(x1, x1 * slope));
+                                    }
+                                    uint4 *dst = (uint4 *)(o16 + c0);
+                                    dst[0] = *(uint4 *)&h[0];
+                                    dst[1] = *(uint4 *)&h[4];
+                                }
+                            }
+                        } else if (grp == 0) {
+                            float f[8];
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                const float x = __uint_as_float(v[j]) + bias_r[j];
+                                f[j] = fmaxf(x, x * slope);
+                            }
+                            float4 *dst = (float4 *)o32;
                             dst[0] = make_float4(f[0], f[1], f[2], f[3]);
                             dst[1] = make_float4(f[4], f[5], f[6], f[7]);
                         }
                     }
+                    o16 += step16;
+                    o32 += step32;
+                    tmem_st_wait();
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[slot]);
+                    if (++slot == (uint32_t)R) { slot = 0; par ^= 1u; }
                 }
-                tmem_st_wait();
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[slot]);
+                orow += (uint32_t)(yb - ya);
             }
-            orow += (uint32_t)(yb - ya);
         }
     }
     __syncthreads();
@@ -900,7 +951,9 @@ int v2e_strip_prepare(V2eStripLaunch *L, const void *x1, int C1, const void *x2,
     {
         int ns, R, cols, cps, nsp;
         p.n_split = 1; p.cout_pad = Cout_pad;
-        if (strip_variant_forced() != 0 && strip2_config(C1, C2, Cout_pad, KH, KW, KC, &ns, &R, &cols, &cps, &nsp)) {
+        // strip2's epilogue evaluates the LeakyReLU as max(x, slope*x): 0 <= slope <= 1
+        if (strip_variant_forced() != 0 && slope >= 0.f && slope <= 1.f &&
+            strip2_config(C1, C2, Cout_pad, KH, KW, KC, &ns, &R, &cols, &cps, &nsp)) {
             p.variant = 1; p.nslot = ns; p.acc_slots = R; p.tmem_cols = cols; ctas_per_sm = cps;
             p.n_split = nsp; p.BN = Cout_pad / nsp;
         }
@@ -944,7 +997,26 @@ int v2e_strip_prepare(V2eStripLaunch *L, const void *x1, int C1, const void *x2,
     return V2E_OK;
 }
 
-int v2e_strip_launch(const V2eStripLaunch *L, cudaStream_t st) {
+#ifdef STRIP2_DEBUG
+static long long *g_dbg = nullptr;
+extern "C" void v2e_strip2_debug_dump(void) {
+    if (!g_dbg) return;
+    std::vector<long long> h(4 * 1024);
+    cudaMemcpy(h.data(), g_dbg, h.size() * 8, cudaMemcpyDeviceToHost);
+    double a = 0, f = 0, t = 0; int n = 0;
+    for (int i = 0; i < 1024; i++) if (h[i * 4 + 2]) { a += h[i * 4]; f += h[i * 4 + 1]; t += h[i * 4 + 2]; n++; }
+    if (n) printf("strip2 issuer: %d CTAs, avg cycles total %.0f, wait acc_empty %.0f (%.1f%%), wait full %.0f (%.1f%%), rows/CTA %.0f\n",
+                  n, t / n, a / n, 100 * a / t, f / n, 100 * f / t, (double)h[3]);
+    cudaMemset(g_dbg, 0, h.size() * 8);
+}
+#endif
+int v2e_strip_launch(const V2eStripLaunch *L0, cudaStream_t st) {
+    V2eStripLaunch Lc = *L0;
+    V2eStripLaunch *L = &Lc;
+#ifdef STRIP2_DEBUG
+    if (!g_dbg) { cudaMalloc((void **)&g_dbg, 4 * 1024 * 8); cudaMemset(g_dbg, 0, 4 * 1024 * 8); }
+    L->p.dbg = g_dbg;
+#endif
 #define STRIP_CASE(KW_, KC_)                                                                                  \
     if (L->p.KW == KW_ && L->p.KC == KC_) {                                                                    \
         static bool attr_set = false;                                                                           \

@@ -50,6 +50,11 @@ typedef struct OracleEmuCfg {
     int32_t csdvs;              /* 1: centre-surround enabled (state->surround != NULL) */
     int32_t _pad;
     double cs_tau_p_s, cs_tau_h_s;  /* emulator.py:1069-1073 */
+    int32_t scidvs;             /* emulator.py:308: nonlinear CR high-pass in front of the change amplifier */
+    int32_t pr_noise;           /* emulator.py:192: Gaussian photoreceptor noise instead of injected shot events */
+    int32_t scidvs_first;       /* this is the frame at which scidvs_highpass is created (emulator.py:720-722) */
+    int32_t _pad2;
+    double pr_vrms;             /* photoreceptor_noise_vrms of this frame (emulator.py:695-697), computed by the caller */
 } OracleEmuCfg;
 
 typedef struct OracleEmuState {
@@ -60,6 +65,11 @@ typedef struct OracleEmuState {
     float *tmem;                /* or NULL when refractory_period_s<=0 */
     double *surround;           /* CSDVS h, or NULL */
     const float *linlog_lut;    /* 256 entries built by the caller with the reference formula */
+    void *hp;                   /* scidvs_highpass, S[H*W] (zeros_like(lp_log_frame)), or NULL */
+    void *prev_photo;           /* scidvs_previous_photo, S[H*W] */
+    const float *tau_arr;       /* scidvs_tau_arr float32 (emulator.py:480-483) */
+    float *noise_arr;           /* photoreceptor_noise_arr float32 (zeros_like of the float32 log frame, :684) */
+    const float *pr_randn;      /* this frame's torch.randn field (emulator.py:698) */
 } OracleEmuState;
 
 /* ---- ATen restatements ------------------------------------------------- */
@@ -254,9 +264,49 @@ long oracle_emu_frame(const OracleEmuCfg *cfg, OracleEmuState *st, const void *f
             ((float *)st->lp)[i] = log_new_f32(st, x);
         }
     }
+    /* photoreceptor noise (emulator.py:694-703): noise = vrms * randn (Python float x float32 tensor ->
+     * float32 product), then low_pass_filter(noise, arr, None, dt, cutoff): eps = dt/tau is a Python float,
+     * so (1-eps) and eps meet a float32 tensor and are rounded to float32; no clamp (emulator_utils.py:96-99) */
+    if (cfg->pr_noise && st->noise_arr) {
+        float vr = (float)cfg->pr_vrms;
+        for (long i = 0; i < n; i++) {
+            float noise = vr * st->pr_randn[i];
+            if (cfg->cutoff_hz > 0) {
+                double eps = dt / tau;
+                float ome = (float)(1.0 - eps), ef = (float)eps;
+                float a = ome * st->noise_arr[i], b = ef * noise;
+                st->noise_arr[i] = a + b;
+            } else {
+                st->noise_arr[i] = noise;
+            }
+        }
+    }
     /* surround diffusion needs the whole lp field (emulator.py:707-708) */
     if (cfg->csdvs && st->surround)
         *cs_steps_out = oracle_emu_csdvs(cfg, st, dt, cfg->cs_tau_p_s, cfg->cs_tau_h_s);
+    /* SCIDVS (emulator.py:58-80, 719-725): hp += (lp - lp_prev) - dt * (1/tau_px) * sinh(hp / efold);
+     * 1/tau_px is a float32 tensor, hp/efold and sinh are evaluated in hp's dtype */
+    if (cfg->scidvs && st->hp) {
+        const double efold = 1 / 0.7;
+        for (long i = 0; i < n; i++) {
+            float inv_tau = 1.0f / st->tau_arr[i];
+            if (cfg->state_f64) {
+                double *hp = (double *)st->hp, *pv = (double *)st->prev_photo, lp = ((double *)st->lp)[i];
+                if (cfg->scidvs_first) { hp[i] = 0.0; pv[i] = lp; }
+                double dvdt = (double)inv_tau * sinh(hp[i] / efold);
+                double d1 = lp - pv[i], d2 = dt * dvdt;
+                hp[i] = hp[i] + (d1 - d2);
+                pv[i] = lp;
+            } else {
+                float *hp = (float *)st->hp, *pv = (float *)st->prev_photo, lp = ((float *)st->lp)[i];
+                if (cfg->scidvs_first) { hp[i] = 0.0f; pv[i] = lp; }
+                float dvdt = inv_tau * sinhf(hp[i] / (float)efold);
+                float d1 = lp - pv[i], d2 = (float)dt * dvdt;
+                hp[i] = hp[i] + (d1 - d2);
+                pv[i] = lp;
+            }
+        }
+    }
     /* pass B: leak, difference, event counts (emulator.py:734-775) */
     for (long i = 0; i < n; i++) {
         float thp_f = cfg->per_pixel_thres ? st->pos_thres[i] : (float)cfg->pos_thres_nominal;
@@ -271,7 +321,9 @@ long oracle_emu_frame(const OracleEmuCfg *cfg, OracleEmuState *st, const void *f
         if (cfg->state_f64) {
             double *lp = (double *)st->lp, *base = (double *)st->base;
             if (cfg->leak_rate_hz > 0) base[i] = base[i] - (double)delta_leak;
-            double photo = lp[i];
+            /* photoreceptor + photoreceptor_noise_arr (a float32 tensor, zeros when the option is off) */
+            double photo = (cfg->scidvs && st->hp) ? 2.0 * ((double *)st->hp)[i] : lp[i];
+            photo = photo + (double)((cfg->pr_noise && st->noise_arr) ? st->noise_arr[i] : 0.0f);
             double diff = (cfg->csdvs && st->surround) ? (photo - st->surround[i]) - base[i]
                                                        : photo - base[i];
             /* a Python-float threshold stays float64 against a float64 tensor */
@@ -283,7 +335,9 @@ long oracle_emu_frame(const OracleEmuCfg *cfg, OracleEmuState *st, const void *f
         } else {
             float *lp = (float *)st->lp, *base = (float *)st->base;
             if (cfg->leak_rate_hz > 0) base[i] = base[i] - delta_leak;
-            float diff = lp[i] - base[i];
+            float photo = (cfg->scidvs && st->hp) ? 2.0f * ((float *)st->hp)[i] : lp[i];
+            photo = photo + 0.0f;
+            float diff = photo - base[i];
             float pf = diff > 0 ? diff : 0.0f, nf = -diff > 0 ? -diff : 0.0f;
             pos_n[i] = (int32_t)div_floor_f32(pf, thp_f);
             neg_n[i] = (int32_t)div_floor_f32(nf, thn_f);

@@ -35,6 +35,9 @@ class _Cfg(ctypes.Structure):
         ("shot_inten_factor", ctypes.c_double),
         ("csdvs", ctypes.c_int32), ("_pad", ctypes.c_int32),
         ("cs_tau_p_s", ctypes.c_double), ("cs_tau_h_s", ctypes.c_double),
+        ("scidvs", ctypes.c_int32), ("pr_noise", ctypes.c_int32),
+        ("scidvs_first", ctypes.c_int32), ("_pad2", ctypes.c_int32),
+        ("pr_vrms", ctypes.c_double),
     ]
 
 
@@ -44,6 +47,8 @@ class _State(ctypes.Structure):
         ("pos_thres", ctypes.c_void_p), ("neg_thres", ctypes.c_void_p),
         ("noise_rate", ctypes.c_void_p), ("tmem", ctypes.c_void_p),
         ("surround", ctypes.c_void_p), ("linlog_lut", ctypes.c_void_p),
+        ("hp", ctypes.c_void_p), ("prev_photo", ctypes.c_void_p), ("tau_arr", ctypes.c_void_p),
+        ("noise_arr", ctypes.c_void_p), ("pr_randn", ctypes.c_void_p),
     ]
 
 
@@ -108,13 +113,43 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 
 
+_vn_cache = {"rate": None, "vn": None}
+
+
+def photoreceptor_noise_vrms(shot_noise_rate_hz, f3db, sample_rate_hz, pos_thr, neg_thr, sigma_thr):
+    """Restatement of emulator_utils.py:177-295 (host-side numpy calibration of the Gaussian noise amplitude
+    that yields the requested shot-noise rate after the RC low-pass). Like the reference it draws from an
+    UNSEEDED numpy generator and caches the value per sample rate (+-10 %), so two runs differ in the last
+    digits: parity tests take the reference's values from the fixture instead."""
+    if _vn_cache["rate"] is not None and abs(sample_rate_hz / _vn_cache["rate"] - 1) < 0.1:
+        return _vn_cache["vn"]
+    x = math.log10((shot_noise_rate_hz / f3db) / 2)
+    y = -0.0026 * x ** 3 - 0.036 * x ** 2 - 0.1949 * x + 0.321
+    N = 300
+    pos = pos_thr + sigma_thr * np.random.default_rng().standard_normal(N)
+    neg = neg_thr + sigma_thr * np.random.default_rng().standard_normal(N)
+    vn = float(np.mean(np.minimum(pos, neg) / (10 ** y)))
+    tau = 1 / (f3db * 2 * math.pi)
+    dt = 1 / sample_rate_hz
+    t = np.arange(0, 1000 * tau, dt)
+    rin = vn * np.random.default_rng().standard_normal(t.shape)
+    eps = dt / tau
+    rout = np.zeros_like(rin)
+    for i in range(1, len(rin)):
+        rout[i] = rout[i - 1] * (1 - eps) + rin[i] * eps
+    scaled = float(np.std(rin) / np.std(rout) * vn)
+    _vn_cache["rate"], _vn_cache["vn"] = sample_rate_hz, scaled
+    return scaled
+
+
 class OracleEmulator:
     """CPU oracle with the reference's constructor defaults (emulator.py:86-117)."""
 
     def __init__(self, pos_thres=0.2, neg_thres=0.2, sigma_thres=0.03, cutoff_hz=0.0,
                  leak_rate_hz=0.1, refractory_period_s=0.0, shot_noise_rate_hz=0.0,
                  leak_jitter_fraction=0.1, noise_rate_cov_decades=0.1, seed=0,
-                 cs_lambda_pixels=None, cs_tau_p_ms=None, hdr=False, shuffle=True, rng=None):
+                 cs_lambda_pixels=None, cs_tau_p_ms=None, hdr=False, shuffle=True, rng=None,
+                 scidvs=False, photoreceptor_noise=False, pr_vrms_tape=None):
         self.pos_thres_nominal, self.neg_thres_nominal = pos_thres, neg_thres
         self.sigma_thres = sigma_thres
         self.cutoff_hz = cutoff_hz
@@ -126,6 +161,12 @@ class OracleEmulator:
         self.hdr = hdr
         self.shuffle = shuffle
         self.rng = rng if rng is not None else TorchGlobalRNG()
+        self.scidvs, self.photoreceptor_noise = scidvs, photoreceptor_noise
+        self.pr_vrms_tape = list(pr_vrms_tape) if pr_vrms_tape is not None else None
+        self.hp = self.prev_photo = self.tau_arr = self.noise_arr = None
+        self._scidvs_started = False
+        self._pr_randn = None
+        self._pr_vrms = 0.0
         self.cs_lambda_pixels, self.cs_tau_p_ms = cs_lambda_pixels, cs_tau_p_ms
         self.csdvs = cs_lambda_pixels is not None
         if self.csdvs:
@@ -173,6 +214,10 @@ class OracleEmulator:
                 else self.cs_tau_p_ms * 1e-3
             c.cs_tau_h_s = abs_min / (self.cs_lambda_pixels ** 2) \
                 if (self.cs_tau_h_ms is None or self.cs_tau_h_ms == 0) else self.cs_tau_h_ms * 1e-3
+        c.scidvs = 1 if self.scidvs else 0
+        c.pr_noise = 1 if self.photoreceptor_noise else 0
+        c.scidvs_first = 1 if (self.scidvs and not self._scidvs_started) else 0
+        c.pr_vrms = float(self._pr_vrms)
         return c
 
     def _make_state(self):
@@ -182,6 +227,8 @@ class OracleEmulator:
         s.noise_rate, s.tmem = _ptr(self.noise_rate), _ptr(self.tmem)
         s.surround = _ptr(self.surround)
         s.linlog_lut = _ptr(self._lut)
+        s.hp, s.prev_photo, s.tau_arr = _ptr(self.hp), _ptr(self.prev_photo), _ptr(self.tau_arr)
+        s.noise_arr, s.pr_randn = _ptr(self.noise_arr), _ptr(self._pr_randn)
         return s
 
     # -- API ---------------------------------------------------------------
@@ -210,6 +257,12 @@ class OracleEmulator:
                 self.pos_thres = torch.clamp(p, min=0.01).numpy().copy()
                 q = self.rng.normal(self.neg_thres_nominal, self.sigma_thres, (H, W))
                 self.neg_thres = torch.clamp(q, min=0.01).numpy().copy()
+            if self.scidvs:     # emulator.py:480-483: SCIDVS_TAU_S * exp(normal(0, SCIDVS_TAU_COV))
+                self.tau_arr = (0.01 * torch.exp(self.rng.normal(0, 0.5, (H, W)))).numpy().copy()
+                self.hp = np.zeros((H, W), sdt)
+                self.prev_photo = np.zeros((H, W), sdt)
+            if self.photoreceptor_noise:
+                self.noise_arr = np.zeros((H, W), np.float32)     # zeros_like(float32 log frame), emulator.py:684
             if self.leak_rate_hz > 0:
                 r = self.rng.randn((H, W))
                 self.noise_rate = torch.exp(math.log(10) * self.noise_rate_cov_decades * r).numpy().copy()
@@ -218,6 +271,15 @@ class OracleEmulator:
             # NOTE: t_previous is NOT advanced on the first frame (emulator.py:717 returns early)
             return None
 
+        if self.photoreceptor_noise:    # emulator.py:694-698: vrms, then the randn draw, before the leak draw
+            dt = t_frame - self.t_previous
+            if self.pr_vrms_tape is not None:
+                self._pr_vrms = float(self.pr_vrms_tape.pop(0))
+            else:
+                self._pr_vrms = photoreceptor_noise_vrms(self.shot_noise_rate_hz, self.cutoff_hz, 1 / dt,
+                                                         self.pos_thres_nominal, self.neg_thres_nominal,
+                                                         self.sigma_thres)
+            self._pr_randn = np.ascontiguousarray(self.rng.randn((H, W)).numpy())
         cfg = self._make_cfg(H, W, dtype)
         st = self._make_state()
         n = H * W
@@ -226,7 +288,8 @@ class OracleEmulator:
             leak = np.ascontiguousarray(self.rng.randn((H, W)).numpy())
         cap = 4 * n + 1024
         iter_cap = 4096
-        snap = [x.copy() if x is not None else None for x in (self.lp, self.base, self.tmem, self.surround)]
+        snap_arrs = (self.lp, self.base, self.tmem, self.surround, self.hp, self.prev_photo, self.noise_arr)
+        snap = [x.copy() if x is not None else None for x in snap_arrs]
         while True:
             ev = np.empty((cap, 4), np.float32)
             iters = np.zeros(2 * iter_cap, np.int32)
@@ -238,13 +301,14 @@ class OracleEmulator:
             if rows >= 0:
                 break
             # output buffer too small: restore the state and retry with more room
-            for dst, src in zip((self.lp, self.base, self.tmem, self.surround), snap):
+            for dst, src in zip(snap_arrs, snap):
                 if dst is not None:
                     dst[...] = src
             cap *= 4
             iter_cap = max(iter_cap, max_n.value + 1)
         if self.csdvs:
             self.cs_steps_taken.append(cs_steps.value)
+        self._scidvs_started = True
         self.last_max_n = max_n.value
         ev = ev[:rows]
         # replay the per-iteration shuffles (emulator.py:866-870)
@@ -261,7 +325,7 @@ class OracleEmulator:
                 self.num_events_off += c_off
                 self.num_events_total += k
             off += k
-        if self.shot_noise_rate_hz > 0:
+        if self.shot_noise_rate_hz > 0 and not self.photoreceptor_noise:     # emulator.py:893
             rnd = np.ascontiguousarray(self.rng.rand((H, W)).numpy())
             sev = np.empty((2 * n, 4), np.float32)
             cnt = np.zeros(2, np.int32)

@@ -67,11 +67,25 @@ def texture_frames(H, W, T, seed=0, speed=1.0, block=4):
 def run_reference(emu_mod, kwargs, frames, times, seed):
     import logging
     logging.disable(logging.WARNING)
-    with Recorder() as rec:
-        em = emu_mod.EventEmulator(device="cpu", seed=seed, **kwargs)
-        per_frame = []
-        for f, t in zip(frames, times):
-            per_frame.append(em.generate_events(f, float(t)))
+    # the photoreceptor-noise amplitude comes from an UNSEEDED numpy generator (emulator_utils.py:234-235,
+    # 254): record the values the reference used, frame by frame
+    vrms = []
+    orig_vn = emu_mod.compute_photoreceptor_noise_voltage
+
+    def vn_wrap(*a, **k):
+        v = orig_vn(*a, **k)
+        vrms.append(float(v))
+        return v
+    emu_mod.compute_photoreceptor_noise_voltage = vn_wrap
+    try:
+        with Recorder() as rec:
+            em = emu_mod.EventEmulator(device="cpu", seed=seed, **kwargs)
+            per_frame = []
+            for f, t in zip(frames, times):
+                per_frame.append(em.generate_events(f, float(t)))
+    finally:
+        emu_mod.compute_photoreceptor_noise_voltage = orig_vn
+    em._pr_vrms_used = vrms
     return em, per_frame, rec.tape
 
 
@@ -103,8 +117,11 @@ def save_case(name, emu_mod, kwargs, frames, times, seed=42, keep_tape=True, kee
                 k = np.lexsort((e[:, 3], e[:, 1], e[:, 2], e[:, 0]))
                 h.update(np.ascontiguousarray(e[k]).tobytes())
         d["events_sha1_canonical"] = np.array(h.hexdigest())
+    if em._pr_vrms_used:
+        d["pr_vrms"] = np.asarray(em._pr_vrms_used, np.float64)
     for nm in ("lp_log_frame", "base_log_frame", "timestamp_mem", "pos_thres", "neg_thres",
-               "noise_rate_array", "cs_surround_frame"):
+               "noise_rate_array", "cs_surround_frame", "scidvs_highpass", "photoreceptor_noise_arr",
+               "scidvs_tau_arr"):
         v = getattr(em, nm, None)
         if isinstance(v, torch.Tensor):
             d["state_" + nm] = v.detach().cpu().numpy()
@@ -124,8 +141,31 @@ def save_case(name, emu_mod, kwargs, frames, times, seed=42, keep_tape=True, kee
         os.path.getsize(path) / 1024))
 
 
+def main_optional(emu_mod):
+    """SCIDVS (emulator.py:58-80, 719-725) and photoreceptor noise (emulator.py:694-703) fixtures."""
+    H, W, T = 24, 40, 10
+    fr = texture_frames(H, W, T)
+    ts = np.arange(T) * 1e-3
+    save_case("emu_scidvs", emu_mod,
+              dict(scidvs=True, cutoff_hz=100, leak_rate_hz=0.1, shot_noise_rate_hz=5.0, sigma_thres=0.03,
+                   refractory_period_s=0.0005), fr, ts)
+    save_case("emu_scidvs_f32", emu_mod,
+              dict(scidvs=True, cutoff_hz=0, leak_rate_hz=0.1, shot_noise_rate_hz=0, sigma_thres=0.03,
+                   pos_thres=0.4, neg_thres=0.4), fr[:6, :16, :24].copy(), ts[:6])
+    save_case("emu_prnoise", emu_mod,
+              dict(photoreceptor_noise=True, cutoff_hz=100, shot_noise_rate_hz=5.0, leak_rate_hz=0.1,
+                   sigma_thres=0.03), fr, ts)
+    fr4 = texture_frames(20, 36, 6, seed=7)
+    save_case("emu_prnoise_scidvs_csdvs", emu_mod,
+              dict(photoreceptor_noise=True, scidvs=True, cs_lambda_pixels=10, cs_tau_p_ms=0.5, cutoff_hz=100,
+                   refractory_period_s=1e-3, leak_rate_hz=0.1, shot_noise_rate_hz=1.0, sigma_thres=0.03,
+                   pos_thres=0.05, neg_thres=0.05), fr4, np.arange(6) * 1e-4)
+
+
 def main():
     emu_mod, _, _, _ = ref_shim.load_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "optional":
+        return main_optional(emu_mod)
     H, W, T = 24, 40, 10
     fr = texture_frames(H, W, T)
     ts = np.arange(T) * 1e-3

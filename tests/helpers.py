@@ -10,6 +10,8 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 EMU_GOLDENS = ["emu_class_default", "emu_cli_noisy", "emu_clean", "emu_scalar_thres_f64",
                "emu_refractory_multi", "emu_float_frames", "emu_static_leak_shot",
                "emu_ragged_13x37", "emu_csdvs", "emu_csdvs_120x176"]
+# optional pixel models: SCIDVS (emulator.py:58-80, 719-725), photoreceptor noise (emulator.py:694-703)
+EMU_GOLDENS_OPT = ["emu_scidvs", "emu_scidvs_f32", "emu_prnoise", "emu_prnoise_scidvs_csdvs"]
 
 
 def load_golden(name):

@@ -7,14 +7,18 @@ import pytest
 import torch
 
 from emu_oracle import OracleEmulator, lib
-from helpers import EMU_GOLDENS, TapeRNG, assert_events_equal, canonical, load_golden, split_events
+from helpers import (EMU_GOLDENS, EMU_GOLDENS_OPT, TapeRNG, assert_events_equal, canonical, load_golden,
+                     split_events)
 
 
-@pytest.mark.parametrize("name", EMU_GOLDENS)
+@pytest.mark.parametrize("name", EMU_GOLDENS + EMU_GOLDENS_OPT)
 def test_oracle_matches_reference_golden(name):
     g = load_golden(name)
     rng = TapeRNG(g["tape"])
-    em = OracleEmulator(rng=rng, **g["kwargs"])
+    # photoreceptor noise: the amplitude comes from an unseeded numpy generator in the reference
+    # (emulator_utils.py:234-235); the fixture carries the values it used
+    extra = {"pr_vrms_tape": list(g["pr_vrms"])} if "pr_vrms" in g else {}
+    em = OracleEmulator(rng=rng, **extra, **g["kwargs"])
     want = split_events(g["events"], g["event_counts"])
     for i, (f, t) in enumerate(zip(g["frames"], g["times"])):
         ev = em.generate_events(f, float(t))
@@ -28,6 +32,14 @@ def test_oracle_matches_reference_golden(name):
         if key in g and arr is not None:
             assert g[key].dtype == arr.dtype, key
             assert np.array_equal(g[key], arr), key
+    if em.noise_arr is not None:      # (the reference keeps a zero tensor when the option is off)
+        assert np.array_equal(g["state_photoreceptor_noise_arr"], em.noise_arr)
+    if em.hp is not None:
+        # sinh: torch's CPU kernel (Sleef) and libm may differ in the last place; everything else is exact
+        assert g["state_scidvs_highpass"].dtype == em.hp.dtype
+        tol = 4e-15 if em.hp.dtype == np.float64 else 2e-6
+        assert np.max(np.abs(g["state_scidvs_highpass"] - em.hp)) <= tol
+        assert np.array_equal(g["state_scidvs_tau_arr"], em.tau_arr)
 
 
 def test_oracle_moving_dot_config1_seeded():

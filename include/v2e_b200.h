@@ -64,6 +64,9 @@ typedef struct V2eEmuCfg {
     int32_t csdvs;                  /* 1: centre-surround model enabled (emulator.py:245-265) */
     int32_t max_frames_per_step;    /* upper bound of T in v2e_emu_step (control-block slots) */
     double cs_tau_p_s, cs_tau_h_s;  /* emulator.py:1069-1073 (already floored at 1e-9) */
+    int32_t scidvs;                 /* emulator.py:114, 719-725: nonlinear CR high-pass before the change amplifier */
+    int32_t photoreceptor_noise;    /* emulator.py:95, 694-703: Gaussian photoreceptor noise instead of injected
+                                       shot events (needs shot_noise_rate_hz > 0 and cutoff_hz > 0, :196-204) */
 } V2eEmuCfg;
 
 typedef struct V2eEmu V2eEmu;
@@ -90,6 +93,14 @@ int v2e_emu_set_linlog_lut(V2eEmu *h, const float *lut256_host, void *stream);
  * when the feature is off. Host pointers, [H*W] float32. Synchronous copy. */
 int v2e_emu_set_fields(V2eEmu *h, const float *pos_thres_host, const float *neg_thres_host,
                        const float *noise_rate_host);
+
+/* SCIDVS per-pixel time constants (emulator.py:480-483), host pointer, [H*W] float32. Synchronous copy. */
+int v2e_emu_set_scidvs_tau(V2eEmu *h, const float *tau_host);
+/* Photoreceptor noise inputs of the NEXT v2e_emu_step (T frames) or v2e_emu_phase_count (T = 1):
+ * vrms_host[T] = photoreceptor_noise_vrms per frame (emulator.py:695-697, a host-side calibration the caller
+ * runs); pr_randn_dev [T][H*W] float32 = the values torch.randn would return (emulator.py:698), required in
+ * rng_mode 0, ignored (may be NULL) in rng_mode 1. */
+int v2e_emu_set_pr_noise(V2eEmu *h, const float *pr_randn_dev, const double *vrms_host, int T);
 
 /* First frame (emulator.py:663-717): seeds lp / base / surround / timestamp_mem. Emits nothing.
  * t_previous stays unchanged, as in the reference (it returns before emulator.py:1011). */
@@ -168,7 +179,8 @@ int v2e_emu_profile_read4(V2eEmu *h, float *ms_sum4, int *launches4, void *strea
 
 /* State access for parity probes (emulator.py:756-764 reads them by name). which:
  * 0 lp_log_frame, 1 base_log_frame, 2 pos_thres, 3 neg_thres, 4 noise_rate_array,
- * 5 timestamp_mem, 6 cs_surround_frame. dst_host must hold H*W elements of the state's
+ * 5 timestamp_mem, 6 cs_surround_frame, 7 scidvs_highpass (state dtype), 8 photoreceptor_noise_arr (float32),
+ * 9 scidvs_tau_arr (float32). dst_host must hold H*W elements of the state's
  * dtype (*elem_size returns 4 or 8). Synchronous. */
 int v2e_emu_get_state(V2eEmu *h, int which, void *dst_host, int *elem_size);
 int v2e_emu_state_is_f64(V2eEmu *h);

@@ -6,7 +6,8 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import (EMU_GOLDENS, TapeRNG, assert_events_equal, canonical, load_golden, split_events)
+from helpers import (EMU_GOLDENS, EMU_GOLDENS_OPT, TapeRNG, assert_events_equal, canonical, load_golden,
+                     split_events)
 
 pytestmark = pytest.mark.gpu
 
@@ -45,6 +46,58 @@ def test_reference_golden_bit_exact(name):
             got = getattr(em, attr).cpu().numpy()
             assert got.dtype == g[key].dtype, key
             assert np.array_equal(got, g[key]), key
+
+
+@pytest.mark.parametrize("name", EMU_GOLDENS_OPT)
+def test_optional_models_match_reference_golden(name):
+    """SCIDVS high-pass (emulator.py:58-80, 719-725) and photoreceptor noise (emulator.py:694-703) against
+    the reference's own output. Rows (values and order), counters, lp / base / noise state bit-exact; the
+    high-pass state within a few ulp (CUDA's sinh vs torch's CPU sinh; same allowance as the oracle's libm).
+    The noise amplitude comes from the fixture: the reference calibrates it with an unseeded generator."""
+    g = load_golden(name)
+    rng = TapeRNG(g["tape"])
+    extra = {"pr_vrms_tape": list(g["pr_vrms"])} if "pr_vrms" in g else {}
+    em = _emulator(rng=rng, **extra, **g["kwargs"])
+    want = split_events(g["events"], g["event_counts"])
+    for i, (f, t) in enumerate(zip(g["frames"], g["times"])):
+        ev = em.generate_events(f, float(t))
+        assert_events_equal(ev, want[i], exact_order=True, ctx="%s frame %d" % (name, i))
+    assert rng.exhausted()
+    assert em.num_events_on == int(g["num_on"]) and em.num_events_off == int(g["num_off"])
+    for key, attr in (("state_base_log_frame", "base_log_frame"), ("state_lp_log_frame", "lp_log_frame")):
+        got = getattr(em, attr).cpu().numpy()
+        assert got.dtype == g[key].dtype and np.array_equal(got, g[key]), key
+    if g["kwargs"].get("photoreceptor_noise"):
+        assert np.array_equal(em.photoreceptor_noise_arr.cpu().numpy(), g["state_photoreceptor_noise_arr"])
+    if g["kwargs"].get("scidvs"):
+        hp = em.scidvs_highpass.cpu().numpy()
+        assert hp.dtype == g["state_scidvs_highpass"].dtype
+        tol = 4e-15 if hp.dtype == np.float64 else 2e-6
+        assert np.max(np.abs(hp - g["state_scidvs_highpass"])) <= tol
+        assert np.array_equal(em.scidvs_tau_arr.cpu().numpy(), g["state_scidvs_tau_arr"])
+
+
+def test_optional_models_device_rng_batch():
+    """Batch path (device RNG) with SCIDVS + photoreceptor noise: runs, emits events, and the noise state has
+    the amplitude the low-passed Gaussian should have (statistical: the draws are Philox's, not torch's)."""
+    H, W, T = 64, 96, 40
+    fr = texture_frames(H, W, T, seed=11)
+    ts = np.arange(T) * 1e-3
+    em = _emulator(rng_mode="device", seed=5, photoreceptor_noise=True, scidvs=True, cutoff_hz=100,
+                   shot_noise_rate_hz=5.0, leak_rate_hz=0.1, pr_vrms_tape=[0.05] * T, max_frames_per_step=16)
+    rows, offs = em.generate_events_batch(fr, ts)
+    assert rows.shape[0] > 0 and offs[-1] == rows.shape[0]
+    na = em.photoreceptor_noise_arr.cpu().numpy()
+    # stationary std of y <- (1-e) y + e x with x ~ N(0, v): v * sqrt(e / (2 - e))
+    e = 1e-3 / (1 / (2 * np.pi * 100))
+    want = 0.05 * np.sqrt(e / (2 - e))
+    assert 0.85 * want < na.std() < 1.15 * want and abs(na.mean()) < 0.1 * want
+    assert np.isfinite(em.scidvs_highpass.cpu().numpy()).all()
+
+
+def test_photoreceptor_noise_needs_shot_rate_and_cutoff():
+    with pytest.raises(SystemExit):       # emulator.py:196-204 quits
+        _emulator(photoreceptor_noise=True, shot_noise_rate_hz=0.0, cutoff_hz=100)
 
 
 def test_moving_dot_config1_seeded():

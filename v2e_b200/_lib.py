@@ -19,6 +19,7 @@ class V2eEmuCfg(ctypes.Structure):
         ("seed", ctypes.c_uint64),
         ("csdvs", ctypes.c_int32), ("max_frames_per_step", ctypes.c_int32),
         ("cs_tau_p_s", ctypes.c_double), ("cs_tau_h_s", ctypes.c_double),
+        ("scidvs", ctypes.c_int32), ("photoreceptor_noise", ctypes.c_int32),
     ]
 
 
@@ -79,6 +80,8 @@ _SIGS = {
     "v2e_resize_create": (_i, [_i, _i, _i, _i, _i, _i, ctypes.POINTER(_vp)]),
     "v2e_resize_destroy": (_i, [_vp]),
     "v2e_resize_run": (_i, [_vp, _vp, _vp, _i, _vp]),
+    "v2e_emu_set_scidvs_tau": (_i, [_vp, _vp]),
+    "v2e_emu_set_pr_noise": (_i, [_vp, _vp, ctypes.POINTER(_d), _i]),
     "v2e_emu_profile": (_i, [_vp, _i]),
     "v2e_emu_profile_read": (_i, [_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_i), _vp]),
     "v2e_emu_profile_read4": (_i, [_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_i), _vp]),

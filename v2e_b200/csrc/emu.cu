@@ -74,6 +74,11 @@ struct EmuDev {                         // passed by value to every kernel
     int32_t seg_px, upb;                // block b owns the 128-pixel units [b*units/n_blocks, (b+1)*units/n_blocks): upb or
                                         // upb-1 of them; seg_px = upb * 128 = capacity of a list segment
     int32_t units, pad1;                // ceil(n / 128)
+    // optional pixel models (emulator.py:58-80, 694-703, 719-725)
+    int32_t scidvs, pr_noise;
+    void *hp, *prev_photo;              // scidvs_highpass / scidvs_previous_photo, state dtype
+    void *pr_eff;                       // photoreceptor + photoreceptor_noise_arr as the change amplifier sees it
+    float *tau_arr, *noise_arr;         // scidvs_tau_arr, photoreceptor_noise_arr (float32 tensors)
     const float *lut;                   // [256] lin_log
     FrameCtrl *ctrl;                    // [max_slots+1]
     uint32_t *hist_pre, *hist_post, *segoff, *cursor;   // [max_slots][seg_stride]
@@ -88,6 +93,8 @@ struct FrameParams {
     double shot_c;                      // (shot_noise_rate_hz/2)*delta_time (emulator_utils.py:323-324)
     double shot_bound;                  // >= every pixel's ON/OFF shot probability of this frame (x >= 0)
     float shot_lo_f, shot_hi_f;         // float32 fast reject: a draw r with shot_lo_f <= r <= shot_hi_f cannot fire
+    float pr_vrms_f, pr_ome_f, pr_eps_f;// photoreceptor noise: float32(vrms), float32(1-dt/tau), float32(dt/tau)
+    int32_t scidvs_first;               // the frame that creates scidvs_highpass (zeros) and scidvs_previous_photo
     uint64_t capacity;
 };
 
@@ -501,6 +508,94 @@ __global__ void emu_csdvs_finish_kernel(EmuDev d, int num_steps, int slot) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// optional front end (SCIDVS and/or photoreceptor noise): emulator.py:686-703, 719-725, 748.
+// Low-pass of the whole field, the noise IIR, the nonlinear CR high-pass, and the field the change
+// amplifier sees: pr_eff = (scidvs ? 2*hp : lp) + photoreceptor_noise_arr. The update kernel then runs
+// with lp_done and reads pr_eff in place of lp.
+// ---------------------------------------------------------------------------------------------
+template <typename S, int FT>
+__global__ void __launch_bounds__(kThreads) emu_front_kernel(EmuDev d, FrameParams p, const void *frame,
+                                                             const float *pr_randn, int lp_done) {
+    __shared__ float s_lut[256];
+    if (*(volatile int32_t *)d.abort_flag) return;
+    s_lut[threadIdx.x] = d.lut[threadIdx.x];
+    __syncthreads();
+    const int i0 = (blockIdx.x * kThreads + threadIdx.x) * kVec;
+    if (i0 >= d.n) return;
+    double x[4];
+    S lp[4], hp[4], pv[4], eff[4];
+    float na[4], rn[4], tau[4];
+    load_frame4<FT>(frame, i0, d.n, x);
+    ld4((const S *)d.lp, i0, lp);
+    if (d.scidvs) { ld4((const S *)d.hp, i0, hp); ld4((const S *)d.prev_photo, i0, pv); ld4(d.tau_arr, i0, tau); }
+    if (d.pr_noise) {
+        ld4(d.noise_arr, i0, na);
+        if (pr_randn) load_f32x4_any(pr_randn, i0, d.n, rn);
+        else {
+            const uint2 key = make_uint2((uint32_t)d.seed, (uint32_t)(d.seed >> 32));
+            uint4 r = philox4x32<kPhiloxRounds>(make_uint4((uint32_t)(i0 >> 2), p.frame_index, 2u, 0x70726e7au), key);
+            float a = sqrt_approx(-2.0f * __logf(u01_open(r.x))), b = sqrt_approx(-2.0f * __logf(u01_open(r.z)));
+            float sa, ca, sb, cb;
+            __sincosf(6.283185307179586f * u01_half(r.y), &sa, &ca);
+            __sincosf(6.283185307179586f * u01_half(r.w), &sb, &cb);
+            rn[0] = a * ca; rn[1] = a * sa; rn[2] = b * cb; rn[3] = b * sb;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const double xv = x[k];
+        if (!lp_done) {
+            float lnf = 0.f;
+            if (!d.hdr) lnf = (FT == V2E_U8 || (xv >= 0.0 && xv <= 255.0 && xv == floor(xv))) ? s_lut[(int)xv] : lin_log_eval(xv);
+            if (sizeof(S) == 8) {
+                const double ln = d.hdr ? xv : (double)lnf;
+                if (d.lowpass_on) {
+                    double eps = ((xv + 20.0) / 275.0) * p.eps_scale;
+                    if (eps > 1.0) eps = 1.0;
+                    lp[k] = (S)((1.0 - eps) * (double)lp[k] + eps * ln);
+                } else {
+                    lp[k] = (S)ln;
+                }
+            } else {
+                lp[k] = (S)lnf;
+            }
+        }
+        // photoreceptor noise (emulator.py:694-701; emulator_utils.py:96-99 with a scalar eps, no clamp)
+        if (d.pr_noise) {
+            const float noise = p.pr_vrms_f * rn[k];
+            if (d.lowpass_on) {
+                const float a = p.pr_ome_f * na[k], b = p.pr_eps_f * noise;
+                na[k] = a + b;
+            } else {
+                na[k] = noise;
+            }
+        }
+        // SCIDVS (emulator.py:58-80, 719-725)
+        S photo = lp[k];
+        if (d.scidvs) {
+            if (p.scidvs_first) { hp[k] = (S)0; pv[k] = lp[k]; }
+            const float inv_tau = 1.0f / tau[k];
+            if (sizeof(S) == 8) {
+                const double dvdt = (double)inv_tau * sinh((double)hp[k] / (1 / 0.7));
+                const double d1 = (double)lp[k] - (double)pv[k], d2 = p.dt * dvdt;
+                hp[k] = (S)((double)hp[k] + (d1 - d2));
+            } else {
+                const float dvdt = inv_tau * sinhf((float)hp[k] / (float)(1 / 0.7));
+                const float d1 = (float)lp[k] - (float)pv[k], d2 = p.dt_f * dvdt;
+                hp[k] = (S)((float)hp[k] + (d1 - d2));
+            }
+            pv[k] = lp[k];
+            photo = (S)2 * hp[k];
+        }
+        eff[k] = d.pr_noise ? (S)(photo + (S)na[k]) : (S)(photo + (S)0);
+    }
+    if (!lp_done) st4((S *)d.lp, i0, lp);
+    if (d.scidvs) { st4((S *)d.hp, i0, hp); st4((S *)d.prev_photo, i0, pv); }
+    if (d.pr_noise) st4(d.noise_arr, i0, na);
+    st4((S *)d.pr_eff, i0, eff);
+}
+
+// ---------------------------------------------------------------------------------------------
 // update kernel: emulator.py:663-775 for 4 pixels per thread
 // RNG: 0 = replay (host-drawn fields), 1 = device (Philox). Everything else is a uniform runtime flag.
 // FAST: the configuration fixed at compile time to v2e's CLI defaults in device-RNG mode (per-pixel
@@ -587,6 +682,8 @@ emu_update_kernel(EmuDev d, FrameParams p, const void *frame, const float *leak_
     const int u1 = (int)(((long long)(blockIdx.x + 1) * d.units) / d.n_blocks);
     const int nj = (u1 - u0 - warp + kWarps - 1) / kWarps;     // units of this warp (<= 0: none)
     unsigned char *my_stage = s_stage + (size_t)warp * (kStages * StageLayout<S>::bytes);
+    // SCIDVS / photoreceptor noise: the front kernel has prepared what the change amplifier sees
+    const S *lp_src = (lp_done && d.pr_eff) ? (const S *)d.pr_eff : (const S *)d.lp;
     const uint32_t leader = elect_one();
     const uint32_t stage_u32 = smem_u32(my_stage), bar_u32 = smem_u32(&s_full[warp][0]);
     auto issue = [&](int j) {                // whole warp, warp-uniform arguments
@@ -596,7 +693,7 @@ emu_update_kernel(EmuDev d, FrameParams p, const void *frame, const float *leak_
         constexpr uint32_t nS = kUnitPx * (uint32_t)sizeof(S), nF = kUnitPx * 4u;
         const uint32_t total = (need_lp ? nS : 0u) + nS + (f_pp ? 2u * nF : 0u) + (f_leak ? nF : 0u);
         mbar_expect_tx_pred(bar, total, leader);
-        if (need_lp) bulk_load_pred(st + StageLayout<S>::lp, (const S *)d.lp + px0, nS, bar, leader);
+        if (need_lp) bulk_load_pred(st + StageLayout<S>::lp, lp_src + px0, nS, bar, leader);
         bulk_load_pred(st + StageLayout<S>::base, (const S *)d.base + px0, nS, bar, leader);
         if (f_pp) {
             bulk_load_pred(st + StageLayout<S>::thp, d.pos_thres + px0, nF, bar, leader);
@@ -1149,6 +1246,12 @@ struct V2eEmu {
     int prof_frames;
     unsigned char *prof_used;   // [max_slots][kProfKinds]
     float *lut_dev;
+    // optional models: per-frame inputs of the next step / phase_count (v2e_emu_set_pr_noise)
+    const float *pr_randn_dev;  // [T][H*W] or null (device RNG)
+    double *pr_vrms;            // [max_slots]
+    int pr_T;                   // frames covered by pr_vrms (0: not set)
+    int pr_T_last;              // what the last step consumed (a resume_emit step re-counts its later frames)
+    int scidvs_started;         // scidvs_highpass exists (emulator.py:720-722)
     FrameCtrl *ctrl_host;       // pinned
     int32_t *abort_host;        // pinned [2]
     size_t state_elem;
@@ -1203,6 +1306,12 @@ static FrameParams make_params(const V2eEmu *h, double t_frame, double t_prev, u
         p.shot_hi_f = hi;
     }
     p.capacity = capacity;
+    if (h->cfg.photoreceptor_noise && h->cfg.cutoff_hz > 0) {
+        const double eps = p.dt / (1.0 / (M_PI * 2 * h->cfg.cutoff_hz));   // emulator_utils.py:80, 97: a Python float
+        p.pr_ome_f = (float)(1.0 - eps);
+        p.pr_eps_f = (float)eps;
+    }
+    p.scidvs_first = (h->cfg.scidvs && !h->scidvs_started) ? 1 : 0;
     return p;
 }
 
@@ -1215,6 +1324,8 @@ extern "C" int v2e_emu_create(const V2eEmuCfg *cfg, V2eEmu **out) {
     if (cfg->csdvs && !(cfg->cutoff_hz > 0 || cfg->hdr))
         return fail(V2E_E_UNSUPPORTED, "csdvs needs a float64 photoreceptor state (cutoff_hz > 0)");
     if (cfg->csdvs && !(cfg->cs_tau_p_s > 0 && cfg->cs_tau_h_s > 0)) return fail(V2E_E_INVALID, "csdvs time constants must be positive");
+    if (cfg->photoreceptor_noise && !(cfg->shot_noise_rate_hz > 0 && cfg->cutoff_hz > 0))   // emulator.py:196-204
+        return fail(V2E_E_INVALID, "photoreceptor_noise needs shot_noise_rate_hz > 0 and cutoff_hz > 0");
     V2eEmu *h = new V2eEmu();
     memset(h, 0, sizeof(*h));
     h->cfg = *cfg;
@@ -1229,7 +1340,10 @@ extern "C" int v2e_emu_create(const V2eEmuCfg *cfg, V2eEmu **out) {
     d.csdvs = cfg->csdvs;
     d.leak_on = cfg->leak_rate_hz > 0;
     d.lowpass_on = cfg->cutoff_hz > 0;
-    d.shot_on = cfg->shot_noise_rate_hz > 0;
+    d.scidvs = cfg->scidvs ? 1 : 0;
+    d.pr_noise = cfg->photoreceptor_noise ? 1 : 0;
+    // emulator.py:893: with photoreceptor noise the shot events come from the noise, none are injected
+    d.shot_on = cfg->shot_noise_rate_hz > 0 && !d.pr_noise;
     d.refr_on = cfg->refractory_period_s > 0;
     d.rng_mode = cfg->rng_mode;
     d.iter_cap = cfg->iter_cap;
@@ -1261,6 +1375,12 @@ extern "C" int v2e_emu_create(const V2eEmuCfg *cfg, V2eEmu **out) {
     if (d.per_pixel_thres) { ALLOC(d.pos_thres, np * 4); ALLOC(d.neg_thres, np * 4); }
     if (d.leak_on) ALLOC(d.noise_rate, np * 4);
     if (d.refr_on) ALLOC(d.tmem, np * 4);
+    if (d.scidvs) { ALLOC(d.hp, np * h->state_elem); ALLOC(d.prev_photo, np * h->state_elem); ALLOC(d.tau_arr, np * 4); }
+    if (d.pr_noise) ALLOC(d.noise_arr, np * 4);
+    if (d.scidvs || d.pr_noise) {
+        ALLOC(d.pr_eff, np * h->state_elem);
+        h->pr_vrms = new double[cfg->max_frames_per_step]();
+    }
     if (d.csdvs) {
         ALLOC(d.surround, np * 8);
         ALLOC(d.surround2, np * 8);
@@ -1305,7 +1425,9 @@ extern "C" int v2e_emu_create(const V2eEmuCfg *cfg, V2eEmu **out) {
 extern "C" int v2e_emu_destroy(V2eEmu *h) {
     if (!h) return V2E_OK;
     EmuDev &d = h->d;
-    void *ptrs[] = {d.lp, d.base, d.rec, d.pos_thres, d.neg_thres, d.noise_rate, d.tmem, d.surround,
+    delete[] h->pr_vrms;
+    void *ptrs[] = {d.hp, d.prev_photo, d.tau_arr, d.noise_arr, d.pr_eff,
+                    d.lp, d.base, d.rec, d.pos_thres, d.neg_thres, d.noise_rate, d.tmem, d.surround,
                     h->lut_dev, d.ctrl, d.hist_pre, d.hist_post, d.segoff, d.cursor, d.abort_flag, d.act_list, d.act_count, d.surround2, d.cs_cur, d.cs_max};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->ctrl_host) cudaFreeHost(h->ctrl_host);
@@ -1342,6 +1464,24 @@ extern "C" int v2e_emu_set_fields(V2eEmu *h, const float *pos, const float *neg,
         if (!nr) return fail(V2E_E_INVALID, "noise_rate field required when leak_rate_hz > 0");
         CU(cudaMemcpy(h->d.noise_rate, nr, bytes, cudaMemcpyHostToDevice));
     }
+    return V2E_OK;
+}
+
+extern "C" int v2e_emu_set_scidvs_tau(V2eEmu *h, const float *tau_host) {
+    if (!h || !tau_host) return fail(V2E_E_INVALID, "null argument");
+    if (!h->d.scidvs) return fail(V2E_E_STATE, "scidvs is not enabled for this handle");
+    CU(cudaMemcpy(h->d.tau_arr, tau_host, (size_t)h->d.n * 4, cudaMemcpyHostToDevice));
+    return V2E_OK;
+}
+
+extern "C" int v2e_emu_set_pr_noise(V2eEmu *h, const float *pr_randn_dev, const double *vrms_host, int T) {
+    if (!h || !vrms_host) return fail(V2E_E_INVALID, "null argument");
+    if (!h->d.pr_noise) return fail(V2E_E_STATE, "photoreceptor_noise is not enabled for this handle");
+    if (T < 1 || T > h->d.max_slots) return fail(V2E_E_INVALID, "bad T");
+    if (h->d.rng_mode == 0 && !pr_randn_dev) return fail(V2E_E_INVALID, "the randn field is required in replay mode");
+    h->pr_randn_dev = pr_randn_dev;
+    memcpy(h->pr_vrms, vrms_host, sizeof(double) * (size_t)T);
+    h->pr_T = T;
     return V2E_OK;
 }
 
@@ -1435,8 +1575,9 @@ static size_t frame_elem(int dt) { return dt == V2E_U8 ? 1 : (dt == V2E_F32 ? 4 
 
 // enqueue the counting kernels of one frame into `slot`
 static int enqueue_count(V2eEmu *h, const FrameParams &p, const void *frame, int dtype, const float *lr,
-                         const float *sr, int shot_pending, int slot, cudaStream_t st) {
+                         const float *sr, int shot_pending, int slot, cudaStream_t st, const float *pr_randn = nullptr) {
     const EmuDev &d = h->d;
+    if (d.pr_noise && d.rng_mode == 0 && !pr_randn) return fail(V2E_E_STATE, "v2e_emu_set_pr_noise must precede this call");
     if (d.rng_mode == 0 && d.leak_on && !lr) return fail(V2E_E_INVALID, "leak_randn field required in replay mode");
     const bool shot_in_update = d.shot_on && (d.rng_mode == 1 || sr != nullptr);
     if (d.shot_on && !shot_in_update && !shot_pending)
@@ -1453,6 +1594,23 @@ static int enqueue_count(V2eEmu *h, const FrameParams &p, const void *frame, int
             case V2E_F64: emu_lp_kernel<V2E_F64><<<g, kThreads, 0, st>>>(d, p, frame); break;
             default: return fail(V2E_E_INVALID, "bad frame dtype");
         }
+        lp_done = 1;
+    }
+    if (d.scidvs || d.pr_noise) {
+        // low-pass (unless the surround path just did it), noise IIR, nonlinear high-pass -> pr_eff
+        const int g = grid_for(d);
+#define FRONT(S_)                                                                                                  \
+        switch (dtype) {                                                                                            \
+            case V2E_U8: emu_front_kernel<S_, V2E_U8><<<g, kThreads, 0, st>>>(d, p, frame, pr_randn, lp_done); break;   \
+            case V2E_F32: emu_front_kernel<S_, V2E_F32><<<g, kThreads, 0, st>>>(d, p, frame, pr_randn, lp_done); break; \
+            case V2E_F64: emu_front_kernel<S_, V2E_F64><<<g, kThreads, 0, st>>>(d, p, frame, pr_randn, lp_done); break; \
+            default: return fail(V2E_E_INVALID, "bad frame dtype");                                                 \
+        }
+        if (d.state_f64) { FRONT(double) } else { FRONT(float) }
+#undef FRONT
+        lp_done = 1;
+    }
+    if (d.csdvs) {
         const double tau_p = h->cfg.cs_tau_p_s, tau_h = h->cfg.cs_tau_h_s;
         const double min_tau = tau_p < tau_h ? tau_p : tau_h;
         const int num_steps = (int)ceil((p.dt / min_tau) * 5);              // emulator.py:1076-1078
@@ -1467,7 +1625,6 @@ static int enqueue_count(V2eEmu *h, const FrameParams &p, const void *frame, int
         for (int k = 0; k < num_steps; k++)
             emu_csdvs_step_kernel<<<gs, kThreads, 0, st>>>(d, alpha_p, (float)alpha_h, k);
         emu_csdvs_finish_kernel<<<1, 1, 0, st>>>(d, num_steps, slot);
-        lp_done = 1;
     }
     {
         ProfScope ps(h, slot, 0, st);
@@ -1527,6 +1684,7 @@ extern "C" int v2e_emu_step(V2eEmu *h, const void *frames, int dtype, int T, con
     } else {
         if ((rc = reset_slots(h, first, T - first, st))) return rc;
     }
+    if (resume_emit && h->pr_T == 0) h->pr_T = h->pr_T_last;
     if (h->profile) { memset(h->prof_used, 0, (size_t)d.max_slots * kProfKinds); h->prof_frames = T - first; }
     if (!resume_emit) {
         h->step_base = h->frame_counter;
@@ -1543,13 +1701,22 @@ extern "C" int v2e_emu_step(V2eEmu *h, const void *frames, int dtype, int T, con
         if (resume_emit && f == first) {
             emu_plan_kernel<<<1, kThreads, 0, st>>>(d, p, f);   // only the plan has to be redone
         } else {
-            if ((rc = enqueue_count(h, p, frame, dtype, lr, sr, 0, f, st))) return rc;
+            const float *prn = nullptr;
+            if (d.pr_noise) {
+                if (h->pr_T < T) return fail(V2E_E_STATE, "v2e_emu_set_pr_noise must cover every frame of the step");
+                p.pr_vrms_f = (float)h->pr_vrms[f];
+                prn = h->pr_randn_dev ? h->pr_randn_dev + (size_t)f * d.n : nullptr;
+            }
+            if ((rc = enqueue_count(h, p, frame, dtype, lr, sr, 0, f, st, prn))) return rc;
+            h->scidvs_started = 1;
         }
         if ((rc = enqueue_emit(h, p, f, events, st))) return rc;
         enqueue_null_bracket(h, f, st);
     }
     CU(cudaGetLastError());
     h->last_T = T;
+    h->pr_T_last = h->pr_T;
+    h->pr_T = 0;
     return V2E_OK;
 }
 
@@ -1594,7 +1761,15 @@ extern "C" int v2e_emu_phase_count(V2eEmu *h, const void *frame, int dtype, doub
     emu_begin_step_kernel<<<1, 1, 0, st>>>(h->d, 0, ev_base_start);
     FrameParams p = make_params(h, t_frame, t_previous, h->frame_counter++, capacity);
     h->last_dt = p.dt;
-    if ((rc = enqueue_count(h, p, frame, dtype, lr, sr, shot_pending, 0, st))) return rc;
+    const float *prn = nullptr;
+    if (h->d.pr_noise) {
+        if (h->pr_T < 1) return fail(V2E_E_STATE, "v2e_emu_set_pr_noise must precede v2e_emu_phase_count");
+        p.pr_vrms_f = (float)h->pr_vrms[0];
+        prn = h->pr_randn_dev;
+        h->pr_T = 0;
+    }
+    if ((rc = enqueue_count(h, p, frame, dtype, lr, sr, shot_pending, 0, st, prn))) return rc;
+    h->scidvs_started = 1;
     CU(cudaGetLastError());
     h->last_T = 1;
     return V2E_OK;
@@ -1618,6 +1793,7 @@ extern "C" int v2e_emu_phase_update(V2eEmu *h, const void *frame, int dtype, dou
     const EmuDev &d = h->d;
     if (d.rng_mode == 0 && d.leak_on && !lr) return fail(V2E_E_INVALID, "leak_randn field required in replay mode");
     if (d.csdvs) return fail(V2E_E_UNSUPPORTED, "pixel sharding of the centre-surround model needs a halo exchange per Euler step (not built)");
+    if (d.scidvs || d.pr_noise) return fail(V2E_E_UNSUPPORTED, "pixel sharding with scidvs / photoreceptor_noise is not built");
     rc = d.state_f64 ? launch_update<double>(h, p, frame, dtype, lr, sr, 0, 0, 0, st)
                      : launch_update<float>(h, p, frame, dtype, lr, sr, 0, 0, 0, st);
     if (rc) return rc;
@@ -1731,6 +1907,9 @@ extern "C" void *v2e_emu_state_ptr(V2eEmu *h, int which) {
             cudaMemcpy(&cur, h->d.cs_cur, sizeof(cur), cudaMemcpyDeviceToHost);
             return cur ? h->d.surround2 : h->d.surround;
         }
+        case 7: return h->d.hp;
+        case 8: return h->d.noise_arr;
+        case 9: return h->d.tau_arr;
     }
     return nullptr;
 }
@@ -1739,7 +1918,7 @@ extern "C" int v2e_emu_get_state(V2eEmu *h, int which, void *dst, int *elem_size
     if (!h || !dst) return fail(V2E_E_INVALID, "null argument");
     void *src = v2e_emu_state_ptr(h, which);
     if (!src) return fail(V2E_E_STATE, "state array not allocated for this configuration");
-    int es = (which <= 1) ? (int)h->state_elem : (which == 6 ? 8 : 4);
+    int es = (which <= 1 || which == 7) ? (int)h->state_elem : (which == 6 ? 8 : 4);
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpy(dst, src, (size_t)h->d.n * es, cudaMemcpyDeviceToHost));
     if (elem_size) *elem_size = es;

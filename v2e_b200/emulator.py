@@ -65,7 +65,8 @@ def _linlog_lut():
 
 
 _STATE_IDS = {"lp_log_frame": 0, "base_log_frame": 1, "pos_thres": 2, "neg_thres": 3,
-              "noise_rate_array": 4, "timestamp_mem": 5, "cs_surround_frame": 6}
+              "noise_rate_array": 4, "timestamp_mem": 5, "cs_surround_frame": 6,
+              "scidvs_highpass": 7, "photoreceptor_noise_arr": 8, "scidvs_tau_arr": 9}
 
 
 class EventEmulator(object):
@@ -106,6 +107,7 @@ class EventEmulator(object):
             # ---- extensions ----
             rng_mode: str = "replay",
             rng=None,
+            pr_vrms_tape=None,
             iter_cap: int = 1024,
             max_frames_per_step: int = 64,
             exact_order: bool = True,
@@ -114,11 +116,12 @@ class EventEmulator(object):
         if not str(device).startswith("cuda"):
             raise RuntimeError("v2e_b200.EventEmulator runs on a CUDA device only (device=%r); "
                                "there is no CPU fallback" % (device,))
-        if photoreceptor_noise:
-            raise NotImplementedError("photoreceptor_noise (emulator.py:694-703) is not built; its "
-                                      "calibration uses an unseeded numpy generator in the reference")
-        if scidvs:
-            raise NotImplementedError("scidvs (emulator.py:719-725) is not built")
+        if photoreceptor_noise and (shot_noise_rate_hz == 0 or cutoff_hz == 0):
+            # emulator.py:196-204 logs and calls v2e_quit(1)
+            logger.warning("--photoreceptor_noise needs a finite --shot_noise_rate_hz and --cutoff_hz")
+            raise SystemExit(1)
+        if (photoreceptor_noise or scidvs) and shard is not None:
+            raise NotImplementedError("pixel sharding with scidvs / photoreceptor_noise is not built")
         if dvs_h5 or dvs_aedat2 or dvs_aedat4 or dvs_text or show_dvs_model_state or \
                 record_single_pixel_states is not None:
             raise NotImplementedError("file sinks / state display are the caller's job here "
@@ -137,6 +140,10 @@ class EventEmulator(object):
         self.refractory_period_s = refractory_period_s
         self.shot_noise_rate_hz = shot_noise_rate_hz
         self.photoreceptor_noise = photoreceptor_noise
+        self.photoreceptor_noise_vrms = None
+        # parity tests: the reference's own amplitudes (its calibration draws from an unseeded generator)
+        self._pr_vrms_tape = list(pr_vrms_tape) if pr_vrms_tape is not None else None
+        self._vn_cache = [None, None]
         self.leak_jitter_fraction = leak_jitter_fraction
         self.noise_rate_cov_decades = noise_rate_cov_decades
         self.SHOT_NOISE_INTEN_FACTOR = 0.25
@@ -265,6 +272,8 @@ class EventEmulator(object):
         cfg.seed = int(self.seed) & 0xFFFFFFFFFFFFFFFF
         cfg.csdvs = 1 if self.csdvs_enabled else 0
         cfg.max_frames_per_step = self.max_frames_per_step
+        cfg.scidvs = 1 if self.scidvs else 0
+        cfg.photoreceptor_noise = 1 if self.photoreceptor_noise else 0
         if self.csdvs_enabled:
             abs_min_tau_p = 1e-9  # emulator.py:1068-1073
             cfg.cs_tau_p_s = abs_min_tau_p if (self.cs_tau_p_ms is None or self.cs_tau_p_ms == 0) \
@@ -283,12 +292,15 @@ class EventEmulator(object):
         self._state_f64 = bool(self._lib.v2e_emu_state_is_f64(h))
 
     def _init_fields(self, H, W):
-        """emulator.py:439-511 draw order: normal(pos), normal(neg), randn(noise_rate)."""
+        """emulator.py:439-511 draw order: normal(pos), normal(neg), [normal(scidvs tau)], randn(noise_rate)."""
         pos = neg = nr = None
         if self.sigma_thres > 0:
             pos = torch.clamp(self.rng.normal(self.pos_thres_nominal, self.sigma_thres, (H, W)), min=0.01)
             neg = torch.clamp(self.rng.normal(self.neg_thres_nominal, self.sigma_thres, (H, W)), min=0.01)
             pos, neg = pos.contiguous(), neg.contiguous()
+        if self.scidvs:     # emulator.py:480-483: SCIDVS_TAU_S * exp(normal(0, SCIDVS_TAU_COV))
+            tau = (0.01 * torch.exp(self.rng.normal(0, 0.5, (H, W)))).contiguous()
+            _lib.check(self._lib.v2e_emu_set_scidvs_tau(self._h, ctypes.c_void_p(tau.data_ptr())))
         if self.leak_rate_hz > 0:
             r = self.rng.randn((H, W))
             nr = torch.exp(math.log(10) * self.noise_rate_cov_decades * r).contiguous()
@@ -343,7 +355,7 @@ class EventEmulator(object):
             return None
         if fr.shape != (self._H, self._W):
             raise ValueError("frame size changed")
-        per_frame_rng = (self.leak_rate_hz > 0 or self.shot_noise_rate_hz > 0)
+        per_frame_rng = (self.leak_rate_hz > 0 or self.shot_noise_rate_hz > 0 or self.photoreceptor_noise)
         if self.rng_mode == "replay" and (per_frame_rng or self.exact_order):
             ev = self._generate_replay(fr, code, t_frame)
         else:
@@ -354,19 +366,56 @@ class EventEmulator(object):
             return ev
         return None
 
+    def _pr_vrms(self, delta_time):
+        """emulator.py:695-697 -> emulator_utils.py:177-295: host-side calibration of the Gaussian noise
+        amplitude that gives the requested shot-noise rate after the RC low-pass; cached per sample rate
+        (+-10 %). Like the reference it draws from an unseeded numpy generator."""
+        if self._pr_vrms_tape is not None:
+            v = float(self._pr_vrms_tape.pop(0))
+        else:
+            rate = 1.0 / delta_time
+            if self._vn_cache[0] is not None and abs(rate / self._vn_cache[0] - 1) < 0.1:
+                v = self._vn_cache[1]
+            else:
+                f3db = self.cutoff_hz
+                x = math.log10((self.shot_noise_rate_hz / f3db) / 2)
+                y = -0.0026 * x ** 3 - 0.036 * x ** 2 - 0.1949 * x + 0.321
+                n_s = 300
+                pos = self.pos_thres_nominal + self.sigma_thres * np.random.default_rng().standard_normal(n_s)
+                neg = self.neg_thres_nominal + self.sigma_thres * np.random.default_rng().standard_normal(n_s)
+                vn = float(np.mean(np.minimum(pos, neg) / (10 ** y)))
+                tau = 1 / (f3db * 2 * math.pi)
+                dt = 1 / rate
+                rin = vn * np.random.default_rng().standard_normal(np.arange(0, 1000 * tau, dt).shape)
+                eps = dt / tau
+                rout = np.zeros_like(rin)
+                acc = 0.0
+                for i in range(1, len(rin)):
+                    acc = acc * (1 - eps) + rin[i] * eps
+                    rout[i] = acc
+                v = float(np.std(rin) / np.std(rout) * vn)
+                self._vn_cache = [rate, v]
+        self.photoreceptor_noise_vrms = v
+        return v
+
     # replay path: one frame, host draws interleaved exactly like the reference ----------------
     def _generate_replay(self, fr, code, t_frame):
         H, W, n = self._H, self._W, self._H * self._W
         L, h = self._lib, self._h
-        leak_on, shot_on = self.leak_rate_hz > 0, self.shot_noise_rate_hz > 0
+        leak_on = self.leak_rate_hz > 0
+        shot_on = self.shot_noise_rate_hz > 0 and not self.photoreceptor_noise      # emulator.py:893
         with torch.cuda.device(self.device):
             st = self._stream()
             lr_dev = None
+            tp = float(self.t_previous)
+            if self.photoreceptor_noise:    # emulator.py:694-698: amplitude, then the randn draw, before the leak's
+                vr = (ctypes.c_double * 1)(self._pr_vrms(t_frame - tp))
+                pr_dev = self.rng.randn((H, W)).contiguous().to(self.device, non_blocking=False)
+                _lib.check(L.v2e_emu_set_pr_noise(h, ctypes.c_void_p(pr_dev.data_ptr()), vr, 1))
             if leak_on:
                 lr_dev = self.rng.randn((H, W)).contiguous().to(self.device, non_blocking=False)
             self._ensure_event_buffers(self.event_rows_hint or max(4 * n, 1 << 16))
             cap = self._ev_dev.shape[0]
-            tp = float(self.t_previous)
             fp = ctypes.c_void_p(fr.data_ptr())
             _lib.check(L.v2e_emu_phase_count(h, fp, code, t_frame, tp,
                                              None if lr_dev is None else ctypes.c_void_p(lr_dev.data_ptr()),
@@ -555,7 +604,12 @@ class EventEmulator(object):
             info = (_lib.V2eFrameInfo * T)()
             done, rows = ctypes.c_int(0), ctypes.c_uint64(0)
             first, resume, base = 0, 0, int(base_row)
+            if self.photoreceptor_noise:
+                tps = [float(self.t_previous)] + [float(t) for t in t_frames[:-1]]
+                vr = (ctypes.c_double * T)(*[self._pr_vrms(float(t) - tp_) for t, tp_ in zip(t_frames, tps)])
             while True:
+                if self.photoreceptor_noise and not resume:
+                    _lib.check(L.v2e_emu_set_pr_noise(h, None, vr, T))
                 _lib.check(L.v2e_emu_step(h, ctypes.c_void_p(frames_dev.data_ptr()), code, T, ts,
                                           float(self.t_previous), None, None,
                                           ctypes.c_void_p(self._ev_dev.data_ptr()), self._ev_dev.shape[0],
@@ -587,7 +641,8 @@ class EventEmulator(object):
         With return_device=True rows is a view of the emulator's device buffer (valid until the next
         call); with copy=False the host rows are a view of the pinned staging buffer (same lifetime). The first frame of a fresh emulator only initialises state (zero rows), as in the
         reference. Needs rng_mode="device" when leak or shot noise is on."""
-        if self.rng_mode == "replay" and (self.leak_rate_hz > 0 or self.shot_noise_rate_hz > 0):
+        if self.rng_mode == "replay" and (self.leak_rate_hz > 0 or self.shot_noise_rate_hz > 0 or
+                                          self.photoreceptor_noise):
             raise RuntimeError("generate_events_batch with per-frame noise needs rng_mode='device' "
                                "(replay mode must interleave host draws frame by frame)")
         fr, code = self._to_device_frames(frames)
@@ -630,7 +685,7 @@ class EventEmulator(object):
         ptr = self._lib.v2e_emu_state_ptr(self._h, which)
         if not ptr:
             return None
-        f64 = (which <= 1 and self._state_f64) or which == 6
+        f64 = (which in (0, 1, 7) and self._state_f64) or which == 6
         view = _DevView(ptr, (self._H, self._W), "<f8" if f64 else "<f4", self)
         torch.cuda.current_stream(self.device).synchronize()
         return torch.as_tensor(view, device=self.device)
@@ -640,6 +695,9 @@ class EventEmulator(object):
     timestamp_mem = property(lambda self: self._state("timestamp_mem"))
     noise_rate_array = property(lambda self: self._state("noise_rate_array"))
     cs_surround_frame = property(lambda self: self._state("cs_surround_frame"))
+    scidvs_highpass = property(lambda self: self._state("scidvs_highpass"))
+    photoreceptor_noise_arr = property(lambda self: self._state("photoreceptor_noise_arr"))
+    scidvs_tau_arr = property(lambda self: self._state("scidvs_tau_arr"))
 
     @property
     def pos_thres(self):

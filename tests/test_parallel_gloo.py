@@ -83,3 +83,44 @@ def test_merge_by_time_is_stable_and_sorted():
     assert torch.all(m[1:, 0] >= m[:-1, 0])
     assert m[0, 1] == 1 and m[1, 1] == 9          # ties keep rank order
     assert m.shape == (5, 4)
+
+
+def _exchange_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        H, W, n_pairs, U = 11, 7, 5, 3
+        clip = np.arange(n_pairs * U * H * W, dtype=np.int64).reshape(n_pairs * U, H, W) % 251
+        p0, p1 = parallel.pair_range(n_pairs, rank, world)
+        local = torch.from_numpy(clip[p0 * U:p1 * U].astype(np.uint8))       # this rank's run of the clip
+        bands = parallel.exchange_frame_bands(local, H)
+        y0, y1 = parallel.row_band(H, rank, world)
+        q.put((rank, bands.numpy(), clip[:, y0:y1].astype(np.uint8)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_exchange_frame_bands_world2():
+    """One clip over two ranks: ragged runs of frames in, every frame's row band out, in clip order."""
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_exchange_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, bands, want in got:
+        assert bands.shape == want.shape and np.array_equal(bands, want), rank
+
+
+def test_pair_range_covers_all_pairs_contiguously():
+    for n, w in [(8, 8), (9, 4), (30, 8), (5, 2), (3, 3)]:
+        edges = [parallel.pair_range(n, r, w) for r in range(w)]
+        assert edges[0][0] == 0 and edges[-1][1] == n
+        for (a0, a1), (b0, b1) in zip(edges, edges[1:]):
+            assert a1 == b0 and a1 >= a0
+        assert max(b - a for a, b in edges) - min(b - a for a, b in edges) <= 1

@@ -277,3 +277,57 @@ def test_superslomo_errors():
         s.interpolate_frames(np.zeros((3, 64, 64), np.uint8))
     with pytest.raises(ValueError):
         s.interpolate("/tmp", None, (64, 64))
+
+
+def _clip_sharded_worker(rank, world, port, frames, kw, q):
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)     # gloo moves CUDA tensors through the host:
+    try:                                                              # two ranks can share the one test GPU
+        from v2e_b200 import EventEmulator, SuperSloMo, V2EPipeline
+        fc, at = _weights(5)
+        sl = SuperSloMo(model=None, auto_upsample=False, upsampling_factor=3, batch_size=2,
+                        state_dicts={'state_dictFC': fc, 'state_dictAT': at})
+        em = EventEmulator(device="cuda:0", seed=9, shard=(rank, world, None), **kw)
+        rows, t, nf = V2EPipeline(sl, em).run_clip_sharded(frames, 0.2)
+        q.put((rank, rows, nf))
+        sl.cleanup()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_one_clip_sharded_over_two_ranks_matches_single_gpu():
+    """BASELINE config 5 layout: SloMo sharded over frame pairs, all-to-all of uint8 row bands, pixel model
+    sharded over rows with the per-frame all-reduce(MAX). The union of the two ranks' events must equal the
+    single-process pipeline's events frame by frame (noise off: no per-frame draws; thresholds seeded)."""
+    import socket
+    import torch.multiprocessing as mp
+    from v2e_b200 import EventEmulator, SuperSloMo, V2EPipeline
+    rng = np.random.default_rng(4)
+    big = np.kron(rng.integers(30, 220, (14, 30)).astype(np.uint8), np.ones((8, 8), np.uint8))
+    frames = np.stack([big[3:3 + 96, 4 * k:4 * k + 128] for k in range(6)])     # 5 pairs, 96x128
+    kw = dict(cutoff_hz=200, leak_rate_hz=0, shot_noise_rate_hz=0, refractory_period_s=0.001, sigma_thres=0.02)
+    fc, at = _weights(5)
+    sl = SuperSloMo(model=None, auto_upsample=False, upsampling_factor=3, batch_size=2,
+                    state_dicts={'state_dictFC': fc, 'state_dictAT': at})
+    em = EventEmulator(device="cuda:0", seed=9, rng_mode="device", **kw)
+    ev, offs, t, nf = V2EPipeline(sl, em).run(frames, 0.2)
+    sl.cleanup()
+    assert nf == 15 and ev.shape[0] > 0
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_clip_sharded_worker, args=(r, 2, port, frames, kw, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[2] == 15 for r in res)
+    got = np.concatenate([r[1] for r in sorted(res, key=lambda r: r[0])], 0)
+    assert got.shape == ev.shape
+    key = lambda e: e[np.lexsort((e[:, 3], e[:, 1], e[:, 2], e[:, 0]))]
+    assert np.array_equal(key(got), key(np.asarray(ev)))

@@ -469,12 +469,32 @@ class EventEmulator(object):
         with a single-GPU run) and keeps its rows."""
         return draw((H, W))[y0:y1].contiguous()
 
-    def _generate_sharded(self, fr_full, code, t_frame):
+    def generate_events_band(self, band_frame, t_frame, full_height):
+        """Pixel-sharded operation with the rows already cut: band_frame is [y1-y0, W], this rank's rows
+        (v2e_b200.parallel.row_band) of a frame of `full_height` rows -- what the frame exchange of
+        V2EPipeline.run_clip_sharded delivers. Same contract as generate_events otherwise."""
+        if self.shard is None:
+            raise RuntimeError("generate_events_band needs shard=(rank, world, group)")
+        t_frame = float(t_frame)
+        self.frame_counter += 1
+        self._check_time(t_frame)
+        fr, code = self._to_device_frames(band_frame)
+        y0, y1 = self._band(int(full_height))
+        if fr.dim() != 2 or fr.shape[0] != y1 - y0:
+            raise ValueError("band_frame must hold rows [%d, %d) of the frame" % (y0, y1))
+        return self._generate_sharded(fr, code, t_frame, full_height=int(full_height))
+
+    def _generate_sharded(self, fr_full, code, t_frame, full_height=None):
         import torch.distributed as dist
         rank, world, group = self.shard
-        H, W = fr_full.shape
-        y0, y1 = self._band(H)
-        fr = fr_full[y0:y1].contiguous()
+        if full_height is None:
+            H, W = fr_full.shape
+            y0, y1 = self._band(H)
+            fr = fr_full[y0:y1].contiguous()
+        else:
+            H, W = full_height, fr_full.shape[1]
+            y0, y1 = self._band(H)
+            fr = fr_full.contiguous()
         hb = y1 - y0
         if hb == 0:
             raise ValueError("more ranks than pixel rows")

@@ -5,6 +5,10 @@ The paths shard without a data-path collective:
   * independent clips (BASELINE config 4): clips are dealt round-robin to ranks, every rank runs the
     whole SloMo + pixel-model path on its clips;
   * the only exchange is the merge of the packed event streams at the end (`gather_event_streams`).
+One clip over several GPUs (BASELINE config 5): SloMo is sharded over frame PAIRS (every (pair, t) is
+independent given the pair, slomo.py:404-433, so no halo), the pixel model over pixel ROWS (per-pixel state;
+one all-reduce(MAX) of an int32 per frame, emulator.py:773-775); in between every rank needs its rows of
+every frame: `exchange_frame_bands`, one all-to-all of uint8 row bands.
 Nothing here touches model arithmetic.
 """
 import numpy as np
@@ -29,6 +33,46 @@ def row_band(height, rank, world, align=1):
     u0 = rank * base + min(rank, extra)
     u1 = u0 + base + (1 if rank < extra else 0)
     return min(u0 * align, height), min(u1 * align, height)
+
+
+def pair_range(n_pairs, rank, world):
+    """[p0, p1) of the consecutive frame pairs rank `rank` interpolates when ONE clip's SloMo is sharded
+    over ranks (contiguous, so that the rank's interpolated frames are a contiguous run of the clip)."""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    base, extra = divmod(n_pairs, world)
+    p0 = rank * base + min(rank, extra)
+    return p0, p0 + base + (1 if rank < extra else 0)
+
+
+def exchange_frame_bands(frames_local, height, group=None):
+    """frames_local: [M_r, H, W] uint8, the interpolated frames this rank synthesised (ranks hold consecutive
+    runs of the clip, in rank order). Returns [sum_r M_r, y1-y0, W]: rows `row_band(H, rank, world)` of EVERY
+    frame of the clip, in clip order. NCCL: one all-to-all of the row bands (rank r sends rank q the band q
+    of its frames). Backends without all-to-all (gloo, in the tests): every rank's frames are all-gathered
+    and cut locally."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if frames_local.dim() != 3 or frames_local.dtype != torch.uint8 or frames_local.shape[1] != height:
+        raise ValueError("frames_local must be [M, H, W] uint8")
+    W = frames_local.shape[2]
+    dev = frames_local.device
+    m = torch.tensor([frames_local.shape[0]], dtype=torch.int64, device=dev)
+    ms = [torch.zeros_like(m) for _ in range(world)]
+    dist.all_gather(ms, m, group=group)
+    ms = [int(x.item()) for x in ms]
+    y0, y1 = row_band(height, rank, world)
+    if dist.get_backend(group) == "nccl":
+        send = [frames_local[:, a:b, :].contiguous() for a, b in (row_band(height, q, world) for q in range(world))]
+        recv = [torch.empty((ms[r], y1 - y0, W), dtype=torch.uint8, device=dev) for r in range(world)]
+        dist.all_to_all(recv, send, group=group)
+        return torch.cat(recv, 0)
+    mx = max(ms)
+    pad = torch.zeros((mx, height, W), dtype=torch.uint8, device=dev)
+    pad[:frames_local.shape[0]] = frames_local
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    return torch.cat([b[:c, y0:y1, :] for b, c in zip(bufs, ms)], 0).contiguous()
 
 
 def gather_event_streams(rows, clip_ids=None, dst=0, group=None):

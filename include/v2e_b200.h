@@ -262,6 +262,21 @@ int v2e_resize_create(int src_w, int src_h, int dst_w, int dst_h, int filter, in
 int v2e_resize_destroy(V2eResizer *r);
 int v2e_resize_run(V2eResizer *r, const uint8_t *src_dev, uint8_t *dst_dev, int n_images, void *stream);
 
+/* ------------------------------------------------------------------------- */
+/* Event-sink row conversions: packed rows [t, x, y, p] float32 -> what the reference's writers
+ * store. events_dev: [n][4] float32, 16-byte aligned. Enqueue only.                                             */
+/* ------------------------------------------------------------------------- */
+/* HDF5 "events" dataset rows (emulator.py:953-959): rows_dev [n][4] uint32 = [t * 1e6 (float32 product,
+ * truncated), x, y, p with -1 -> 0]. */
+int v2e_events_to_h5_rows(const float *events_dev, uint64_t n, uint32_t *rows_dev, void *stream);
+/* AEDAT-2.0 body (v2ecore/output/aedat2_output.py:133-165): words_dev [2n] uint32 = per event the address
+ * x << x_shift | y << y_shift | p01 << pol_shift (x, y flipped about size-1 when asked) and the int32 microsecond
+ * timestamp, both big endian, ready for file.write(). The shifts / flips of the three supported cameras are in
+ * aedat2_output.py:38-60. n_on_dev (nullable): += number of ON events (numOnEvents, :176). */
+int v2e_events_to_aedat2(const float *events_dev, uint64_t n, int size_x, int size_y, int x_shift, int y_shift,
+                         int pol_shift, int flip_x, int flip_y, uint32_t *words_dev, uint64_t *n_on_dev,
+                         void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -82,6 +82,8 @@ _SIGS = {
     "v2e_resize_run": (_i, [_vp, _vp, _vp, _i, _vp]),
     "v2e_emu_set_scidvs_tau": (_i, [_vp, _vp]),
     "v2e_emu_set_pr_noise": (_i, [_vp, _vp, ctypes.POINTER(_d), _i]),
+    "v2e_events_to_h5_rows": (_i, [_vp, _u64, _vp, _vp]),
+    "v2e_events_to_aedat2": (_i, [_vp, _u64, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "v2e_emu_profile": (_i, [_vp, _i]),
     "v2e_emu_profile_read": (_i, [_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_i), _vp]),
     "v2e_emu_profile_read4": (_i, [_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_i), _vp]),

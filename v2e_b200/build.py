@@ -21,6 +21,7 @@ UNITS = {
     "emu.cu": ["-fmad=false"],
     "slomo.cu": [],
     "conv_tc.cu": [],
+    "sinks.cu": [],
 }
 
 

@@ -217,6 +217,21 @@ int v2e_conv2d_lrelu_sm100_strip(const void *x1_dev, int C1, const void *x2_dev,
                                  int out_mode, int co_real, float slope, void *stream);
 int v2e_conv_strip_pick_kc(int C1, int C2, int Cout_pad, int KH, int KW, int W);
 
+/* conv2d 3x3 (+bias +LeakyReLU) over the x2 bilinear up-sampling (align_corners=False) of x_low, i.e. the first
+ * convolution of an up block (model.py:140-147: interpolate -> conv1 -> leaky_relu) WITHOUT materialising the
+ * up-sampled tensor: the up-sampling is folded into four phase-specific 3x3 filters over the low-resolution
+ * tensor (v2e_conv_up2_fold_weights), a 2-pixel frame is rewritten by a direct kernel.
+ *   x_low_dev [N, H_out/2, W_out/2, C] fp16 NHWC, C a multiple of 64; out_dev [N, H_out, W_out, out_cstride] fp16.
+ *   wgt_fold_dev: output of v2e_conv_up2_fold_weights copied to the device; wgt_plain_dev: the layout of
+ *   v2e_conv2d_lrelu_sm100 ([Cout_pad][9*C]), used for the frame. Cout_pad must be 32, 0 <= slope <= 1.
+ * v2e_conv_up2_supported_c returns 1 when a layer qualifies (weights resident in shared memory). */
+int v2e_conv2d_up2_lrelu_sm100(const void *x_low_dev, int C, const void *wgt_fold_dev, const void *wgt_plain_dev,
+                               const float *bias_dev, int Cout_pad, int N, int H_out, int W_out, void *out_dev,
+                               int out_cstride, float slope, void *stream);
+/* w_host: float32 [cout][cin][3][3]; out_host: fp16 [C_pad/64][2][3][6][Cout_pad][64] (host buffers). */
+int v2e_conv_up2_fold_weights(const float *w_host, int cout, int cin, int Cout_pad, int C_pad, void *out_host);
+int v2e_conv_up2_supported_c(int C, int Cout_pad, int W_out);
+
 /* The 23 convolutions of one UNet (model.py:184-196) in forward order: conv1, conv2,
  * down1..down5 {conv1, conv2}, up1..up5 {conv1, conv2}, conv3. Host pointers to the float32
  * tensors of the reference's state_dict ([Cout][Cin][KH][KW] weights, [Cout] biases), i.e. what

@@ -331,3 +331,41 @@ def test_one_clip_sharded_over_two_ranks_matches_single_gpu():
     assert got.shape == ev.shape
     key = lambda e: e[np.lexsort((e[:, 3], e[:, 1], e[:, 2], e[:, 0]))]
     assert np.array_equal(key(got), key(np.asarray(ev)))
+
+
+@pytest.mark.parametrize("case", [(2, 48, 640, 64, 32), (1, 38, 512, 64, 17), (1, 8, 768, 64, 32)])
+def test_fused_upsample_conv_matches_torch(case):
+    """conv3x3(bilinear_up2(x)) + bias + LeakyReLU with the up-sampling folded into the filter (strip2up + frame
+    kernel) vs torch's interpolate -> conv2d on the same fp16-rounded input and weights. The folded filter is
+    rounded to fp16 after the combination, so the tolerance is 5e-3 rel + 5e-3 abs (same order as the per-tap bar)."""
+    N, H, W, C, Cout = case                       # H, W: output size
+    Lm, L = _lib()
+    assert L.v2e_conv_up2_supported_c(C, cout_pad(Cout), W) == 1
+    g = torch.Generator().manual_seed(hash(case) & 0xFFFF)
+    x = torch.randn((N, C, H // 2, W // 2), generator=g).to(DEV)
+    w = (torch.randn((Cout, C, 3, 3), generator=g) / np.sqrt(C * 9)).to(DEV)
+    b = (torch.randn((Cout,), generator=g) * 0.1).to(DEV)
+    a = to_nhwc16(x)
+    Cp = cout_pad(Cout)
+    wp, _ = pack_w(w, C, 0)
+    fold = np.zeros(((C // 64) * 2 * 3 * 6 * Cp * 64,), np.float16)
+    wh = np.ascontiguousarray(w.half().float().cpu().numpy())
+    Lm.check(L.v2e_conv_up2_fold_weights(wh.ctypes.data_as(ctypes.c_void_p), Cout, C, Cp, C,
+                                         fold.ctypes.data_as(ctypes.c_void_p)))
+    fold_d = torch.from_numpy(fold).to(DEV)
+    bp = torch.zeros(Cp, device=DEV)
+    bp[:Cout] = b
+    out = torch.full((N, H, W, Cp), float("nan"), dtype=torch.float16, device=DEV)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    Lm.check(L.v2e_conv2d_up2_lrelu_sm100(p(a), C, p(fold_d), p(wp), p(bp), Cp, N, H, W, p(out), Cp, ctypes.c_float(0.1), st))
+    torch.cuda.synchronize()
+    up = torch.nn.functional.interpolate(x.half().float(), scale_factor=2, mode="bilinear", align_corners=False)
+    ref = torch.nn.functional.leaky_relu(torch.nn.functional.conv2d(up, w.half().float(), b, padding=1), 0.1)
+    ref = ref.permute(0, 2, 3, 1)
+    got = out[..., :Cout].float()
+    assert torch.isfinite(out.float()).all()
+    err = (got - ref).abs() - 5e-3 * ref.abs()
+    assert (err <= 5e-3).all(), (err.max().item(), torch.nonzero(err > 5e-3)[:5].tolist())
+    if Cp > Cout:
+        assert (out[..., Cout:] == 0).all()

@@ -702,6 +702,304 @@ conv_strip2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// strip2up: conv3x3(bilinear_up2(L)) + bias + LeakyReLU without materialising the up-sampled tensor
+// (model.py:140-147: up.forward = interpolate(x, scale_factor=2, mode='bilinear') -> conv1 -> leaky_relu).
+//
+// The x2 bilinear up-sampling (align_corners=False) is linear and shift-invariant with period 2, so it folds
+// into the convolution: out[2m+py][2j+px] = sum_{a,b in -1..1} Wf[py][px][a][b] . L[m+a][j+b] -- four
+// phase-specific 3x3 filters over the LOW-resolution tensor (Wf = W combined with the 0.25/0.75 coefficients,
+// built in float32 on the host, scratch/fold_upsample.py checks the identity). Same MACs as the convolution
+// over the up-sampled tensor, a quarter of the input bytes, no upsample kernel. In the strip2 scheme a
+// low-resolution input row k feeds SIX output rows (2k-2 .. 2k+3), so the stack is N = 6*Cout = 192 columns
+// per MMA (better A reuse than the 3-row stack of the plain 3x3), and the two horizontal phases are two
+// M tiles over the same A windows with their own weights and their own accumulator ring (epilogue warp group
+// g drains phase g and writes pixels 2j+g). Only the 2-pixel frame of the image differs (bilinear clamping
+// and the conv's zero padding are not shift-invariant there); a small direct kernel rewrites it afterwards.
+// ---------------------------------------------------------------------------------------------
+constexpr int kUpBlocks = 6;
+
+__global__ void __launch_bounds__(kStrip2Threads)
+conv_strip2up_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const StripParams p) {
+    constexpr int KC = 64, KW = 3;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t full_bar[kMaxSlot], empty_bar[kMaxSlot], w_bar, acc_full[kMaxAcc], acc_empty[kMaxAcc];
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slabs = p.C1 / KC;
+    constexpr int PW = kRowTile + KW - 1;
+    uint8_t *ring = smem + ((p.w_bytes + 1023) & ~1023);
+    const int R = p.acc_slots;
+    const uint32_t BN = (uint32_t)p.BN;
+    const uint32_t tile_bytes = BN * (uint32_t)KC * 2u;
+    const int hl = p.H / 2, wl = p.W / 2;                     // low-resolution input size
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.nslot; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&w_bar, 1);
+        for (int s = 0; s < R; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
+        fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); }
+    if (warp == 1) {
+        tmem_alloc(&tmem_base_smem, (uint32_t)p.tmem_cols);
+        tmem_relinquish();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        // ===== TMA producer: folded weights (already in stack order), then low-resolution rows =====
+        if (lane == 0) {
+            mbar_expect_tx(&w_bar, (uint32_t)p.w_bytes);
+            for (int l = 0; l < p.w_loads; l++)
+                tma_load_2d(smem + (size_t)l * p.w_rows_per_load * KC * 2, &tmB, &w_bar, 0, l * p.w_rows_per_load);
+            uint32_t cnt = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                const int tx = item % p.tiles_x, rest = item / p.tiles_x;
+                const int seg = rest % p.n_seg, n = rest / p.n_seg;
+                const int ka = seg * p.seg_h, kb = min(hl, ka + p.seg_h);
+                const int j0 = tx * kRowTile;
+                for (int k = ka - 1; k <= kb; k++) {
+                    for (int sl = 0; sl < slabs; sl++, cnt++) {
+                        const int e = (int)(cnt % (uint32_t)p.nslot);
+                        const uint32_t phase = (cnt / (uint32_t)p.nslot) & 1u;
+                        mbar_wait(&empty_bar[e], phase ^ 1);
+                        mbar_expect_tx(&full_bar[e], (uint32_t)(PW * KC * 2));
+                        tma_load_4d(ring + (size_t)e * p.slab_bytes, &tmA, &full_bar[e], sl * KC, j0 - 1, k, n);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        const uint32_t leader = elect_one();
+        constexpr uint32_t rowb = (uint32_t)KC * 2u, sbo = 8u * rowb;
+        constexpr int ksteps = KC / 16;
+        const uint64_t dhi = make_smem_desc(0, 2u, sbo);                  // SWIZZLE_128B
+        const uint32_t lo_flags = (uint32_t)(dhi & 0xFFFF0000u);
+        const uint32_t w16 = (smem_u32(smem) >> 4) | lo_flags, ring16 = (smem_u32(ring) >> 4) | lo_flags;
+        const uint32_t slab16 = (uint32_t)p.slab_bytes >> 4, tile16 = tile_bytes >> 4;
+        const uint32_t phase_cols = (uint32_t)R * BN;                     // accumulator ring of phase 1 starts here
+        mbar_wait(&w_bar, 0);
+        uint32_t cnt = 0, orow = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            const int rest = item / p.tiles_x;
+            const int seg = rest % p.n_seg;
+            const int ka = seg * p.seg_h, kb = min(hl, ka + p.seg_h);
+            const int rows_out = 2 * (kb - ka), rows_in = (kb - ka) + 2;
+            for (int ii = 0; ii < rows_in; ii++) {
+                // low row k = ka-1+ii feeds output rows (relative) 2ii-4+q, q = 0..5
+                for (int t = 0; t < 2; t++) {                             // output rows that start here
+                    const int yr = 2 * ii + t;
+                    if (yr < rows_out) {
+                        const uint32_t g = orow + (uint32_t)yr;
+                        mbar_wait(&acc_empty[g % (uint32_t)R], (g / (uint32_t)R) & 1u);
+                    }
+                }
+                tcgen05_fence_after();
+                const int q_lo = max(0, 4 - 2 * ii), q_hi = min(kUpBlocks - 1, rows_out + 3 - 2 * ii);
+                uint32_t rd[3], rb[3], ri[3];
+                int nr = 0;
+                for (int q = q_lo; q <= q_hi && nr < 3;) {
+                    const int yr = 2 * ii - 4 + q;
+                    const int slot = (int)((orow + (uint32_t)yr) % (uint32_t)R);
+                    const int nb = min(q_hi - q + 1, R - slot);
+                    rd[nr] = (uint32_t)slot * BN;
+                    rb[nr] = (uint32_t)q * tile16;
+                    ri[nr] = make_idesc_f16(kBM, nb * (int)BN);
+                    nr++;
+                    q += nb;
+                }
+                for (int sl = 0; sl < slabs; sl++, cnt++) {
+                    const uint32_t e = cnt % (uint32_t)p.nslot;
+                    mbar_wait(&full_bar[e], (cnt / (uint32_t)p.nslot) & 1u);
+                    tcgen05_fence_after();
+                    const uint32_t a_lo = ring16 + e * slab16;
+#pragma unroll
+                    for (int px = 0; px < 2; px++) {
+                        const uint32_t d0 = tmem_base + (uint32_t)px * phase_cols;
+#pragma unroll
+                        for (int b = 0; b < KW; b++) {
+                            const uint32_t b_tile = w16 + (uint32_t)(((sl * 2 + px) * KW + b) * kUpBlocks) * tile16;
+#pragma unroll
+                            for (int j = 0; j < ksteps; j++) {
+                                const uint64_t adesc = desc_with_lo(dhi, a_lo + (uint32_t)(b * (rowb >> 4) + 2 * j));
+#pragma unroll
+                                for (int k = 0; k < 3; k++)
+                                    if (k < nr)
+                                        umma_f16_pred(d0 + rd[k], adesc, desc_with_lo(dhi, b_tile + rb[k] + (uint32_t)(2 * j)),
+                                                      ri[k], 1u, leader);
+                            }
+                        }
+                    }
+                    umma_commit_pred(&empty_bar[e], leader);
+                }
+                for (int t = 0; t < 2; t++) {                             // output rows that just completed
+                    const int yr = 2 * ii - 4 + t;
+                    if (yr >= 0 && yr < rows_out) {
+                        const uint32_t g = orow + (uint32_t)yr;
+                        umma_commit_pred(&acc_full[g % (uint32_t)R], leader);
+                    }
+                }
+            }
+            orow += (uint32_t)rows_out;
+        }
+    } else {
+        // ===== epilogue: warps 2..5 drain horizontal phase 0 (even output columns), warps 6..9 phase 1 =====
+        const int q4 = warp & 3, px = (warp - 2) >> 2;
+        const int m = q4 * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
+        const uint32_t col0 = (uint32_t)px * (uint32_t)R * BN;
+        for (int s = 0; s < R; s++)
+            for (uint32_t c0 = 0; c0 < BN; c0 += 16) tmem_st_zero_32x32b_x16(tmem_base + lane_addr + col0 + (uint32_t)s * BN + c0);
+        tmem_st_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0)
+            for (int s = 0; s < R; s++) mbar_arrive(&acc_empty[s]);
+        float bias_r[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) bias_r[j] = __ldg(p.bias + j);
+        const float slope = p.slope;
+        uint32_t orow = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            const int tx = item % p.tiles_x, rest = item / p.tiles_x;
+            const int seg = rest % p.n_seg, n = rest / p.n_seg;
+            const int ka = seg * p.seg_h, kb = min(hl, ka + p.seg_h);
+            const int jl = tx * kRowTile + m;                             // low-resolution column of this thread
+            const bool inb = jl < wl;
+            const size_t pix0 = ((size_t)n * p.H + 2 * ka) * p.W + (size_t)(2 * jl + px);
+            __half *o16 = (__half *)p.out + pix0 * p.out_cstride;
+            const size_t step16 = (size_t)p.W * p.out_cstride;
+            uint32_t g = orow, slot = g % (uint32_t)R, par = (g / (uint32_t)R) & 1u;
+            for (int yr = 0; yr < 2 * (kb - ka); yr++) {
+                mbar_wait(&acc_full[slot], par);
+                tcgen05_fence_after();
+                const uint32_t tmem_acc = tmem_base + lane_addr + col0 + slot * BN;
+                uint32_t v[32];
+                tmem_ld_32x32b_x16(tmem_acc, v);
+                tmem_ld_32x32b_x16(tmem_acc + 16, v + 16);
+                tmem_ld_wait();
+                tmem_st_zero_32x32b_x16(tmem_acc);
+                tmem_st_zero_32x32b_x16(tmem_acc + 16);
+                if (inb) {
+#pragma unroll
+                    for (int c0 = 0; c0 < 32; c0 += 16) {
+                        __half2 h[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            const float x0 = __uint_as_float(v[c0 + 2 * j]) + bias_r[c0 + 2 * j];
+                            const float x1 = __uint_as_float(v[c0 + 2 * j + 1]) + bias_r[c0 + 2 * j + 1];
+                            h[j] = __floats2half2_rn(fmaxf(x0, x0 * slope), fmaxf(x1, x1 * slope));
+                        }
+                        uint4 *dst = (uint4 *)(o16 + c0);
+                        dst[0] = *(uint4 *)&h[0];
+                        dst[1] = *(uint4 *)&h[4];
+                    }
+                }
+                o16 += step16;
+                tmem_st_wait();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[slot]);
+                if (++slot == (uint32_t)R) { slot = 0; par ^= 1u; }
+            }
+            orow += (uint32_t)(2 * (kb - ka));
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    }
+}
+
+// The 2-pixel frame of conv3x3(up2(L)): direct evaluation with the unfolded weights [Cout_pad][9*C] (K index =
+// tap*C + c), the bilinear sample rounded to fp16 like the materialised tensor would be, zero outside the
+// up-sampled image. C = 64, Cout_pad = 32. One warp per frame pixel: a lane holds two channels (one half2) of
+// the nine bilinear samples; the 32 output channels are 32 dot products over (tap, channel) against weights
+// staged in shared memory. A lane's 18 products per output channel are accumulated with HFMA2 (the frame is
+// 1.4 % of the layer's pixels; the partial sums are ~0.2 in magnitude, fp16 rounding of them stays below
+// 1e-3 absolute), widened to float32 for the cross-lane reduction: a halving butterfly after which lane co holds
+// output channel co.
+__global__ void __launch_bounds__(128, 4)
+conv_up2_border_kernel(const __half *__restrict__ L, const __half *__restrict__ wgt, const float *__restrict__ bias,
+                       __half *__restrict__ out, int N, int H, int W, int out_cstride, float slope) {
+    constexpr int C = 64, BN = 32;
+    extern __shared__ __align__(16) unsigned char s_wraw[];
+    __half2 *s_w = (__half2 *)s_wraw;                          // [co][tap][32 lanes] half2
+    for (int i = threadIdx.x; i < BN * 9 * 32; i += blockDim.x) s_w[i] = ((const __half2 *)wgt)[i];
+    __syncthreads();
+    const int hl = H / 2, wl = W / 2;
+    const int per_img = 4 * W + 4 * (H - 4);                  // rows 0,1,H-2,H-1 and columns 0,1,W-2,W-1 of the rest
+    const long total = (long)N * per_img;
+    const int lane = threadIdx.x & 31;
+    const long warp0 = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarps = (long)gridDim.x * (blockDim.x >> 5);
+    const float bias_l = bias[lane];
+    const __half2 *base = (const __half2 *)L + lane;
+    for (long pi = warp0; pi < total; pi += nwarps) {
+        const int n = (int)(pi / per_img), f = (int)(pi % per_img);
+        int y, x;
+        if (f < 4 * W) { const int r = f / W; y = r < 2 ? r : H - 4 + r; x = f % W; }
+        else { const int g = f - 4 * W; const int c = g % 4; y = 2 + g / 4; x = c < 2 ? c : W - 4 + c; }
+        __half2 smp[9];
+#pragma unroll
+        for (int t = 0; t < 9; t++) {
+            const int uy = y + t / 3 - 1, ux = x + t % 3 - 1;
+            __half2 v = __floats2half2_rn(0.f, 0.f);
+            if (uy >= 0 && uy < H && ux >= 0 && ux < W) {
+                const float sy = fmaxf(0.f, (uy + 0.5f) * 0.5f - 0.5f), sx = fmaxf(0.f, (ux + 0.5f) * 0.5f - 0.5f);
+                const int y0 = (int)sy, y1 = min(y0 + 1, hl - 1), x0 = (int)sx, x1 = min(x0 + 1, wl - 1);
+                const float ly = sy - (float)y0, lx = sx - (float)x0;
+                const float2 a = __half22float2(base[(((size_t)n * hl + y0) * wl + x0) * (C / 2)]);
+                const float2 b = __half22float2(base[(((size_t)n * hl + y0) * wl + x1) * (C / 2)]);
+                const float2 c = __half22float2(base[(((size_t)n * hl + y1) * wl + x0) * (C / 2)]);
+                const float2 d = __half22float2(base[(((size_t)n * hl + y1) * wl + x1) * (C / 2)]);
+                const float v0 = (1.f - ly) * ((1.f - lx) * a.x + lx * b.x) + ly * ((1.f - lx) * c.x + lx * d.x);
+                const float v1 = (1.f - ly) * ((1.f - lx) * a.y + lx * b.y) + ly * ((1.f - lx) * c.y + lx * d.y);
+                v = __floats2half2_rn(v0, v1);
+            }
+            smp[t] = v;
+        }
+        // two groups of 16 output channels (keeps 16 accumulators live): partial dot products, a halving
+        // butterfly over lane bits 3..0 (lane keeps channel lane & 15 of the group), then the two 16-lane halves
+        // are added; the half whose index equals the group writes
+        float res = 0.f;
+#pragma unroll
+        for (int g = 0; g < 2; g++) {
+            float acc[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const int co = g * 16 + j;
+                __half2 h = __hmul2(smp[0], s_w[(co * 9) * 32 + lane]);
+#pragma unroll
+                for (int t = 1; t < 9; t++) h = __hfma2(smp[t], s_w[(co * 9 + t) * 32 + lane], h);
+                const float2 hf = __half22float2(h);
+                acc[j] = hf.x + hf.y;
+            }
+#pragma unroll
+            for (int o = 8; o >= 1; o >>= 1) {
+                const bool up = (lane & o) != 0;
+#pragma unroll
+                for (int j = 0; j < o; j++) {
+                    const float mine = up ? acc[j + o] : acc[j];
+                    const float send = up ? acc[j] : acc[j + o];
+                    acc[j] = mine + __shfl_xor_sync(0xffffffffu, send, o);
+                }
+            }
+            const float tot = acc[0] + __shfl_xor_sync(0xffffffffu, acc[0], 16);
+            if ((lane >> 4) == g) res = tot;                   // channel g*16 + (lane & 15) == lane
+        }
+        const float v = res + bias_l;
+        out[(((size_t)n * H + y) * W + x) * out_cstride + lane] = __float2half_rn(fmaxf(v, v * slope));
+    }
+}
+
 }  // namespace
 
 // =============================================================================================
@@ -1059,6 +1357,149 @@ extern "C" int v2e_conv2d_lrelu_sm100_strip(const void *x1_dev, int C1, const vo
     if (rc) return rc;
     return v2e_strip_launch(&L, (cudaStream_t)stream);
 }
+
+
+// ---- fused up-sample + 3x3 convolution (strip2up) host side ---------------------------------------------
+struct V2eUpLaunch {
+    CUtensorMap tmA, tmB;
+    StripParams p;
+    int grid;
+    size_t smem;
+    const __half *low;            // border kernel inputs
+    const __half *w_plain;
+    int C;
+};
+
+// 64-channel slabs, Cout_pad = 32, folded weights resident: slabs * 36 tiles of 32 x 64 fp16
+int v2e_conv_up2_supported(int C, int Cout_pad, int W_out) {
+    if (C != 64 || Cout_pad != 32 || W_out % 2 || W_out < 4 * kRowTile) return 0;   // the frame kernel is written for C = 64
+    const size_t wb = (size_t)(C / 64) * 2 * 3 * kUpBlocks * Cout_pad * 64 * 2;
+    const size_t slab = ((size_t)(kRowTile + 2) * 64 * 2 + 1023) & ~(size_t)1023;
+    return wb + 2048 + 3 * slab <= 222 * 1024;
+}
+
+// Folds the x2 bilinear up-sampling into the 3x3 filter (see conv_strip2up_kernel). w: float32 [cout][cin][3][3]
+// (the reference's state_dict layout); out: fp16 [C_pad/64][2 px][3 b][6 q][Cout_pad][64], zero padded.
+extern "C" int v2e_conv_up2_fold_weights(const float *w, int cout, int cin, int Cout_pad, int C_pad, void *out_host) {
+    if (!w || !out_host || C_pad % 64 || cin > C_pad || cout > Cout_pad) return v2e_set_error(V2E_E_INVALID, "bad argument%s", "");
+    __half *o = (__half *)out_host;
+    auto coef = [](int i, int a) -> float {      // weight of low index m+a in up-sampled index 2m+i (interior)
+        const int t = i >= 0 ? i / 2 : -((1 - i) / 2), odd = i - 2 * t;
+        if (!odd) return a == t - 1 ? 0.25f : (a == t ? 0.75f : 0.f);
+        return a == t ? 0.75f : (a == t + 1 ? 0.25f : 0.f);
+    };
+    const int slabs = C_pad / 64;
+    for (int sl = 0; sl < slabs; sl++)
+        for (int px = 0; px < 2; px++)
+            for (int b = 0; b < 3; b++)
+                for (int q = 0; q < kUpBlocks; q++) {
+                    const int py = q & 1, a = 1 - (q >> 1);
+                    for (int co = 0; co < Cout_pad; co++)
+                        for (int c = 0; c < 64; c++) {
+                            const int ci = sl * 64 + c;
+                            float v = 0.f;
+                            if (co < cout && ci < cin)
+                                for (int r = 0; r < 3; r++)
+                                    for (int s2 = 0; s2 < 3; s2++)
+                                        v += w[(((size_t)co * cin + ci) * 3 + r) * 3 + s2] * coef(py + r - 1, a) * coef(px + s2 - 1, b - 1);
+                            o[((((size_t)(sl * 2 + px) * 3 + b) * kUpBlocks + q) * Cout_pad + co) * 64 + c] = __float2half_rn(v);
+                        }
+                }
+    return V2E_OK;
+}
+
+size_t v2e_conv_up2_launch_size(void) { return sizeof(V2eUpLaunch); }
+
+int v2e_conv_up2_prepare(V2eUpLaunch *L, const void *x_low, int C, const void *wgt_fold, const void *wgt_plain,
+                         const float *bias, int Cout_pad, int N, int H, int W, void *out, int out_cstride, float slope,
+                         int n_sms) {
+    memset(L, 0, sizeof(*L));
+    if (!v2e_conv_up2_supported(C, Cout_pad, W) || H % 2) return v2e_set_error(V2E_E_INVALID, "layer does not qualify for the fused up-sampling convolution%s", "");
+    if (!(slope >= 0.f && slope <= 1.f)) return v2e_set_error(V2E_E_INVALID, "slope must be in [0, 1]%s", "");
+    StripParams &p = L->p;
+    const int hl = H / 2, wl = W / 2, KC = 64;
+    p.N = N; p.H = H; p.W = W; p.C1 = C; p.C2 = 0; p.KH = 3; p.KW = 3; p.KC = KC; p.BN = Cout_pad;
+    p.tiles_x = (wl + kRowTile - 1) / kRowTile;
+    const int strips = p.tiles_x * N;
+    int n_seg = (6 * n_sms + strips - 1) / strips;
+    if (n_seg < 1) n_seg = 1;
+    int seg_h = (hl + n_seg - 1) / n_seg;
+    if (seg_h < 8) seg_h = hl < 8 ? hl : 8;
+    p.seg_h = seg_h;
+    p.n_seg = (hl + seg_h - 1) / seg_h;
+    p.n_items = strips * p.n_seg;
+    p.variant = 2; p.acc_slots = 8; p.tmem_cols = 512; p.n_split = 1; p.cout_pad = Cout_pad;
+    const int slabs = C / KC;
+    p.slab_bytes = (int)(((size_t)(kRowTile + 2) * KC * 2 + 1023) & ~(size_t)1023);
+    p.w_bytes = slabs * 2 * 3 * kUpBlocks * Cout_pad * KC * 2;
+    const int rows_total = slabs * 2 * 3 * kUpBlocks * Cout_pad;
+    p.w_rows_per_load = kUpBlocks * Cout_pad;                  // 192 rows: one (slab, px, b) stack per load
+    p.w_loads = rows_total / p.w_rows_per_load;
+    int ns = (int)((222 * 1024 - (size_t)p.w_bytes - 2048) / p.slab_bytes);
+    if (ns > kMaxSlot) ns = kMaxSlot;
+    if (ns < 3) return v2e_set_error(V2E_E_INVALID, "fused up-sampling convolution: weights leave no room for the input ring%s", "");
+    p.nslot = ns;
+    p.out_cstride = out_cstride; p.out_mode = 0; p.co_real = Cout_pad; p.slope = slope;
+    p.bias = bias; p.out = out;
+    int rc;
+    if ((rc = make_rowseg_tmap(&L->tmA, x_low, N, hl, wl, C, KC, 3))) return rc;
+    {
+        EncodeTiledFn fn = encode_fn();
+        cuuint64_t dims[2] = {(cuuint64_t)KC, (cuuint64_t)rows_total};
+        cuuint64_t strides[1] = {(cuuint64_t)KC * 2};
+        cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)p.w_rows_per_load};
+        cuuint32_t es[2] = {1, 1};
+        CUresult r = fn(&L->tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *)wgt_fold, dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(KC), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return v2e_set_error(V2E_E_CUDA, "cuTensorMapEncodeTiled failed for folded weights%s", "");
+    }
+    L->smem = (size_t)((p.w_bytes + 1023) & ~1023) + (size_t)p.nslot * p.slab_bytes + 1024;
+    L->grid = p.n_items < n_sms ? p.n_items : n_sms;
+    L->low = (const __half *)x_low;
+    L->w_plain = (const __half *)wgt_plain;
+    L->C = C;
+    return V2E_OK;
+}
+
+int v2e_conv_up2_launch(const V2eUpLaunch *L, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(conv_strip2up_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        attr_set = true;
+    }
+    conv_strip2up_kernel<<<L->grid, kStrip2Threads, L->smem, st>>>(L->tmA, L->tmB, L->p);
+    // the 2-pixel frame, where clamping / zero padding break the shift invariance the folding relies on
+    const StripParams &p = L->p;
+    static int skip_frame = -1;                                   // measurement only: time the main kernel alone
+    if (skip_frame < 0) skip_frame = getenv("V2E_UP2_NO_FRAME") ? 1 : 0;
+    if (skip_frame) return V2E_OK;
+    static bool battr = false;
+    if (!battr) {
+        cudaFuncSetAttribute(conv_up2_border_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 9 * 64 * 2);
+        battr = true;
+    }
+    conv_up2_border_kernel<<<L->grid * 4, 128, 32 * 9 * 64 * 2, st>>>(L->low, L->w_plain, p.bias, (__half *)p.out, p.N, p.H, p.W,
+                                                                       p.out_cstride, p.slope);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return v2e_set_error(V2E_E_CUDA, "conv_strip2up_kernel launch: %s", cudaGetErrorString(e));
+    return V2E_OK;
+}
+
+extern "C" int v2e_conv2d_up2_lrelu_sm100(const void *x_low_dev, int C, const void *wgt_fold_dev, const void *wgt_plain_dev,
+                                          const float *bias_dev, int Cout_pad, int N, int H_out, int W_out, void *out_dev,
+                                          int out_cstride, float slope, void *stream) {
+    V2eUpLaunch L;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int rc = v2e_conv_up2_prepare(&L, x_low_dev, C, wgt_fold_dev, wgt_plain_dev, bias_dev, Cout_pad, N, H_out, W_out, out_dev,
+                                  out_cstride, slope, sms);
+    if (rc) return rc;
+    return v2e_conv_up2_launch(&L, (cudaStream_t)stream);
+}
+
+extern "C" int v2e_conv_up2_supported_c(int C, int Cout_pad, int W_out) { return v2e_conv_up2_supported(C, Cout_pad, W_out); }
 
 extern "C" int v2e_conv_strip_pick_kc(int C1, int C2, int Cout_pad, int KH, int KW, int W) {
     return v2e_strip_pick(C1, C2, Cout_pad, KH, KW, W, nullptr);

@@ -17,6 +17,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -37,6 +38,14 @@ int v2e_strip_prepare(V2eStripLaunch *L, const void *x1, int C1, const void *x2,
                       const float *bias, int Cout_pad, int KH, int KW, int N, int H, int W, void *out,
                       int out_cstride, int out_mode, int co_real, float slope, int n_sms);
 int v2e_strip_launch(const V2eStripLaunch *L, cudaStream_t st);
+struct V2eUpLaunch;
+int v2e_conv_up2_supported(int C, int Cout_pad, int W_out);
+extern "C" int v2e_conv_up2_fold_weights(const float *w, int cout, int cin, int Cout_pad, int C_pad, void *out_host);
+size_t v2e_conv_up2_launch_size(void);
+int v2e_conv_up2_prepare(V2eUpLaunch *L, const void *x_low, int C, const void *wgt_fold, const void *wgt_plain,
+                         const float *bias, int Cout_pad, int N, int H, int W, void *out, int out_cstride, float slope,
+                         int n_sms);
+int v2e_conv_up2_launch(const V2eUpLaunch *L, cudaStream_t st);
 int v2e_set_error(int code, const char *fmt, const char *detail);
 
 #define CU(call)                                                                              \
@@ -320,6 +329,7 @@ struct UNet {
     __half *w[23];
     __half *w_row[23];           // [slabs][taps][Cout_pad][KC] for layers that run on the strip kernel
     int row_kc[23];              // slab width of the strip kernel; 0: per-tap kernel
+    __half *w_fold[23];          // up-block conv1 with the x2 bilinear up-sampling folded in (strip2up), or null
     float *b[23];
     int cout_pad[23], c1p[23], c2p[23];
 };
@@ -354,8 +364,8 @@ struct V2eSlomo {
     float *img;                   // [B+1,H,W] fp32
     float *maxspeed;              // device scalar
     int curB;
-    std::vector<char> launch_mem, row_mem;
-    int n_sms, force_tap_kernel;
+    std::vector<char> launch_mem, row_mem, up_mem;
+    int n_sms, force_tap_kernel, no_fused_up;
     // measurement hooks: CUDA events around every conv launch
     int profile;
     std::vector<cudaEvent_t> ev;
@@ -387,6 +397,15 @@ static int upload_unet(UNet &u, const V2eUNetWeights *wts, int W) {
             }
         std::vector<float> bias(cp, 0.f);
         for (int o = 0; o < l.cout; o++) bias[o] = wts->b[i][o];
+        u.w_fold[i] = nullptr;
+        if (i >= 12 && i < 22 && (i & 1) == 0 && l.k == 3 && !c2p && v2e_conv_up2_supported(c1p, cp, W >> layer_level(i))) {
+            // conv1 of an up block: its input is interpolate(x, 2, bilinear) (model.py:140-147)
+            std::vector<__half> fold((size_t)(c1p / 64) * 2 * 3 * 6 * cp * 64);
+            int frc = v2e_conv_up2_fold_weights(src, l.cout, l.cin1, cp, c1p, fold.data());
+            if (frc) return frc;
+            CU(cudaMalloc((void **)&u.w_fold[i], fold.size() * sizeof(__half)));
+            CU(cudaMemcpy(u.w_fold[i], fold.data(), fold.size() * sizeof(__half), cudaMemcpyHostToDevice));
+        }
         u.w_row[i] = nullptr;
         u.row_kc[i] = v2e_strip_pick(c1p, c2p, cp, l.k, l.k, W >> layer_level(i), nullptr);
         if (u.row_kc[i]) {
@@ -448,6 +467,8 @@ extern "C" int v2e_slomo_create(int H, int W, int max_batch, const V2eUNetWeight
     h->row_mem.resize(v2e_strip_launch_size());
     { int dev = 0; cudaGetDevice(&dev); h->n_sms = 148; cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, dev); }
     h->force_tap_kernel = 0;
+    h->no_fused_up = getenv("V2E_NO_FUSED_UP") ? 1 : 0;        // A/B measurements
+    h->up_mem.resize(v2e_conv_up2_launch_size());
     *out = h;
     return V2E_OK;
 }
@@ -455,7 +476,7 @@ extern "C" int v2e_slomo_create(int H, int W, int max_batch, const V2eUNetWeight
 extern "C" int v2e_slomo_destroy(V2eSlomo *h) {
     if (!h) return V2E_OK;
     for (UNet *u : {&h->flow, &h->interp})
-        for (int i = 0; i < 23; i++) { if (u->w[i]) cudaFree(u->w[i]); if (u->b[i]) cudaFree(u->b[i]); if (u->w_row[i]) cudaFree(u->w_row[i]); }
+        for (int i = 0; i < 23; i++) { if (u->w[i]) cudaFree(u->w[i]); if (u->b[i]) cudaFree(u->b[i]); if (u->w_row[i]) cudaFree(u->w_row[i]); if (u->w_fold[i]) cudaFree(u->w_fold[i]); }
     void *ptrs[] = {h->in16, h->x0, h->s1, h->flow_out, h->intrp_out, h->img, h->maxspeed};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int l = 0; l < 5; l++) {
@@ -498,6 +519,29 @@ static int conv(V2eSlomo *h, const UNet &u, int li, const __half *x1, const __ha
     return rc;
 }
 
+static int conv_up2(V2eSlomo *h, const UNet &u, int li, const __half *x_low, int B, int H, int W, void *out, cudaStream_t st) {
+    V2eUpLaunch *L = (V2eUpLaunch *)h->up_mem.data();
+    int rc = v2e_conv_up2_prepare(L, x_low, u.c1p[li], u.w_fold[li], u.w[li], u.b[li], u.cout_pad[li], B, H, W, out,
+                                  u.cout_pad[li], kSlope, h->n_sms);
+    if (rc) return rc;
+    if (h->profile) {
+        if (h->ev_used + 2 > h->ev.size()) {
+            size_t old = h->ev.size();
+            h->ev.resize(old + 512);
+            for (size_t i = old; i < h->ev.size(); i++) cudaEventCreate(&h->ev[i]);
+        }
+        cudaEventRecord(h->ev[h->ev_used], st);
+    }
+    rc = v2e_conv_up2_launch(L, st);
+    if (h->profile) {
+        cudaEventRecord(h->ev[h->ev_used + 1], st);
+        h->ev_used += 2;
+        const LayerSpec &l = u.L[li];
+        h->conv_flops += 2.0 * B * H * W * (double)l.cout * l.cin1 * 9;
+    }
+    return rc;
+}
+
 // UNet.forward (model.py:198-226). in: NHWC16 fp16 [B,H,W,16]; out: fp32 [B,H,W,8]
 static int unet_forward(V2eSlomo *h, const UNet &u, const __half *in, float *out, int B, cudaStream_t st) {
     const int H = h->H, W = h->W;
@@ -519,10 +563,16 @@ static int unet_forward(V2eSlomo *h, const UNet &u, const __half *in, float *out
     for (int k = 0; k < 5; k++) {                       // up blocks (model.py:125-155)
         const int lvl = 5 - k;                          // x lives at 1/2^lvl
         const int hi = H >> lvl, wi = W >> lvl, ho = hi * 2, wo = wi * 2;
-        const long n = (long)B * (hi + 1) * (wi + 1) * (ui[k] / 8);
-        upsample2_kernel<<<cdiv(n, 256), 256, 0, st>>>(x, h->up[k], B, hi, wi, ui[k]);
         const __half *skip = k < 4 ? h->s[3 - k] : h->s1;
-        if ((rc = conv(h, u, 12 + 2 * k, h->up[k], nullptr, B, ho, wo, h->ua[k], 0, st))) return rc;
+        const int li = 12 + 2 * k;
+        if (u.w_fold[li] && !h->no_fused_up && !h->force_tap_kernel) {
+            // interpolate + conv1 in one kernel: the up-sampled tensor is never written
+            if ((rc = conv_up2(h, u, li, x, B, ho, wo, h->ua[k], st))) return rc;
+        } else {
+            const long n = (long)B * (hi + 1) * (wi + 1) * (ui[k] / 8);
+            upsample2_kernel<<<cdiv(n, 256), 256, 0, st>>>(x, h->up[k], B, hi, wi, ui[k]);
+            if ((rc = conv(h, u, li, h->up[k], nullptr, B, ho, wo, h->ua[k], 0, st))) return rc;
+        }
         if ((rc = conv(h, u, 13 + 2 * k, h->ua[k], skip, B, ho, wo, h->ub[k], 0, st))) return rc;
         x = h->ub[k];
     }
@@ -574,6 +624,7 @@ extern "C" int v2e_slomo_interp(V2eSlomo *h, double t, uint8_t *out_u8_dev, floa
 extern "C" int v2e_slomo_set_option(V2eSlomo *h, int option, int value) {
     if (!h) return v2e_set_error(V2E_E_INVALID, "null handle%s", "");
     if (option == 0) { h->force_tap_kernel = value; return V2E_OK; }
+    if (option == 1) { h->no_fused_up = value; return V2E_OK; }
     return v2e_set_error(V2E_E_INVALID, "unknown option%s", "");
 }
 

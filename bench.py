@@ -285,8 +285,18 @@ def main():
         torch.cuda.synchronize()
         step_ms_prof = (time.perf_counter() - w0) * 1e3
         conv_ms, conv_n, conv_fl = ctypes.c_float(0), ctypes.c_int(0), ctypes.c_double(0)
-        _lib.check(eng.lib.v2e_slomo_profile_read(eng._h, ctypes.byref(conv_ms), ctypes.byref(conv_n),
-                                                  ctypes.byref(conv_fl), eng._stream()))
+        ms23, n23, fl23 = (ctypes.c_float * 23)(), (ctypes.c_int * 23)(), (ctypes.c_double * 23)()
+        _lib.check(eng.lib.v2e_slomo_profile_read_layers(eng._h, ms23, n23, fl23, ctypes.byref(conv_ms),
+                                                         ctypes.byref(conv_n), ctypes.byref(conv_fl), eng._stream()))
+        names = ["conv1", "conv2"] + ["down%d.conv%d" % (d, c) for d in range(1, 6) for c in (1, 2)] + \
+                ["up%d.conv%d" % (d, c) for d in range(1, 6) for c in (1, 2)] + ["conv3"]
+        layers = []
+        for i in range(23):
+            if n23[i]:
+                tf = fl23[i] / (ms23[i] * 1e-3) / 1e12
+                layers.append({"layer": names[i], "launches": n23[i], "ms": ms23[i], "tflops": tf,
+                               "frac": tf / pk["bf16_tflops_sustained"]})
+        big = max(range(23), key=lambda i: ms23[i])
         ms3, n3 = (ctypes.c_float * 4)(), (ctypes.c_int * 4)()
         _lib.check(em._lib.v2e_emu_profile_read4(em._h, ms3, n3, em._stream()))
         _lib.check(eng.lib.v2e_slomo_profile(eng._h, 0))
@@ -300,7 +310,16 @@ def main():
                          "frac": achieved / pk["bf16_tflops_sustained"], "traffic": None,
                          "peak_source": pk["source"] + " (sustained 16-bit dense; burst %.1f)" % pk["bf16_tflops"],
                          "flops_per_step": conv_fl.value, "conv_ms_per_step": conv_ms.value,
-                         "launches_per_step": conv_n.value, "share_of_step": conv_ms.value / step_ms_prof},
+                         "launches_per_step": conv_n.value, "share_of_step": conv_ms.value / step_ms_prof,
+                         # the single largest layer, with the DRAM traffic ncu measured for one of its launches
+                         # (profiles/r1_conv_strip2_ncu.md; algorithmic bytes = input + output activations)
+                         "largest_layer": {"layer": names[big], "kernel": "conv_strip2_kernel<7,32>" if big == 1 else None,
+                                           "ms_per_launch": ms23[big] / n23[big],
+                                           "tflops": fl23[big] / (ms23[big] * 1e-3) / 1e12,
+                                           "frac": fl23[big] / (ms23[big] * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
+                                           "traffic": 886.9e6 if big == 1 else None,
+                                           "algorithmic_bytes": 2.0 * args.batch * Hd * Wd * 32 * 2 if big == 1 else None},
+                         "layers": layers},
             "roofline_emulator": {"kernel": "emu_update_kernel<double,u8,philox>", "bound": "hbm",
                                   "achieved": upd_bytes / (upd_us * 1e-6) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                                   "frac": upd_bytes / (upd_us * 1e-6) / 1e9 / pk["hbm_gbs"], "traffic": None,

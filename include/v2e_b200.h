@@ -265,6 +265,10 @@ int v2e_slomo_set_option(V2eSlomo *h, int option, int value);
  * (2 x MACs over the unpadded channel counts) since the last read. */
 int v2e_slomo_profile(V2eSlomo *h, int enable);
 int v2e_slomo_profile_read(V2eSlomo *h, float *conv_ms, int *conv_launches, double *conv_flops, void *stream);
+/* Same, split by UNet layer (forward order of V2eUNetWeights; flow and interpolation networks summed): device
+ * time, launches and algorithmic FLOPs of each of the 23 layers since the last read; the totals are optional. */
+int v2e_slomo_profile_read_layers(V2eSlomo *h, float *ms23, int *launches23, double *flops23, float *conv_ms,
+                                  int *conv_launches, double *conv_flops, void *stream);
 /* device pointers of the last flow / interpolation network outputs, fp32 [B][H][W][8] */
 const float *v2e_slomo_flow_ptr(V2eSlomo *h);
 const float *v2e_slomo_intrp_ptr(V2eSlomo *h);

@@ -78,6 +78,9 @@ _SIGS = {
     "v2e_slomo_profile": (_i, [_vp, _i]),
     "v2e_slomo_profile_read": (_i, [_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_i),
                                     ctypes.POINTER(ctypes.c_double), _vp]),
+    "v2e_slomo_profile_read_layers": (_i, [_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_i),
+                                           ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_float),
+                                           ctypes.POINTER(_i), ctypes.POINTER(ctypes.c_double), _vp]),
     "v2e_slomo_flow_ptr": (_vp, [_vp]),
     "v2e_slomo_intrp_ptr": (_vp, [_vp]),
     "v2e_resize_create": (_i, [_i, _i, _i, _i, _i, _i, ctypes.POINTER(_vp)]),

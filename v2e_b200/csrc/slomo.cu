@@ -371,6 +371,8 @@ struct V2eSlomo {
     std::vector<cudaEvent_t> ev;
     size_t ev_used;
     double conv_flops;           // algorithmic FLOPs (2*MAC, unpadded channels) of the bracketed launches
+    std::vector<int> ev_layer;   // UNet layer index (0..22) of every bracketed launch
+    std::vector<double> ev_flops;
 };
 
 // spatial level (power of two divisor) at which layer i runs
@@ -514,7 +516,10 @@ static int conv(V2eSlomo *h, const UNet &u, int li, const __half *x1, const __ha
         cudaEventRecord(h->ev[h->ev_used + 1], st);
         h->ev_used += 2;
         const LayerSpec &l = u.L[li];
-        h->conv_flops += 2.0 * B * H * W * (double)l.cout * (l.cin1 + l.cin2) * l.k * l.k;
+        const double fl = 2.0 * B * H * W * (double)l.cout * (l.cin1 + l.cin2) * l.k * l.k;
+        h->conv_flops += fl;
+        h->ev_layer.push_back(li);
+        h->ev_flops.push_back(fl);
     }
     return rc;
 }
@@ -537,7 +542,10 @@ static int conv_up2(V2eSlomo *h, const UNet &u, int li, const __half *x_low, int
         cudaEventRecord(h->ev[h->ev_used + 1], st);
         h->ev_used += 2;
         const LayerSpec &l = u.L[li];
-        h->conv_flops += 2.0 * B * H * W * (double)l.cout * l.cin1 * 9;
+        const double fl = 2.0 * B * H * W * (double)l.cout * l.cin1 * 9;
+        h->conv_flops += fl;
+        h->ev_layer.push_back(li);
+        h->ev_flops.push_back(fl);
     }
     return rc;
 }
@@ -633,24 +641,42 @@ extern "C" int v2e_slomo_profile(V2eSlomo *h, int enable) {
     h->profile = enable ? 1 : 0;
     h->ev_used = 0;
     h->conv_flops = 0;
+    h->ev_layer.clear();
+    h->ev_flops.clear();
     return V2E_OK;
 }
 
-extern "C" int v2e_slomo_profile_read(V2eSlomo *h, float *conv_ms, int *conv_launches, double *conv_flops, void *stream) {
-    if (!h || !conv_ms || !conv_launches || !conv_flops) return v2e_set_error(V2E_E_INVALID, "null argument%s", "");
+static int profile_collect(V2eSlomo *h, float *conv_ms, int *conv_launches, double *conv_flops, float *ms23, int *n23,
+                           double *flops23, void *stream) {
     CU(cudaStreamSynchronize((cudaStream_t)stream));
     float tot = 0.f;
-    for (size_t i = 0; i + 1 < h->ev_used; i += 2) {
+    if (ms23) for (int i = 0; i < 23; i++) { ms23[i] = 0.f; n23[i] = 0; flops23[i] = 0.0; }
+    for (size_t i = 0, k = 0; i + 1 < h->ev_used; i += 2, k++) {
         float ms = 0.f;
         CU(cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]));
         tot += ms;
+        if (ms23 && k < h->ev_layer.size()) {
+            const int li = h->ev_layer[k];
+            ms23[li] += ms; n23[li] += 1; flops23[li] += h->ev_flops[k];
+        }
     }
-    *conv_ms = tot;
-    *conv_launches = (int)(h->ev_used / 2);
-    *conv_flops = h->conv_flops;
+    if (conv_ms) *conv_ms = tot;
+    if (conv_launches) *conv_launches = (int)(h->ev_used / 2);
+    if (conv_flops) *conv_flops = h->conv_flops;
     h->ev_used = 0;
     h->conv_flops = 0;
+    h->ev_layer.clear();
+    h->ev_flops.clear();
     return V2E_OK;
+}
+extern "C" int v2e_slomo_profile_read(V2eSlomo *h, float *conv_ms, int *conv_launches, double *conv_flops, void *stream) {
+    if (!h || !conv_ms || !conv_launches || !conv_flops) return v2e_set_error(V2E_E_INVALID, "null argument%s", "");
+    return profile_collect(h, conv_ms, conv_launches, conv_flops, nullptr, nullptr, nullptr, stream);
+}
+extern "C" int v2e_slomo_profile_read_layers(V2eSlomo *h, float *ms23, int *launches23, double *flops23, float *conv_ms,
+                                             int *conv_launches, double *conv_flops, void *stream) {
+    if (!h || !ms23 || !launches23 || !flops23) return v2e_set_error(V2E_E_INVALID, "null argument%s", "");
+    return profile_collect(h, conv_ms, conv_launches, conv_flops, ms23, launches23, flops23, stream);
 }
 
 extern "C" const float *v2e_slomo_flow_ptr(V2eSlomo *h) { return h ? h->flow_out : nullptr; }

@@ -104,6 +104,8 @@ STRIP_CASES = [
     # output channels split over two CTA classes (weights of a slice resident), 2-slab inputs, short items
     (1, 37, 640, 64, 0, 64, 5, 0), (1, 20, 640, 128, 0, 64, 3, 0), (2, 24, 512, 64, 64, 64, 3, 0),
     (1, 2, 512, 32, 0, 32, 7, 0), (1, 1, 640, 16, 0, 32, 3, 0),
+    # 346x260 network width (320 = 2.5 strips)
+    (2, 30, 320, 32, 0, 32, 7, 0), (1, 17, 320, 32, 32, 32, 3, 0), (1, 9, 256, 32, 0, 5, 3, 1),
 ]
 
 

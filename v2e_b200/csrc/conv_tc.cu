@@ -1183,6 +1183,16 @@ static int strip2_config(int C1, int C2, int Cout_pad, int KH, int KW, int kc, i
     return 0;
 }
 
+static int strip_min_w() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("V2E_STRIP_MIN_W");
+        v = e ? atoi(e) : 2 * kRowTile;
+        if (v < kRowTile) v = kRowTile;
+    }
+    return v;
+}
+
 static int strip_variant_forced() {
     static int v = -2;
     if (v == -2) {
@@ -1194,8 +1204,9 @@ static int strip_variant_forced() {
 
 // Slab width and ring depth for the strip kernels; returns KC (0: layer does not qualify), *nslot_out.
 int v2e_strip_pick(int C1, int C2, int Cout_pad, int KH, int KW, int W, int *nslot_out) {
-    // wide layers only: below ~4 row tiles per image row the per-tap kernel's 8x16 tiles waste less
-    if (Cout_pad > 128 || W < 4 * kRowTile || (KW != 3 && KW != 5 && KW != 7)) return 0;
+    // wide layers only: narrow rows waste part of the last 128-pixel strip (320 = 2.5 strips) and the per-tap
+    // kernel's 8x16 tiles take over. V2E_STRIP_MIN_W overrides the threshold for A/B measurements.
+    if (Cout_pad > 128 || W < strip_min_w() || (KW != 3 && KW != 5 && KW != 7)) return 0;
     const int g = C2 ? (C1 < C2 ? C1 : C2) : C1;
     const int kc = g % 64 == 0 ? 64 : (g % 32 == 0 ? 32 : 16);
     const int slabs = (C1 + C2) / kc;
@@ -1372,7 +1383,7 @@ struct V2eUpLaunch {
 
 // 64-channel slabs, Cout_pad = 32, folded weights resident: slabs * 36 tiles of 32 x 64 fp16
 int v2e_conv_up2_supported(int C, int Cout_pad, int W_out) {
-    if (C != 64 || Cout_pad != 32 || W_out % 2 || W_out < 4 * kRowTile) return 0;   // the frame kernel is written for C = 64
+    if (C != 64 || Cout_pad != 32 || W_out % 2 || W_out < 2 * strip_min_w()) return 0;   // the frame kernel is written for C = 64
     const size_t wb = (size_t)(C / 64) * 2 * 3 * kUpBlocks * Cout_pad * 64 * 2;
     const size_t slab = ((size_t)(kRowTile + 2) * 64 * 2 + 1023) & ~(size_t)1023;
     return wb + 2048 + 3 * slab <= 222 * 1024;

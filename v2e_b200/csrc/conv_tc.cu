@@ -1218,6 +1218,8 @@ int v2e_strip_pick(int C1, int C2, int Cout_pad, int KH, int KW, int W, int *nsl
         }
         if (strip_variant_forced() == 1) return 0;
     }
+    // the first strip kernel (per-tap MMAs) only pays on rows of at least four strips
+    if (W < 4 * kRowTile) return 0;
     const size_t wb = ((size_t)slabs * KH * KW * Cout_pad * kc * 2 + 1023) & ~(size_t)1023;
     const size_t slab = ((size_t)(kRowTile + KW - 1) * kc * 2 + 1023) & ~(size_t)1023;
     // two CTAs per SM (two MMA issue streams, epilogues overlap) when weights + a (KH+2)-row ring fit in

@@ -177,6 +177,12 @@ int v2e_emu_profile_read(V2eEmu *h, float *ms_sum3, int *launches3, void *stream
  * tell a kernel's duration from the cost of observing it. */
 int v2e_emu_profile_read4(V2eEmu *h, float *ms_sum4, int *launches4, void *stream);
 
+/* Average duration (microseconds) of the update kernel over K back-to-back launches on `frame_dev` and the
+ * handle's current state, between one pair of CUDA events; the launches store out of place, so each does the work
+ * of the real launch and the state is left untouched. rng_mode 1, plain pixel model only. Synchronises. */
+int v2e_emu_time_update(V2eEmu *h, const void *frame_dev, int frame_dtype, double t_frame, double t_previous,
+                        int K, float *us_per_launch, void *stream);
+
 /* State access for parity probes (emulator.py:756-764 reads them by name). which:
  * 0 lp_log_frame, 1 base_log_frame, 2 pos_thres, 3 neg_thres, 4 noise_rate_array,
  * 5 timestamp_mem, 6 cs_surround_frame, 7 scidvs_highpass (state dtype), 8 photoreceptor_noise_arr (float32),

@@ -93,6 +93,7 @@ _SIGS = {
     "v2e_emu_profile": (_i, [_vp, _i]),
     "v2e_emu_profile_read": (_i, [_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_i), _vp]),
     "v2e_emu_profile_read4": (_i, [_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_i), _vp]),
+    "v2e_emu_time_update": (_i, [_vp, _vp, _i, _d, _d, _i, ctypes.POINTER(ctypes.c_float), _vp]),
     "v2e_emu_get_state": (_i, [_vp, _i, _vp, ctypes.POINTER(_i)]),
     "v2e_emu_state_is_f64": (_i, [_vp]),
     "v2e_emu_state_ptr": (_vp, [_vp, _i]),

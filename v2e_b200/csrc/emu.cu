@@ -61,6 +61,8 @@ struct EmuDev {                         // passed by value to every kernel
     double refr_d, shot_inten_m1;       // refractory_period_s ; (SHOT_NOISE_INTEN_FACTOR-1)
     uint64_t seed;
     void *lp, *base;
+    void *lp_out, *base_out;            // where the update kernel stores lp / base: the same arrays, except while
+                                        // v2e_emu_time_update replays one frame out of place
     float *pos_thres, *neg_thres, *noise_rate, *tmem;
     double *surround;                   // CSDVS h, ping buffer (cs_cur == 0)
     double *surround2;                  // pong buffer
@@ -901,8 +903,8 @@ emu_update_kernel(EmuDev d, FrameParams p, const void *frame, const float *leak_
                 pk += m << (pols[k] ? 8 : 0);
                 nact += recs[k] != 0;
             }
-            if (!lp_done) st4((S *)d.lp, i0, lp);
-            if (f_leak) st4((S *)d.base, i0, base);
+            if (!lp_done) st4((S *)d.lp_out, i0, lp);
+            if (f_leak) st4((S *)d.base_out, i0, base);
             *(short4 *)(d.rec + i0) = make_short4(recs[0], recs[1], recs[2], recs[3]);
         }
         // per-(iteration,polarity) histogram. Iterations 0 and 1 (almost all events) are counted per thread,
@@ -1370,6 +1372,8 @@ extern "C" int v2e_emu_create(const V2eEmuCfg *cfg, V2eEmu **out) {
     } while (0)
     ALLOC(d.lp, np * h->state_elem);
     ALLOC(d.base, np * h->state_elem);
+    d.lp_out = d.lp;
+    d.base_out = d.base;
     ALLOC(d.rec, np * sizeof(int16_t));
 
     if (d.per_pixel_thres) { ALLOC(d.pos_thres, np * 4); ALLOC(d.neg_thres, np * 4); }
@@ -1887,6 +1891,54 @@ extern "C" int v2e_emu_profile_read(V2eEmu *h, float *ms_sum3, int *launches3, v
 }
 extern "C" int v2e_emu_profile_read4(V2eEmu *h, float *ms_sum4, int *launches4, void *stream) {
     return profile_read_n(h, ms_sum4, launches4, 4, stream);
+}
+
+// Average duration of the update kernel: K back-to-back launches on the given frame and the handle's CURRENT
+// state, between ONE pair of CUDA events (no per-launch bracket, whose own cost is several microseconds). The
+// launches store lp / base into scratch arrays, so every one of them does exactly the work of the real launch
+// (same loads, same stores, same event density) and the handle's state is untouched; the per-frame scratch
+// (records, active list, histograms of slot 0) is reset by the next v2e_emu_step as usual.
+extern "C" int v2e_emu_time_update(V2eEmu *h, const void *frame_dev, int dtype, double t_frame, double t_previous,
+                                   int K, float *us_per_launch, void *stream) {
+    if (!h || !frame_dev || !us_per_launch || K < 1) return fail(V2E_E_INVALID, "bad argument");
+    if (!h->first_done) return fail(V2E_E_STATE, "v2e_emu_first_frame must run first");
+    if (h->d.rng_mode != 1 || h->d.csdvs || h->d.scidvs || h->d.pr_noise)
+        return fail(V2E_E_UNSUPPORTED, "v2e_emu_time_update: device RNG, plain pixel model only");
+    cudaStream_t st = (cudaStream_t)stream;
+    EmuDev &d = h->d;
+    const size_t bytes = (size_t)d.units * kUnitPx * h->state_elem;
+    void *lp2 = nullptr, *base2 = nullptr;
+    CU(cudaMalloc(&lp2, bytes));
+    if (cudaMalloc(&base2, bytes) != cudaSuccess) { cudaFree(lp2); return fail(V2E_E_CUDA, "cudaMalloc failed"); }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    int rc = reset_slots(h, 0, 1, st);
+    d.lp_out = lp2;
+    d.base_out = base2;
+    FrameParams p = make_params(h, t_frame, t_previous, h->frame_counter, 0);
+    for (int i = 0; i < 2 && !rc; i++)          // warm-up
+        rc = d.state_f64 ? launch_update<double>(h, p, frame_dev, dtype, nullptr, nullptr, 0, 0, 0, st)
+                         : launch_update<float>(h, p, frame_dev, dtype, nullptr, nullptr, 0, 0, 0, st);
+    cudaEventRecord(e0, st);
+    for (int i = 0; i < K && !rc; i++)
+        rc = d.state_f64 ? launch_update<double>(h, p, frame_dev, dtype, nullptr, nullptr, 0, 0, 0, st)
+                         : launch_update<float>(h, p, frame_dev, dtype, nullptr, nullptr, 0, 0, 0, st);
+    cudaEventRecord(e1, st);
+    d.lp_out = d.lp;
+    d.base_out = d.base;
+    cudaError_t ce = cudaStreamSynchronize(st);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(lp2);
+    cudaFree(base2);
+    if (!rc) rc = reset_slots(h, 0, 1, st);
+    if (rc) return rc;
+    if (ce != cudaSuccess) return fail(V2E_E_CUDA, "v2e_emu_time_update: %s", cudaGetErrorString(ce));
+    *us_per_launch = ms * 1e3f / (float)K;
+    return V2E_OK;
 }
 
 extern "C" int v2e_emu_state_is_f64(V2eEmu *h) { return h ? h->d.state_f64 : 0; }

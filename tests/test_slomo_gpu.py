@@ -371,3 +371,26 @@ def test_fused_upsample_conv_matches_torch(case):
     assert (err <= 5e-3).all(), (err.max().item(), torch.nonzero(err > 5e-3)[:5].tolist())
     if Cp > Cout:
         assert (out[..., Cout:] == 0).all()
+
+
+def test_fused_average_pool_is_bit_identical_to_the_separate_kernel():
+    """The 2x2 average pools after conv2 (and down1.conv2 on wide frames) ride in the strip kernel's epilogue.
+    The mean of four fp16 values in float32 is exact whatever the order, so the network heads must not change by
+    one bit when the fusion is switched off (v2e_slomo_set_option(h, 2, 1))."""
+    from v2e_b200.slomo import SloMoEngine
+    sd_fc, sd_at = _weights(7)
+    for (W, H) in ((1280, 96), (346, 260)):
+        frames = __import__("make_golden_slomo_frames").smooth_frames(3, H, W, 5, dx=4, dy=1, up=16)
+        eng = SloMoEngine(sd_fc, sd_at, (W, H), 2, DEV)
+        fr = torch.from_numpy(frames).to(DEV)
+        outs = []
+        for off in (0, 1):
+            _lib()[0].check(eng.lib.v2e_slomo_set_option(eng._h, 2, off))
+            eng.set_pairs(fr)
+            flow = eng.flow_out().clone()
+            out = torch.empty((2, H, W), dtype=torch.uint8, device=DEV)
+            ft = torch.empty((2, eng.h, eng.w), dtype=torch.float32, device=DEV)
+            eng.interp(0.3, out, ft)
+            outs.append((flow, ft.clone(), out.clone()))
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+        eng.close()

@@ -203,6 +203,8 @@ struct StripParams {
     int nslot;
     int variant;                   // 0: per-tap MMAs (first strip kernel), 1: row-stacked (strip2)
     int acc_slots, tmem_cols;      // strip2: accumulator ring (slots of BN columns), TMEM allocation
+    void *pool_out;                // strip2 POOL variants: F.avg_pool2d(out, 2) written beside the output
+    int pool_cstride;              //   [N, H/2, W/2, pool_cstride] fp16 (model.py:71: the pool that opens a down block)
     long long *dbg;                // STRIP2_DEBUG builds: per-CTA issuer wait cycles
     int n_split, cout_pad;         // strip2: output channels split over n_split CTA classes of BN = cout_pad / n_split
                                    // (layers whose whole weight tensor does not fit in shared memory)
@@ -445,7 +447,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 constexpr int kMaxAcc = 32;
 constexpr int kStrip2Threads = 320;      // warps: 0 producer, 1 issuer, 2..9 epilogue
 
-template <int KW, int KC>
+template <int KW, int KC, bool POOL>
 __global__ void __launch_bounds__(kStrip2Threads)
 conv_strip2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                    const __grid_constant__ CUtensorMap tmB, const StripParams p) {
@@ -643,6 +645,15 @@ conv_strip2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 __half *o16 = (__half *)p.out + pix0 * p.out_cstride + co_off + col0;
                 float *o32 = (float *)p.out + pix0 * 8;
                 const size_t step16 = (size_t)p.W * p.out_cstride, step32 = (size_t)p.W * 8;
+                // POOL: 2x2 average of the stored (fp16) activations: previous row kept in registers, the
+                // horizontal neighbour is the adjacent lane; segments start on even rows (host side)
+                __half2 prev[POOL ? 16 : 1];
+                __half *pl = nullptr;
+                size_t pstep = 0;
+                if (POOL) {
+                    pl = (__half *)p.pool_out + (((size_t)n * (p.H / 2) + ya / 2) * (p.W / 2) + px / 2) * p.pool_cstride + co_off + col0;
+                    pstep = (size_t)(p.W / 2) * p.pool_cstride;
+                }
                 uint32_t g = orow, slot = g % (uint32_t)R, par = (g / (uint32_t)R) & 1u;
                 for (int y = ya; y < yb; y++) {
                     mbar_wait(&acc_full[slot], par);
@@ -654,7 +665,7 @@ conv_strip2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     tmem_ld_wait();
                     tmem_st_zero_32x32b_x16(tmem_acc);
                     if (ncol == 32) tmem_st_zero_32x32b_x16(tmem_acc + 16);
-                    if (inb) {
+                    if (inb || POOL) {
                         if (p.out_mode == 0) {
 #pragma unroll
                             for (int c0 = 0; c0 < 32; c0 += 16) {
@@ -666,12 +677,35 @@ conv_strip2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                                         const float x1 = __uint_as_float(v[c0 + 2 * j + 1]) + bias_r[c0 + 2 * j + 1];
                                         h[j] = __floats2half2_rn(fmaxf(x0, x0 * slope), fmaxf(x1, x1 * slope));
                                     }
-                                    uint4 *dst = (uint4 *)(o16 + c0);
-                                    dst[0] = *(uint4 *)&h[0];
-                                    dst[1] = *(uint4 *)&h[4];
+                                    if (inb) {
+                                        uint4 *dst = (uint4 *)(o16 + c0);
+                                        dst[0] = *(uint4 *)&h[0];
+                                        dst[1] = *(uint4 *)&h[4];
+                                    }
+                                    if (POOL) {
+                                        if (((y - ya) & 1) == 0) {
+#pragma unroll
+                                            for (int j = 0; j < 8; j++) prev[c0 / 2 + j] = h[j];
+                                        } else {
+                                            __half2 hp[8];
+#pragma unroll
+                                            for (int j = 0; j < 8; j++) {
+                                                const float2 a = __half22float2(h[j]), b = __half22float2(prev[c0 / 2 + j]);
+                                                float s0 = a.x + b.x, s1 = a.y + b.y;       // exact: fp16 values in float32
+                                                s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+                                                s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+                                                hp[j] = __floats2half2_rn(s0 * 0.25f, s1 * 0.25f);
+                                            }
+                                            if (inb && (lane & 1) == 0) {
+                                                uint4 *dst = (uint4 *)(pl + c0);
+                                                dst[0] = *(uint4 *)&hp[0];
+                                                dst[1] = *(uint4 *)&hp[4];
+                                            }
+                                        }
+                                    }
                                 }
                             }
-                        } else if (grp == 0) {
+                        } else if (grp == 0 && inb) {
                             float f[8];
 #pragma unroll
                             for (int j = 0; j < 8; j++) {
@@ -683,6 +717,7 @@ conv_strip2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                             dst[1] = make_float4(f[4], f[5], f[6], f[7]);
                         }
                     }
+                    if (POOL && ((y - ya) & 1)) pl += pstep;
                     o16 += step16;
                     o32 += step32;
                     tmem_st_wait();
@@ -1240,9 +1275,21 @@ int v2e_strip_pick(int C1, int C2, int Cout_pad, int KH, int KW, int W, int *nsl
 
 size_t v2e_strip_launch_size(void) { return sizeof(V2eStripLaunch); }
 
+// 1 when the layer's strip2 configuration has a pooled epilogue (conv_strip2_kernel<KW, KC, true>): one CTA per SM
+// (the pooled variant keeps a row of activations in registers), even image size
+int v2e_strip_pool_supported(int C1, int C2, int Cout_pad, int KH, int KW, int H, int W) {
+    if (strip_variant_forced() == 0 || (H & 1) || (W & 1) || Cout_pad < 32) return 0;
+    const int KC = v2e_strip_pick(C1, C2, Cout_pad, KH, KW, W, nullptr);
+    if (!((KW == 7 && KC == 32) || (KW == 5 && KC == 64))) return 0;
+    int ns, R, cols, cps, nsp;
+    if (!strip2_config(C1, C2, Cout_pad, KH, KW, KC, &ns, &R, &cols, &cps, &nsp)) return 0;
+    return cps == 1 && Cout_pad / nsp >= 32;
+}
+
 int v2e_strip_prepare(V2eStripLaunch *L, const void *x1, int C1, const void *x2, int C2, const void *wgt_row,
                       const float *bias, int Cout_pad, int KH, int KW, int N, int H, int W, void *out,
-                      int out_cstride, int out_mode, int co_real, float slope, int n_sms) {
+                      int out_cstride, int out_mode, int co_real, float slope, int n_sms, void *pool_out,
+                      int pool_cstride) {
     memset(L, 0, sizeof(*L));
     StripParams &p = L->p;
     int nslot = 0;
@@ -1254,6 +1301,13 @@ int v2e_strip_prepare(V2eStripLaunch *L, const void *x1, int C1, const void *x2,
     int seg_h = H;
     const int strips = p.tiles_x * N;
     while (seg_h > 4 * KH && (long)strips * ((H + seg_h - 1) / seg_h) < 6L * n_sms) seg_h = (seg_h + 1) / 2;
+    if (pool_out) {
+        if (out_mode != 0 || !v2e_strip_pool_supported(C1, C2, Cout_pad, KH, KW, H, W))
+            return v2e_set_error(V2E_E_UNSUPPORTED, "strip2: this layer has no pooled epilogue%s", "");
+        seg_h = (seg_h + 1) & ~1;                      // 2x2 windows never straddle two items
+    }
+    p.pool_out = pool_out;
+    p.pool_cstride = pool_cstride;
     p.seg_h = seg_h;
     p.n_seg = (H + seg_h - 1) / seg_h;
     p.n_items = strips * p.n_seg;
@@ -1269,6 +1323,7 @@ int v2e_strip_prepare(V2eStripLaunch *L, const void *x1, int C1, const void *x2,
             p.n_split = nsp; p.BN = Cout_pad / nsp;
         }
     }
+    if (pool_out && p.variant != 1) return v2e_set_error(V2E_E_UNSUPPORTED, "strip2: pooled epilogue needs the row-stacked kernel%s", "");
     const int slabs = (C1 + C2) / KC, taps = KH * KW;
     p.slab_bytes = (int)(((size_t)(kRowTile + KW - 1) * KC * 2 + 1023) & ~(size_t)1023);
     p.w_bytes = slabs * taps * p.BN * KC * 2;          // resident per CTA (strip2: its slice of the output channels)
@@ -1337,16 +1392,36 @@ int v2e_strip_launch(const V2eStripLaunch *L0, cudaStream_t st) {
         }                                                                                                       \
         static bool attr2_set = false;                                                                          \
         if (!attr2_set) {                                                                                       \
-            cudaFuncSetAttribute(conv_strip2_kernel<KW_, KC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); \
+            cudaFuncSetAttribute(conv_strip2_kernel<KW_, KC_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); \
             attr2_set = true;                                                                                   \
         }                                                                                                       \
+        if (L->p.variant == 1 && L->p.pool_out)                                                                 \
+            return v2e_set_error(V2E_E_UNSUPPORTED, "strip2: no pooled variant for this filter width / slab%s", ""); \
         if (L->p.variant == 1)                                                                                  \
-            conv_strip2_kernel<KW_, KC_><<<L->grid, kStrip2Threads, L->smem, st>>>(L->tmA, L->tmA2, L->tmB, L->p); \
+            conv_strip2_kernel<KW_, KC_, false><<<L->grid, kStrip2Threads, L->smem, st>>>(L->tmA, L->tmA2, L->tmB, L->p); \
         else                                                                                                    \
             conv_strip_kernel<KW_, KC_><<<L->grid, kStripThreads, L->smem, st>>>(L->tmA, L->tmA2, L->tmB, L->p);  \
         launched = true;                                                                                        \
     }
     bool launched = false;
+    // the two layers that are followed by the pool of a down block at full / half resolution (conv2, down1.conv2)
+#define STRIP_POOL_CASE(KW_, KC_)                                                                              \
+    if (L->p.variant == 1 && L->p.pool_out && L->p.KW == KW_ && L->p.KC == KC_) {                              \
+        static bool attrp_set = false;                                                                          \
+        if (!attrp_set) {                                                                                       \
+            cudaFuncSetAttribute(conv_strip2_kernel<KW_, KC_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); \
+            attrp_set = true;                                                                                   \
+        }                                                                                                       \
+        conv_strip2_kernel<KW_, KC_, true><<<L->grid, kStrip2Threads, L->smem, st>>>(L->tmA, L->tmA2, L->tmB, L->p); \
+        launched = true;                                                                                        \
+    }
+    STRIP_POOL_CASE(7, 32) STRIP_POOL_CASE(5, 64)
+#undef STRIP_POOL_CASE
+    if (launched) {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return v2e_set_error(V2E_E_CUDA, "conv_strip2_kernel launch: %s", cudaGetErrorString(e));
+        return V2E_OK;
+    }
     STRIP_CASE(3, 16) STRIP_CASE(3, 32) STRIP_CASE(3, 64)
     STRIP_CASE(5, 16) STRIP_CASE(5, 32) STRIP_CASE(5, 64)
     STRIP_CASE(7, 16) STRIP_CASE(7, 32) STRIP_CASE(7, 64)
@@ -1366,7 +1441,7 @@ extern "C" int v2e_conv2d_lrelu_sm100_strip(const void *x1_dev, int C1, const vo
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int rc = v2e_strip_prepare(&L, x1_dev, C1, x2_dev, C2, wgt_row_dev, bias_dev, Cout_pad, KH, KW, N, H, W,
-                               out_dev, out_cstride, out_mode, co_real, slope, sms);
+                               out_dev, out_cstride, out_mode, co_real, slope, sms, nullptr, 0);
     if (rc) return rc;
     return v2e_strip_launch(&L, (cudaStream_t)stream);
 }

@@ -34,9 +34,11 @@ size_t v2e_conv_launch_size(void);
 struct V2eStripLaunch;
 int v2e_strip_pick(int C1, int C2, int Cout_pad, int KH, int KW, int W, int *nslot_out);
 size_t v2e_strip_launch_size(void);
+int v2e_strip_pool_supported(int C1, int C2, int Cout_pad, int KH, int KW, int H, int W);
 int v2e_strip_prepare(V2eStripLaunch *L, const void *x1, int C1, const void *x2, int C2, const void *wgt_row,
                       const float *bias, int Cout_pad, int KH, int KW, int N, int H, int W, void *out,
-                      int out_cstride, int out_mode, int co_real, float slope, int n_sms);
+                      int out_cstride, int out_mode, int co_real, float slope, int n_sms, void *pool_out,
+                      int pool_cstride);
 int v2e_strip_launch(const V2eStripLaunch *L, cudaStream_t st);
 struct V2eUpLaunch;
 int v2e_conv_up2_supported(int C, int Cout_pad, int W_out);
@@ -365,7 +367,7 @@ struct V2eSlomo {
     float *maxspeed;              // device scalar
     int curB;
     std::vector<char> launch_mem, row_mem, up_mem;
-    int n_sms, force_tap_kernel, no_fused_up;
+    int n_sms, force_tap_kernel, no_fused_up, no_fused_pool;
     // measurement hooks: CUDA events around every conv launch
     int profile;
     std::vector<cudaEvent_t> ev;
@@ -470,6 +472,7 @@ extern "C" int v2e_slomo_create(int H, int W, int max_batch, const V2eUNetWeight
     { int dev = 0; cudaGetDevice(&dev); h->n_sms = 148; cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, dev); }
     h->force_tap_kernel = 0;
     h->no_fused_up = getenv("V2E_NO_FUSED_UP") ? 1 : 0;        // A/B measurements
+    h->no_fused_pool = getenv("V2E_NO_FUSED_POOL") ? 1 : 0;
     h->up_mem.resize(v2e_conv_up2_launch_size());
     *out = h;
     return V2E_OK;
@@ -490,15 +493,17 @@ extern "C" int v2e_slomo_destroy(V2eSlomo *h) {
     return V2E_OK;
 }
 
+// pool_out != null: the caller has checked pool_fusable(); F.avg_pool2d(out, 2) is written by the same kernel
 static int conv(V2eSlomo *h, const UNet &u, int li, const __half *x1, const __half *x2, int B, int H, int W, void *out,
-                int out_mode, cudaStream_t st) {
+                int out_mode, cudaStream_t st, __half *pool_out = nullptr) {
     int rc;
     const bool row = u.row_kc[li] != 0 && !h->force_tap_kernel;
     V2eConvLaunch *L = (V2eConvLaunch *)h->launch_mem.data();
     V2eStripLaunch *R = (V2eStripLaunch *)h->row_mem.data();
     if (row)
         rc = v2e_strip_prepare(R, x1, u.c1p[li], x2, x2 ? u.c2p[li] : 0, u.w_row[li], u.b[li], u.cout_pad[li], u.L[li].k,
-                               u.L[li].k, B, H, W, out, u.cout_pad[li], out_mode, u.L[li].cout, kSlope, h->n_sms);
+                               u.L[li].k, B, H, W, out, u.cout_pad[li], out_mode, u.L[li].cout, kSlope, h->n_sms,
+                               pool_out, u.cout_pad[li]);
     else
         rc = v2e_conv_prepare(L, x1, u.c1p[li], x2, x2 ? u.c2p[li] : 0, u.w[li], u.b[li], u.cout_pad[li], u.L[li].k,
                               u.L[li].k, B, H, W, out, u.cout_pad[li], out_mode, u.L[li].cout, kSlope);
@@ -550,20 +555,30 @@ static int conv_up2(V2eSlomo *h, const UNet &u, int li, const __half *x_low, int
     return rc;
 }
 
+// the average pool that opens a down block (model.py:71) can ride in the epilogue of the convolution before it
+static bool pool_fusable(const V2eSlomo *h, const UNet &u, int li, int H, int W) {
+    if (h->no_fused_pool || h->force_tap_kernel || !u.row_kc[li] || u.cout_pad[li] != u.L[li].cout) return false;
+    return v2e_strip_pool_supported(u.c1p[li], u.c2p[li], u.cout_pad[li], u.L[li].k, u.L[li].k, H, W) != 0;
+}
+
 // UNet.forward (model.py:198-226). in: NHWC16 fp16 [B,H,W,16]; out: fp32 [B,H,W,8]
 static int unet_forward(V2eSlomo *h, const UNet &u, const __half *in, float *out, int B, cudaStream_t st) {
     const int H = h->H, W = h->W;
     int rc;
     if ((rc = conv(h, u, 0, in, nullptr, B, H, W, h->x0, 0, st))) return rc;
-    if ((rc = conv(h, u, 1, h->x0, nullptr, B, H, W, h->s1, 0, st))) return rc;
+    bool pooled = pool_fusable(h, u, 1, H, W);           // conv2 also writes pool[0]
+    if ((rc = conv(h, u, 1, h->x0, nullptr, B, H, W, h->s1, 0, st, pooled ? h->pool[0] : nullptr))) return rc;
     const int ch[6] = {32, 64, 128, 256, 512, 512};
     const __half *prev = h->s1;
     for (int l = 0; l < 5; l++) {                       // down blocks (model.py:55-77)
         const int hi = H >> l, wi = W >> l, ho = hi / 2, wo = wi / 2;
-        const long n = (long)B * ho * wo * (ch[l] / 8);
-        avgpool2_kernel<<<cdiv(n, 256), 256, 0, st>>>(prev, h->pool[l], B, hi, wi, ch[l]);
+        if (!pooled) {
+            const long n = (long)B * ho * wo * (ch[l] / 8);
+            avgpool2_kernel<<<cdiv(n, 256), 256, 0, st>>>(prev, h->pool[l], B, hi, wi, ch[l]);
+        }
         if ((rc = conv(h, u, 2 + 2 * l, h->pool[l], nullptr, B, ho, wo, h->da[l], 0, st))) return rc;
-        if ((rc = conv(h, u, 3 + 2 * l, h->da[l], nullptr, B, ho, wo, h->s[l], 0, st))) return rc;
+        pooled = l < 4 && pool_fusable(h, u, 3 + 2 * l, ho, wo);        // this block's conv2 writes the next pool
+        if ((rc = conv(h, u, 3 + 2 * l, h->da[l], nullptr, B, ho, wo, h->s[l], 0, st, pooled ? h->pool[l + 1] : nullptr))) return rc;
         prev = h->s[l];
     }
     const int ui[5] = {512, 512, 256, 128, 64};
@@ -633,6 +648,7 @@ extern "C" int v2e_slomo_set_option(V2eSlomo *h, int option, int value) {
     if (!h) return v2e_set_error(V2E_E_INVALID, "null handle%s", "");
     if (option == 0) { h->force_tap_kernel = value; return V2E_OK; }
     if (option == 1) { h->no_fused_up = value; return V2E_OK; }
+    if (option == 2) { h->no_fused_pool = value; return V2E_OK; }
     return v2e_set_error(V2E_E_INVALID, "unknown option%s", "");
 }
 

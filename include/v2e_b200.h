@@ -30,13 +30,17 @@ typedef enum V2eStatus {
     V2E_E_CAPACITY = -3,     /* event buffer too small; state is resumable, see v2e_emu_step */
     V2E_E_ITER_CAP = -4,     /* a pixel produced more events in one frame than iter_cap */
     V2E_E_STATE = -5,        /* call order violated (e.g. step before first frame) */
-    V2E_E_UNSUPPORTED = -6
+    V2E_E_UNSUPPORTED = -6,
+    V2E_E_FALLBACK = -7      /* v2e_emu_collect after v2e_emu_fused_*: the chunk must be replayed frame by frame */
 } V2eStatus;
 
 typedef enum V2eFrameDtype { V2E_U8 = 0, V2E_F32 = 1, V2E_F64 = 2 } V2eFrameDtype;
 
 const char *v2e_last_error(void);
 int v2e_version(void);
+/* ABI guard for bindings that mirror the structs (ctypes): version and the sizes of V2eEmuCfg / V2eFrameInfo /
+ * V2eUNetWeights as this library was compiled. A binding whose own sizes differ must refuse to load. */
+int v2e_abi_info(int *version, int *emu_cfg_size, int *frame_info_size, int *unet_weights_size);
 
 /* ------------------------------------------------------------------------- */
 /* DVS pixel model: replaces EventEmulator.generate_events (emulator.py:619-1022)
@@ -67,6 +71,10 @@ typedef struct V2eEmuCfg {
     int32_t scidvs;                 /* emulator.py:114, 719-725: nonlinear CR high-pass before the change amplifier */
     int32_t photoreceptor_noise;    /* emulator.py:95, 694-703: Gaussian photoreceptor noise instead of injected
                                        shot events (needs shot_noise_rate_hz > 0 and cutoff_hz > 0, :196-204) */
+    uint32_t rng_pixel_offset;      /* rng_mode 1: index, in the WHOLE frame, of this handle's pixel 0. 0 unless the
+                                       handle owns a row band of a pixel-sharded clip (y0 * width): the Philox counters
+                                       use whole-frame pixel indices, so the bands draw what one GPU would draw */
+    uint32_t reserved0;
 } V2eEmuCfg;
 
 typedef struct V2eEmu V2eEmu;
@@ -128,6 +136,33 @@ int v2e_emu_step(V2eEmu *h, const void *frames_dev, int frame_dtype, int T,
                  const float *leak_randn_dev, const float *shot_rand_dev,
                  float *events_out_dev, uint64_t capacity, uint64_t ev_base_start,
                  int first, int resume_emit, void *stream);
+
+/* Multi-frame fast path. v2e_emu_step takes it by itself when it can (T >= 2, uint8 frames, plain pixel model --
+ * no hdr / csdvs / scidvs / photoreceptor noise --, rng_mode 1 or no per-frame noise): per-pixel state stays in
+ * registers across the T frames, per-frame work is one byte read per pixel plus a 16-bit record per active pixel;
+ * rows, counters and state are identical to the frame-by-frame kernels'. It relies on the refractory filter not
+ * running (refractory_period_s <= dt / max_n in every frame, emulator.py:830) and on max_n <= 31; a chunk that
+ * breaks this is rejected on the device (nothing emitted, state untouched) and v2e_emu_collect replays it frame by
+ * frame before it returns. option 0 of v2e_emu_set_option: 0 = never take the fast path (A/B tests), 1 = default. */
+int v2e_emu_set_option(V2eEmu *h, int option, int value);
+/* The fast path in two halves for a pixel-sharded clip: v2e_emu_fused_count enqueues the register-
+ * resident update of the T frames and the per-frame counts; the caller all-reduces (MAX) the T int32 at
+ * v2e_emu_max_vec_dev() over the ranks on the same stream; v2e_emu_fused_emit plans with the reduced maxima, emits and
+ * commits the state. v2e_emu_collect then returns V2E_E_FALLBACK if the chunk was rejected (identically on every
+ * rank: the decision uses only the reduced maxima and the frame times) and the caller replays it frame by frame
+ * (v2e_emu_phase_*). V2E_E_UNSUPPORTED when the configuration does not qualify. */
+int v2e_emu_fused_count(V2eEmu *h, const void *frames_dev, int frame_dtype, int T, const double *t_frames_host,
+                        double t_previous, void *stream);
+int32_t *v2e_emu_max_vec_dev(V2eEmu *h);
+int v2e_emu_fused_emit(V2eEmu *h, float *events_out_dev, uint64_t capacity, uint64_t ev_base_start, void *stream);
+/* counters: chunks that went through the fast path / chunks it rejected */
+int v2e_emu_fused_stats(V2eEmu *h, long long *chunks, long long *rejected);
+/* Measurement: K repetitions of the fast path of one chunk (update, count, plan, emit; no commit, so the state is
+ * left untouched and every repetition does the same work) between one CUDA-event pair, and K repetitions of the
+ * update kernel alone between another. Returns microseconds per chunk. Synchronises. */
+int v2e_emu_time_fused(V2eEmu *h, const void *frames_dev, int frame_dtype, int T, const double *t_frames_host,
+                       double t_previous, float *events_out_dev, uint64_t capacity, int K, float *us_chunk,
+                       float *us_update, void *stream);
 
 /* Copies the per-frame control blocks of the last step to the host. Synchronises `stream`.
  * info_host[T]. *frames_done = number of frames fully emitted. Returns V2E_OK,

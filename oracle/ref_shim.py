@@ -1,7 +1,8 @@
 """TEST INFRASTRUCTURE ONLY — loader for the *unmodified* reference (SensorsINI/v2e).
 
-Only usable where /root/reference exists (the build container, not the GPU box).
-It injects empty stand-ins for GUI / file-format modules that the reference
+Loads the reference from /root/reference (the build container) or, where that does not exist (the
+GPU box), from the verbatim copy oracle/make_ref.py vendored into oracle/_ref/ (git-ignored, travels with
+the snapshot). It injects empty stand-ins for GUI / file-format modules that the reference
 imports at module top level but that the hot path never calls
 (reference: v2ecore/emulator.py:14,17; v2ecore/output/aedat4_output.py:10;
 v2ecore/v2e_utils.py:9-12), then imports the reference packages untouched.
@@ -12,11 +13,26 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("V2E_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _pick_root():
+    for r in (os.environ.get("V2E_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "_ref")):
+        if r and os.path.isfile(os.path.join(r, "v2ecore", "emulator.py")):
+            return r
+    return os.environ.get("V2E_REFERENCE_ROOT", "/root/reference")
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def reference_available() -> bool:
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "v2ecore", "emulator.py"))
+
+
+def reference_kind() -> str:
+    """'_ref' when the vendored verbatim copy is in use, 'reference' for /root/reference itself."""
+    return "_ref" if os.path.abspath(REFERENCE_ROOT) == os.path.join(_HERE, "_ref") else "reference"
 
 
 def _stub(name, **attrs):

@@ -337,3 +337,193 @@ def test_pixel_sharded_two_ranks_match_oracle(kw):
         parts = [res[r][0][i] for r in (0, 1) if res[r][0][i] is not None]
         got = np.concatenate(parts) if parts else None
         assert_events_equal(got, want[i], exact_order=False, ctx="frame %d" % i)
+
+
+# ---------------------------------------------------------------------------------------------------
+# multi-frame (fused) path: per-pixel state in registers across the frames of a chunk
+# ---------------------------------------------------------------------------------------------------
+def _fused_stats(em):
+    import ctypes
+    a, b = ctypes.c_longlong(0), ctypes.c_longlong(0)
+    em._lib.v2e_emu_fused_stats(em._h, ctypes.byref(a), ctypes.byref(b))
+    return a.value, b.value
+
+
+FUSED_CONFIGS = [
+    # v2e's CLI defaults (v2e_args.py:150-204): float64 state, leak + shot noise, refractory 0.5 ms (never active here)
+    (dict(cutoff_hz=300, leak_rate_hz=0.01, shot_noise_rate_hz=0.001, refractory_period_s=0.0005), 1e-3, False),
+    # the 'noisy' preset (emulator.py:525-535): dense shot noise
+    (dict(cutoff_hz=30, leak_rate_hz=0.1, shot_noise_rate_hz=5.0, sigma_thres=0.05), 2e-3, False),
+    # float32 state (no low-pass), scalar thresholds, leak only
+    (dict(sigma_thres=0.0, cutoff_hz=0, leak_rate_hz=0.3, shot_noise_rate_hz=0), 1e-3, False),
+    # class defaults
+    (dict(), 1e-3, False),
+    # the refractory filter runs in some frames (low thresholds, 4 ms): those chunks must be rejected and replayed
+    (dict(cutoff_hz=200, leak_rate_hz=0.1, refractory_period_s=0.004, pos_thres=0.05, neg_thres=0.05,
+          sigma_thres=0.01, shot_noise_rate_hz=2), 1e-2, True),
+]
+
+
+@pytest.mark.parametrize("ci", range(len(FUSED_CONFIGS)))
+@pytest.mark.parametrize("shape", [(37, 53), (13, 37), (260, 346)])
+def test_fused_multi_frame_path_equals_frame_by_frame_kernels(ci, shape):
+    """Same seed (Philox counters are (whole-frame pixel, frame index)): the multi-frame kernels and the
+    frame-by-frame kernels must give the same rows per frame, counters and state, bit for bit, with every
+    noise source on; rows inside one (frame, iteration, polarity) group are unordered on both sides."""
+    kw, dt, expect_reject = FUSED_CONFIGS[ci]
+    H, W = shape
+    T = 23
+    fr = texture_frames(H, W, T, seed=40 + ci, speed=3.0 if expect_reject else 1.0)
+    ts = [k * dt for k in range(T)]
+    a = _emulator(seed=11, rng_mode="device", max_frames_per_step=9, fused=True, **kw)
+    b = _emulator(seed=11, rng_mode="device", max_frames_per_step=9, fused=False, **kw)
+    ra, oa = a.generate_events_batch(fr, ts)
+    rb, ob = b.generate_events_batch(fr, ts)
+    assert np.array_equal(oa, ob)
+    for i in range(T):
+        assert_events_equal(ra[oa[i]:oa[i + 1]], rb[ob[i]:ob[i + 1]], exact_order=False, ctx="frame %d" % i)
+    assert (a.num_events_total, a.num_events_on, a.num_events_off) == (b.num_events_total, b.num_events_on, b.num_events_off)
+    assert a.num_events_total > 0
+    assert torch.equal(a.base_log_frame, b.base_log_frame) and torch.equal(a.lp_log_frame, b.lp_log_frame)
+    if kw.get("refractory_period_s", 0) > 0:
+        assert torch.equal(a.timestamp_mem, b.timestamp_mem)
+    chunks, rejected = _fused_stats(a)
+    assert chunks >= 2 and _fused_stats(b) == (0, 0)
+    assert (rejected > 0) == expect_reject, (chunks, rejected)
+
+
+def test_fused_path_grows_the_event_buffer_without_loss():
+    kw = dict(cutoff_hz=300, leak_rate_hz=0.01, shot_noise_rate_hz=0.001, refractory_period_s=0.0005)
+    H, W, T = 64, 96, 17
+    fr = texture_frames(H, W, T, seed=3, speed=2.0)
+    ts = [k * 2e-3 for k in range(T)]
+    a = _emulator(seed=2, rng_mode="device", max_frames_per_step=8, **kw)
+    b = _emulator(seed=2, rng_mode="device", max_frames_per_step=8, **kw)
+    b.event_rows_hint = 64
+    ra, oa = a.generate_events_batch(fr, ts)
+    rb, ob = b.generate_events_batch(fr, ts)
+    assert np.array_equal(oa, ob) and len(ra) > 64
+    for i in range(T):
+        assert_events_equal(ra[oa[i]:oa[i + 1]], rb[ob[i]:ob[i + 1]], exact_order=False, ctx="frame %d" % i)
+    assert torch.equal(a.base_log_frame, b.base_log_frame)
+
+
+def test_full_size_replay_mode_bit_exact_1280x720():
+    """The headline frame size with v2e's CLI defaults in the bit-exact mode (rng_mode='replay': torch's CPU
+    generator replayed like the reference does): rows INCLUDING ORDER, counters and per-pixel state equal to
+    the scalar C oracle (itself pinned to the unmodified reference's output, tests/test_oracle_golden.py)."""
+    from emu_oracle import OracleEmulator
+    H, W, T = 720, 1280, 7
+    kw = dict(cutoff_hz=300, leak_rate_hz=0.01, shot_noise_rate_hz=0.001, refractory_period_s=0.0005)
+    fr = texture_frames(H, W, T, seed=12, speed=2.0, block=8)
+    ts = [k / 300.0 for k in range(T)]
+    orc = OracleEmulator(seed=77, **kw)
+    want = [orc.generate_events(f, t) for f, t in zip(fr, ts)]
+    em = _emulator(seed=77, **kw)
+    n = 0
+    for i, (f, t) in enumerate(zip(fr, ts)):
+        got = em.generate_events(f, t)
+        assert_events_equal(got, want[i], exact_order=True, ctx="frame %d" % i)
+        n += 0 if got is None else len(got)
+    assert n > 100000
+    assert (em.num_events_total, em.num_events_on, em.num_events_off) == \
+        (orc.num_events_total, orc.num_events_on, orc.num_events_off)
+    assert np.array_equal(em.base_log_frame.cpu().numpy(), orc.base)
+    assert np.array_equal(em.lp_log_frame.cpu().numpy(), orc.lp)
+
+
+@pytest.mark.parametrize("scene", ["bands", "texture"])
+def test_device_rng_rates_per_polarity_and_intensity(scene):
+    """rng_mode='device' draws from Philox, not from torch's generator, so with leak / shot noise on only the
+    STATISTICS can agree with the reference. Static scenes (test/leak_event_test.py recipe), four intensity
+    bins x two polarities: every bin's event count must agree with the oracle's (torch draws) within 5 sigma of
+    the two-sample Poisson error -- no percentage slack. The shot rate depends on intensity
+    (emulator_utils.py:323-324) and the leak only makes ON events, so a wrong branch shows up in a bin."""
+    from emu_oracle import OracleEmulator
+    H, W, T = 128, 160, 80
+    kw = dict(cutoff_hz=200, leak_rate_hz=0.2, shot_noise_rate_hz=10)
+    levels = np.array([8, 60, 130, 245], np.uint8)
+    if scene == "bands":
+        img = np.repeat(levels[None, :], H, 0).repeat(W // 4, 1)
+    else:
+        rng = np.random.default_rng(9)
+        img = levels[rng.integers(0, 4, (H // 4, W // 4))].repeat(4, 0).repeat(4, 1)
+    ts = [k * 5e-3 for k in range(T)]
+    orc = OracleEmulator(seed=5, **kw)
+    ref_rows = [orc.generate_events(img, t) for t in ts]
+    ref = np.concatenate([r for r in ref_rows if r is not None])
+    em = _emulator(seed=5, rng_mode="device", **kw)
+    dev, _ = em.generate_events_batch(np.repeat(img[None], T, 0), ts)
+
+    def table(ev):
+        lv = img[ev[:, 2].astype(int), ev[:, 1].astype(int)]
+        return np.array([[np.sum((lv == L) & (ev[:, 3] == p)) for p in (1, -1)] for L in levels], np.int64)
+    a, b = table(ref), table(dev)
+    assert a.sum() > 20000 and a.min() > 200, a
+    z = np.abs(a - b) / np.sqrt(np.maximum(a + b, 1))
+    assert z.max() < 5.0, (a, b, z)
+    # and the two runs are not the same draws
+    assert len(ref) != len(dev) or not np.array_equal(canonical(ref), canonical(dev))
+
+
+def _sharded_batch_worker(rank, world, port, kw, frames, ts, q):
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from v2e_b200 import EventEmulator
+        from v2e_b200.parallel import row_band
+        em = EventEmulator(device="cuda:0", seed=21, rng_mode="device", shard=(rank, world, None),
+                           max_frames_per_step=6, **kw)
+        H = frames.shape[1]
+        y0, y1 = row_band(H, rank, world)
+        rows, offs = em.generate_events_band_batch(np.ascontiguousarray(frames[:, y0:y1]), ts, H)
+        q.put((rank, rows, offs, em.num_events_total, _fused_stats(em)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case", [
+    # device RNG with leak + shot noise: the bands must draw what one GPU draws (Philox counters use whole-frame
+    # pixel indices); H = 50 rows, W = 64: band offsets are multiples of 4
+    (dict(cutoff_hz=300, leak_rate_hz=0.1, shot_noise_rate_hz=2.0, refractory_period_s=0.0005), (50, 64), False),
+    # odd width: a band starts in the middle of a Philox quad
+    (dict(cutoff_hz=100, leak_rate_hz=0.1, shot_noise_rate_hz=5.0), (37, 53), False),
+    # refractory filter active: chunks rejected on every rank, replayed frame by frame
+    (dict(cutoff_hz=200, leak_rate_hz=0.1, refractory_period_s=0.004, pos_thres=0.05, neg_thres=0.05,
+          sigma_thres=0.01, shot_noise_rate_hz=2), (50, 64), True),
+])
+def test_pixel_sharded_batched_equals_single_gpu_device_rng(case):
+    """One clip, rows split over 2 ranks, batched (one all-reduce(MAX) of the frame maxima per chunk): the union
+    of the two ranks' rows equals the unsharded device-RNG run with the same seed, per frame (the
+    Philox counter must not restart in every band)."""
+    import socket
+    import torch.multiprocessing as mp
+    kw, (H, W), expect_reject = case
+    T = 14
+    fr = texture_frames(H, W, T, seed=3, speed=3.0 if expect_reject else 1.0)
+    ts = [k * (1e-2 if expect_reject else 2e-3) for k in range(T)]
+    one = _emulator(seed=21, rng_mode="device", max_frames_per_step=6, **kw)
+    want, woffs = one.generate_events_batch(fr, ts)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sharded_batch_worker, args=(r, 2, port, kw, fr, ts, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict()
+    for _ in range(2):
+        r, rows, offs, n, st = q.get(timeout=300)
+        res[r] = (rows, offs, n, st)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][2] + res[1][2] == one.num_events_total > 0
+    for i in range(T):
+        got = np.concatenate([res[r][0][res[r][1][i]:res[r][1][i + 1]] for r in (0, 1)])
+        assert_events_equal(got, want[woffs[i]:woffs[i + 1]], exact_order=False, ctx="frame %d" % i)
+    for r in (0, 1):
+        chunks, rejected = res[r][3]
+        assert chunks >= 2 and (rejected > 0) == expect_reject

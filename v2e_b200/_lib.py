@@ -20,6 +20,7 @@ class V2eEmuCfg(ctypes.Structure):
         ("csdvs", ctypes.c_int32), ("max_frames_per_step", ctypes.c_int32),
         ("cs_tau_p_s", ctypes.c_double), ("cs_tau_h_s", ctypes.c_double),
         ("scidvs", ctypes.c_int32), ("photoreceptor_noise", ctypes.c_int32),
+        ("rng_pixel_offset", ctypes.c_uint32), ("reserved0", ctypes.c_uint32),
     ]
 
 
@@ -37,8 +38,9 @@ class V2eFrameInfo(ctypes.Structure):
     ]
 
 
-V2E_OK, V2E_E_INVALID, V2E_E_CUDA, V2E_E_CAPACITY, V2E_E_ITER_CAP, V2E_E_STATE, V2E_E_UNSUPPORTED = \
-    0, -1, -2, -3, -4, -5, -6
+V2E_OK, V2E_E_INVALID, V2E_E_CUDA, V2E_E_CAPACITY, V2E_E_ITER_CAP, V2E_E_STATE, V2E_E_UNSUPPORTED, V2E_E_FALLBACK = \
+    0, -1, -2, -3, -4, -5, -6, -7
+ABI_VERSION = 200
 U8, F32, F64 = 0, 1, 2
 
 _vp, _i, _d, _u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_uint64
@@ -46,6 +48,14 @@ _vp, _i, _d, _u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_uin
 _SIGS = {
     "v2e_last_error": (ctypes.c_char_p, []),
     "v2e_version": (_i, []),
+    "v2e_abi_info": (_i, [ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i)]),
+    "v2e_emu_set_option": (_i, [_vp, _i, _i]),
+    "v2e_emu_fused_count": (_i, [_vp, _vp, _i, _i, _vp, _d, _vp]),
+    "v2e_emu_max_vec_dev": (_vp, [_vp]),
+    "v2e_emu_fused_emit": (_i, [_vp, _vp, _u64, _u64, _vp]),
+    "v2e_emu_fused_stats": (_i, [_vp, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong)]),
+    "v2e_emu_time_fused": (_i, [_vp, _vp, _i, _i, _vp, _d, _vp, _u64, _i, ctypes.POINTER(ctypes.c_float),
+                                ctypes.POINTER(ctypes.c_float), _vp]),
     "v2e_emu_create": (_i, [ctypes.POINTER(V2eEmuCfg), ctypes.POINTER(_vp)]),
     "v2e_emu_destroy": (_i, [_vp]),
     "v2e_emu_set_linlog_lut": (_i, [_vp, _vp, _vp]),
@@ -113,18 +123,30 @@ def load(build_if_missing=True):
     if build_if_missing and os.environ.get("V2E_B200_NO_BUILD") != "1":
         try:
             _build.build()
-        except Exception as e:  # stale-but-present library is still usable; a missing one is fatal
+        except Exception as e:  # a present library may still be current (checked below); a missing one is fatal
             if not os.path.exists(path):
                 raise RuntimeError("v2e_b200: the CUDA library is not built and nvcc failed: %s" % e)
+            import warnings
+            warnings.warn("v2e_b200: rebuilding %s failed (%s); using the existing library if its ABI matches"
+                          % (path, e))
     if not os.path.exists(path):
         raise RuntimeError("v2e_b200: %s is missing -- run `python -m v2e_b200.build`; "
                            "there is no CPU fallback" % path)
     lib = ctypes.CDLL(path)
+    missing = [name for name in _SIGS if not hasattr(lib, name)]
+    if missing:
+        raise RuntimeError("v2e_b200: %s is stale (missing %s) -- rebuild with `python -m v2e_b200.build --force`"
+                           % (path, ", ".join(missing[:6])))
     for name, (res, args) in _SIGS.items():
-        if not hasattr(lib, name):
-            continue  # symbols of units that are not built yet are checked by tests/test_abi.py
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
+    # the ctypes structs above must be the layouts the library was compiled with
+    ver, a, b, c = _i(0), _i(0), _i(0), _i(0)
+    lib.v2e_abi_info(ctypes.byref(ver), ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+    want = (ABI_VERSION, ctypes.sizeof(V2eEmuCfg), ctypes.sizeof(V2eFrameInfo), ctypes.sizeof(V2eUNetWeights))
+    if (ver.value, a.value, b.value, c.value) != want:
+        raise RuntimeError("v2e_b200: %s has ABI %s, this binding expects %s -- rebuild with "
+                           "`python -m v2e_b200.build --force`" % (path, (ver.value, a.value, b.value, c.value), want))
     _LIB = lib
     return lib
 

@@ -75,7 +75,9 @@ struct EmuDev {                         // passed by value to every kernel
     int32_t n_blocks;                   // blocks of the update kernel = list segments of seg_px pixels
     int32_t seg_px, upb;                // block b owns the 128-pixel units [b*units/n_blocks, (b+1)*units/n_blocks): upb or
                                         // upb-1 of them; seg_px = upb * 128 = capacity of a list segment
-    int32_t units, pad1;                // ceil(n / 128)
+    int32_t units;                      // ceil(n / 128)
+    uint32_t px_off;                    // global index of this handle's pixel 0 (row band of a pixel-sharded clip):
+                                        // Philox counters use global pixel indices
     // optional pixel models (emulator.py:58-80, 694-703, 719-725)
     int32_t scidvs, pr_noise;
     void *hp, *prev_photo;              // scidvs_highpass / scidvs_previous_photo, state dtype
@@ -95,6 +97,7 @@ struct FrameParams {
     double shot_c;                      // (shot_noise_rate_hz/2)*delta_time (emulator_utils.py:323-324)
     double shot_bound;                  // >= every pixel's ON/OFF shot probability of this frame (x >= 0)
     float shot_lo_f, shot_hi_f;         // float32 fast reject: a draw r with shot_lo_f <= r <= shot_hi_f cannot fire
+    uint32_t pref_lo;                   // device RNG: a 12-bit prefix p with pref_lo <= p < 4096 - pref_lo cannot fire
     float pr_vrms_f, pr_ome_f, pr_eps_f;// photoreceptor noise: float32(vrms), float32(1-dt/tau), float32(dt/tau)
     int32_t scidvs_first;               // the frame that creates scidvs_highpass (zeros) and scidvs_previous_photo
     uint64_t capacity;
@@ -185,6 +188,64 @@ __device__ __forceinline__ float sqrt_approx(float x) {
     return y;
 }
 
+// Per-frame noise of one aligned quad of pixels (GLOBAL pixel indices 4q .. 4q+3 of the whole frame, so that a
+// pixel-sharded run draws what the unsharded run draws) from ONE Philox call:
+//   n[j]    : N(0,1) for the leak jitter (emulator_utils.py:122-124). Box-Muller on fast intrinsics: radius from 24
+//             bits, angle from 16 bits -- this stream only has to be normal, not torch's bits;
+//   pref[j] : 12 uniform bits per pixel from the bits Box-Muller leaves over: the top of the pixel's shot-noise
+//             uniform (emulator_utils.py:340-343). Only a pixel whose prefix lies within pref_lo of either end can
+//             fire; it then takes its low bits from a second call (shot_uniform) -- a few pixels per thousand.
+__device__ __forceinline__ void noise_quad(uint64_t seed, uint32_t quad, uint32_t frame_index, float n[4],
+                                           uint32_t pref[4]) {
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    const uint4 r = philox4x32<kPhiloxRounds>(make_uint4(quad, frame_index, 0u, 0x6c65616bu), key);
+    const float a = sqrt_approx(-2.0f * __logf(u01_open(r.x))), b = sqrt_approx(-2.0f * __logf(u01_open(r.z)));
+    float sa, ca, sb, cb;
+    __sincosf(6.283185307179586f * ((float)(r.y >> 16) * (1.0f / 65536.0f)), &sa, &ca);
+    __sincosf(6.283185307179586f * ((float)(r.w >> 16) * (1.0f / 65536.0f)), &sb, &cb);
+    n[0] = a * ca; n[1] = a * sa; n[2] = b * cb; n[3] = b * sb;
+    pref[0] = (r.x & 0xffu) | ((r.y & 0xfu) << 8);
+    pref[1] = (r.y >> 4) & 0xfffu;
+    pref[2] = (r.z & 0xffu) | ((r.w & 0xfu) << 8);
+    pref[3] = (r.w >> 4) & 0xfffu;
+}
+// The shot-noise uniform of pixel j of the quad, in [0,1): 12-bit prefix, then 20 bits of a second Philox call,
+// truncated to float32 (never rounds up to 1).
+__device__ __forceinline__ float shot_uniform(uint64_t seed, uint32_t quad, uint32_t frame_index, int j, uint32_t pref) {
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    const uint4 r = philox4x32<kPhiloxRounds>(make_uint4(quad, frame_index, 1u, 0x73686f74u), key);
+    const uint32_t w = j == 0 ? r.x : (j == 1 ? r.y : (j == 2 ? r.z : r.w));
+    return __uint2float_rz((pref << 20) | (w >> 12)) * (1.0f / 4294967296.0f);
+}
+__device__ __forceinline__ bool shot_candidate(uint32_t pref, uint32_t pref_lo) {
+    return pref < pref_lo || pref >= 4096u - pref_lo;
+}
+// noise of the 4 consecutive pixels starting at GLOBAL index g0: one call when g0 is quad-aligned (always, unless a
+// row band of a sharded clip starts at an odd offset), two otherwise
+__device__ __forceinline__ void noise_px4(uint64_t seed, uint32_t g0, uint32_t frame_index, float n[4], uint32_t pref[4]) {
+    const uint32_t q = g0 >> 2, r = g0 & 3u;
+    if (r == 0) {
+        noise_quad(seed, q, frame_index, n, pref);
+        return;
+    }
+    float na[4], nb[4];
+    uint32_t pa[4], pb[4];
+    noise_quad(seed, q, frame_index, na, pa);
+    noise_quad(seed, q + 1, frame_index, nb, pb);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t j = r + (uint32_t)k;
+        float nv = 0.f;
+        uint32_t pv = 0u;
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+            if ((j & 3u) == (uint32_t)m) { nv = j < 4u ? na[m] : nb[m]; pv = j < 4u ? pa[m] : pb[m]; }
+        }
+        n[k] = nv;
+        pref[k] = pv;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // vector load helpers: 4 consecutive elements starting at i (i % 4 == 0)
 // ---------------------------------------------------------------------------------------------
@@ -240,10 +301,10 @@ __device__ __forceinline__ void st4(double *p, int i, const double v[4]) {
 }
 
 // shot-noise flags of one pixel (emulator_utils.py:323-349): bit0 ON, bit1 OFF
-__device__ __forceinline__ int shot_flags(const EmuDev &d, const FrameParams &p, double x, float rnd,
+__device__ __forceinline__ int shot_flags(const EmuDev &d, double shot_c, double x, float rnd,
                                           float thp, float thn) {
     double inten01 = (x + 20.0) / 275.0;
-    double factor = p.shot_c * (d.shot_inten_m1 * inten01 + 1.0);
+    double factor = shot_c * (d.shot_inten_m1 * inten01 + 1.0);
     double pre_on, pre_off;
     if (d.per_pixel_thres) {
         pre_on = (double)((float)d.pos_nom / thp);       // emulator.py:475-478, float32 tensor
@@ -767,6 +828,7 @@ emu_update_kernel(EmuDev d, FrameParams p, const void *frame, const float *leak_
         const bool t_on = i0 < d.n;
         const unsigned char *st = my_stage + (size_t)(j % kStages) * StageLayout<S>::bytes;
         int mags[4] = {0, 0, 0, 0}, pols[4] = {0, 0, 0, 0}, flg[4] = {0, 0, 0, 0};
+        bool cand[4] = {false, false, false, false};
         short recs[4] = {0, 0, 0, 0};
         // direct (unstaged) inputs first: their latency overlaps the wait for the stage
         double x[4] = {0.0, 0.0, 0.0, 0.0};
@@ -780,22 +842,9 @@ emu_update_kernel(EmuDev d, FrameParams p, const void *frame, const float *leak_
             if (RNG == 0 && f_leak) load_f32x4_any(leak_randn, i0, d.n, lr);
             if (RNG == 0 && shot_here) load_f32x4_any(shot_rand, i0, d.n, sr);
         }
-        if (RNG == 1) {
-            const uint2 key = make_uint2((uint32_t)d.seed, (uint32_t)(d.seed >> 32));
-            if (f_leak) {
-                // Box-Muller on fast intrinsics: this stream only has to be N(0,1), not torch's bits
-                uint4 r = philox4x32<kPhiloxRounds>(make_uint4((uint32_t)(i0 >> 2), p.frame_index, 0u, 0x6c65616bu), key);
-                float a = sqrt_approx(-2.0f * __logf(u01_open(r.x))), b = sqrt_approx(-2.0f * __logf(u01_open(r.z)));
-                float sa, ca, sb, cb;
-                __sincosf(6.283185307179586f * u01_half(r.y), &sa, &ca);
-                __sincosf(6.283185307179586f * u01_half(r.w), &sb, &cb);
-                lr[0] = a * ca; lr[1] = a * sa; lr[2] = b * cb; lr[3] = b * sb;
-            }
-            if (f_shot) {
-                uint4 r = philox4x32<kPhiloxRounds>(make_uint4((uint32_t)(i0 >> 2), p.frame_index, 1u, 0x73686f74u), key);
-                sr[0] = u01_half(r.x); sr[1] = u01_half(r.y); sr[2] = u01_half(r.z); sr[3] = u01_half(r.w);
-            }
-        }
+        uint32_t pref[4] = {0u, 0u, 0u, 0u};
+        const uint32_t g0 = (uint32_t)i0 + d.px_off;       // global pixel index (Philox counter)
+        if (RNG == 1 && (f_leak || f_shot)) noise_px4(d.seed, g0, p.frame_index, lr, pref);
         // staged state -> registers
         S lp[4], base[4];
         float thp[4], thn[4], nr[4];
@@ -867,11 +916,14 @@ emu_update_kernel(EmuDev d, FrameParams p, const void *frame, const float *leak_
                     if (mag > kRecMaxCount) mag = kRecMaxCount;
                     deep = 1;
                 }
-                // shot noise: the exact test (below) only when the draw can possibly cross. shot_lo_f /
-                // shot_hi_f are float32 bounds rounded outwards from shot_bound >= any per-pixel probability
+                // shot noise: the exact test (below) only when the draw can possibly cross. Replay: shot_lo_f /
+                // shot_hi_f are float32 bounds rounded outwards from shot_bound >= any per-pixel probability;
+                // device RNG: the 12-bit prefix of the uniform decides (shot_candidate)
                 if (shot_here) {
-                    const float r = sr[k];
-                    shot_maybe |= (FT != V2E_U8 && !(xv >= 0.0 && xv <= 255.0)) || r < p.shot_lo_f || r > p.shot_hi_f;
+                    const bool wild = FT != V2E_U8 && !(xv >= 0.0 && xv <= 255.0);
+                    if (RNG == 1) cand[k] = wild || shot_candidate(pref[k], p.pref_lo);
+                    else cand[k] = wild || sr[k] < p.shot_lo_f || sr[k] > p.shot_hi_f;
+                    shot_maybe |= cand[k];
                 }
                 recs[k] = (short)((neg ? -mag : mag) << kRecShift);
                 mags[k] = mag;
@@ -886,10 +938,10 @@ emu_update_kernel(EmuDev d, FrameParams p, const void *frame, const float *leak_
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     const double xv = (FT == V2E_U8) ? (double)((codes >> (8 * k)) & 0xffu) : x[k];
-                    const float r = sr[k];
-                    if ((i0 + k) < d.n &&
-                        ((FT != V2E_U8 && !(xv >= 0.0 && xv <= 255.0)) || r < p.shot_lo_f || r > p.shot_hi_f)) {
-                        const int flags = shot_flags(d, p, xv, r, thp[k], thn[k]);
+                    if ((i0 + k) < d.n && cand[k]) {
+                        const float r = RNG == 1 ? shot_uniform(d.seed, (g0 + k) >> 2, p.frame_index, (int)((g0 + k) & 3u), pref[k])
+                                                 : sr[k];
+                        const int flags = shot_flags(d, p.shot_c, xv, r, thp[k], thn[k]);
                         flg[k] = flags;
                         recs[k] = (short)(recs[k] | flags);
                     }
@@ -1076,7 +1128,7 @@ emu_shot_kernel(EmuDev d, FrameParams p, const void *frame, const float *shot_ra
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             if (i0 + k >= d.n) continue;
-            int flags = shot_flags(d, p, x[k], sr[k], thp[k], thn[k]);
+            int flags = shot_flags(d, p.shot_c, x[k], sr[k], thp[k], thn[k]);
             if (flags) {
                 const short old = d.rec[i0 + k];
                 if (old == 0) {
@@ -1217,6 +1269,390 @@ emu_emit_kernel(EmuDev d, FrameParams p, int slot, float4 *events) {
     }
 }
 
+
+// =============================================================================================
+// Fused multi-frame path (v2e_emu_step with T >= 2 frames, uint8 frames, plain pixel model, device RNG or no
+// per-frame noise).
+//
+// The only frame-global quantity of the model is max_num_events_any_pixel (emulator.py:773-775): it sets the
+// timestamps of the frame and decides whether the refractory filter runs at all (refractory_period_s > dt / max_n,
+// emulator.py:830). Whenever the filter does NOT run, everything a pixel does is local: its event count is
+// floor(|lp - base| / theta), its base moves by count * theta, timestamp_mem is not touched. So:
+//   pass 1 (emu_fused_update_kernel): a thread keeps lp / base / thresholds / noise rate of its 4 pixels in
+//           REGISTERS across all T frames, reads one byte per pixel and frame (prefetched 4 frames ahead), and
+//           appends a 16-bit record (pixel, polarity, count, shot flags) per active pixel and frame to the list
+//           segment of its (frame, 128-pixel unit). New state goes to alternate arrays.
+//   pass 2 (emu_fused_count_kernel): walks the (sparse) records: per-frame (iteration, polarity) histogram and
+//           frame maximum.
+//   plan   (emu_fused_plan_kernel): per frame, checks the assumption (filter inactive, max_n small enough for the
+//           record) and lays out the iteration-major rows of all T frames; if any frame breaks the assumption the
+//           chunk is REJECTED: nothing is emitted or committed, and the caller replays the chunk frame by frame from
+//           the untouched state (v2e_emu_collect does that itself for v2e_emu_step).
+//   emit   (emu_fused_emit_kernel): records -> packed rows with the frame's linspace timestamps.
+//   commit (emu_fused_commit_kernel): alternate lp / base -> the handle's state.
+// Arithmetic per pixel and frame is the update + emit kernels' (same operations in the same order), so the rows,
+// counters and state equal the per-frame path's bit for bit (tests/test_emulator_gpu.py).
+// =============================================================================================
+struct FusedFrame {                     // what pass 1 needs of one frame
+    double eps_scale, shot_c;
+    float dt_f;
+    uint32_t frame_index, pref_lo, pad;
+};
+static_assert(sizeof(FusedFrame) == 32, "FusedFrame layout");
+constexpr int kFusedPrefetch = 4;
+constexpr int kFusedGroup = 64;                     // 128-pixel units per block of the count / emit kernels
+constexpr int kFusedMaxN = 31;                      // largest per-frame maximum the fused plan accepts
+constexpr int kFusedFallback = 100;                 // abort_flag value: chunk rejected (internal)
+constexpr int kBlkSeg = kSegSmem + 2;
+// record: bits 0-6 pixel within the unit, 7 polarity (1 = OFF), 8-9 shot flags, 10-15 event count (clamped to 63)
+__device__ __forceinline__ uint32_t make_rec16(int px_local, int neg, int flags, int mag) {
+    return (uint32_t)px_local | ((uint32_t)neg << 7) | ((uint32_t)flags << 8) | ((uint32_t)(mag > 63 ? 63 : mag) << 10);
+}
+
+template <typename S, bool FAST>
+__global__ void __launch_bounds__(kThreads, 3)
+emu_fused_update_kernel(EmuDev d, const FusedFrame *__restrict__ ff, const uint8_t *__restrict__ frames, int T,
+                        S *__restrict__ lp_out, S *__restrict__ base_out, uint16_t *__restrict__ rec_list,
+                        uint32_t *__restrict__ rec_cnt) {
+    const bool f_pp = FAST || d.per_pixel_thres, f_leak = FAST || d.leak_on, f_shot = FAST || d.shot_on;
+    constexpr bool f_lp = sizeof(S) == 8;        // no hdr here: float64 state <=> the low-pass is on
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    FusedFrame *s_ff = (FusedFrame *)s_dyn;
+    __shared__ double s_ln[256];                 // lin_log(code), float32 value widened
+    __shared__ double s_in[256];                 // inten01(code) = (code + 20) / 275 (emulator_utils.py:48-54)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    {
+        const uint4 *src = (const uint4 *)ff;
+        uint4 *dst = (uint4 *)s_dyn;
+        for (int i = tid; i < T * 2; i += kThreads) dst[i] = src[i];
+        s_ln[tid] = (double)d.lut[tid];
+        s_in[tid] = ((double)tid + 20.0) / 275.0;
+    }
+    __syncthreads();
+    if (*(volatile int32_t *)d.abort_flag) return;
+    const int u0 = (int)(((long long)blockIdx.x * d.units) / d.n_blocks);
+    const int u1 = (int)(((long long)(blockIdx.x + 1) * d.units) / d.n_blocks);
+    const size_t n = (size_t)d.n;
+    for (int unit = u0 + warp; unit < u1; unit += kWarps) {
+        const int i0 = unit * kUnitPx + lane * kVec;
+        const bool t_on = i0 < d.n;
+        const bool full = i0 + 4 <= d.n;
+        auto load_codes = [&](int f) -> uint32_t {
+            if (!t_on) return 0u;
+            const uint8_t *pf = frames + (size_t)f * n + i0;
+            if (full && (((uintptr_t)pf) & 3) == 0) return __ldg((const uint32_t *)pf);
+            uint32_t v = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) if (i0 + k < d.n) v |= (uint32_t)pf[k] << (8 * k);
+            return v;
+        };
+        uint32_t ring[kFusedPrefetch];
+#pragma unroll
+        for (int q = 0; q < kFusedPrefetch; q++) ring[q] = q < T ? load_codes(q) : 0u;
+        // per-pixel state -> registers for the whole clip chunk
+        S lp[4] = {(S)0, (S)0, (S)0, (S)0}, base[4] = {(S)0, (S)0, (S)0, (S)0};
+        float thp[4], thn[4], lnr[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < 4; k++) { thp[k] = (float)d.pos_nom; thn[k] = (float)d.neg_nom; }
+        if (t_on) {
+            if (f_lp) ld4((const S *)d.lp, i0, lp);
+            ld4((const S *)d.base, i0, base);
+            if (f_pp) { ld4(d.pos_thres, i0, thp); ld4(d.neg_thres, i0, thn); }
+            if (f_leak) {
+                ld4(d.noise_rate, i0, lnr);
+#pragma unroll
+                for (int k = 0; k < 4; k++) lnr[k] = d.leak_rate_f * lnr[k];      // emulator_utils.py:127, float32 product
+            }
+        }
+        const uint32_t g0 = (uint32_t)i0 + d.px_off;
+        const bool use_rng = (f_leak || f_shot) && d.rng_mode == 1;
+        for (int fb = 0; fb < T; fb += kFusedPrefetch) {
+#pragma unroll
+            for (int q = 0; q < kFusedPrefetch; q++) {
+                const int f = fb + q;
+                if (f >= T) break;
+                const uint32_t codes = ring[q];
+                if (f + kFusedPrefetch < T) ring[q] = load_codes(f + kFusedPrefetch);
+                const FusedFrame fr = s_ff[f];
+                uint32_t r16[4] = {0u, 0u, 0u, 0u};
+                int act[4] = {0, 0, 0, 0};
+                if (t_on) {
+                    float lr[4] = {0.f, 0.f, 0.f, 0.f};
+                    uint32_t pref[4] = {0u, 0u, 0u, 0u};
+                    if (use_rng) noise_px4(d.seed, g0, fr.frame_index, lr, pref);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int code = (int)((codes >> (8 * k)) & 0xffu);
+                        // photoreceptor low-pass (emulator_utils.py:57-109)
+                        const double ln = s_ln[code];
+                        if (f_lp) {
+                            double eps = s_in[code] * fr.eps_scale;
+                            if (eps > 1.0) eps = 1.0;
+                            lp[k] = (S)((1.0 - eps) * (double)lp[k] + eps * ln);
+                        } else {
+                            lp[k] = (S)ln;
+                        }
+                        // leak (emulator_utils.py:114-134): float32 products, subtract in S
+                        if (f_leak) {
+                            const float rate = lnr[k] * (1.0f - d.leak_jit_f * lr[k]);
+                            const float delta = (fr.dt_f * rate) * thp[k];
+                            base[k] = base[k] - (S)delta;
+                        }
+                        // difference and event count (emulator.py:748-772, emulator_utils.py:137-173)
+                        const S diff = lp[k] - base[k];
+                        S tp, tn;
+                        if (sizeof(S) == 8 && !f_pp) { tp = (S)d.pos_nom; tn = (S)d.neg_nom; }
+                        else { tp = (S)thp[k]; tn = (S)thn[k]; }
+                        const bool neg = diff < (S)0;
+                        const S a = neg ? -diff : diff, b = neg ? tn : tp, b2 = b + b;
+                        const int ge1 = a >= b, ge2 = a >= b2;
+                        int32_t mag = ge1 + ge2;
+                        if (ge2 && !(a - b2 < b)) {                  // >= 3 events: rare
+                            mag = div_floor_count<S>(a, b);
+                            if (mag > kRecMaxCount) mag = kRecMaxCount;
+                        }
+                        int flags = 0;
+                        if (f_shot && shot_candidate(pref[k], fr.pref_lo)) {        // rare
+                            const float r = shot_uniform(d.seed, (g0 + k) >> 2, fr.frame_index, (int)((g0 + k) & 3u), pref[k]);
+                            flags = shot_flags(d, fr.shot_c, (double)code, r, thp[k], thn[k]);
+                        }
+                        if (i0 + k >= d.n) { mag = 0; flags = 0; }
+                        // the refractory filter does not run (checked by the plan): every event is emitted
+                        // (emulator.py:936-942: int32 * float32 -> float32, then the state's dtype)
+                        if (mag | flags) {
+                            const float prod = (float)mag * (neg ? thn[k] : thp[k]);
+                            S bb = neg ? base[k] - (S)prod : base[k] + (S)prod;
+                            if (flags) bb = lp[k];
+                            base[k] = bb;
+                            act[k] = 1;
+                            r16[k] = make_rec16(lane * kVec + k, neg, flags, mag);
+                        }
+                    }
+                }
+                // compaction of this frame's active pixels into the (frame, unit) list segment
+                uint32_t cnt = 0;
+                if (__any_sync(0xffffffffu, act[0] | act[1] | act[2] | act[3])) {
+                    uint16_t *seg = rec_list + ((size_t)f * d.units + unit) * kUnitPx;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const unsigned m = __ballot_sync(0xffffffffu, act[k]);
+                        if (act[k]) seg[cnt + __popc(m & lt_mask)] = (uint16_t)r16[k];
+                        cnt += __popc(m);
+                    }
+                }
+                if (lane == 0) rec_cnt[(size_t)f * d.units + unit] = cnt;
+            }
+        }
+        if (t_on) {
+            st4(lp_out, i0, lp);
+            st4(base_out, i0, base);
+        }
+    }
+}
+
+// pass 2: histogram per (iteration, polarity) and maximum per frame from the records. Block = (frame, group of
+// kFusedGroup units). The block's own per-segment counts are kept for the emit kernel (blk_cnt).
+__global__ void __launch_bounds__(kThreads)
+emu_fused_count_kernel(EmuDev d, int T, int groups, const uint16_t *__restrict__ rec_list,
+                       const uint32_t *__restrict__ rec_cnt, uint32_t *__restrict__ blk_cnt) {
+    __shared__ uint32_t s_hist[kBlkSeg];
+    __shared__ int s_max;
+    if (*(volatile int32_t *)d.abort_flag) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int f = blockIdx.x / groups, g = blockIdx.x - f * groups;
+    if (tid < kBlkSeg) s_hist[tid] = 0;
+    if (tid == 0) s_max = 0;
+    __syncthreads();
+    uint32_t *hist = d.hist_pre + (size_t)f * d.seg_stride;
+    const int ue = min(d.units, (g + 1) * kFusedGroup);
+    int local_max = 0;
+    for (int u = g * kFusedGroup + warp; u < ue; u += kWarps) {
+        const uint32_t n = rec_cnt[(size_t)f * d.units + u];
+        const uint16_t *seg = rec_list + ((size_t)f * d.units + u) * kUnitPx;
+        for (uint32_t b0 = 0; b0 < n; b0 += 32) {
+            const uint32_t r = b0 + lane < n ? (uint32_t)seg[b0 + lane] : 0u;
+            const int mag = (int)(r >> 10), neg = (int)((r >> 7) & 1u), flags = (int)((r >> 8) & 3u);
+            local_max = max(local_max, mag);
+            const int magc = min(mag, d.iter_cap);
+            const int wmax = __reduce_max_sync(0xffffffffu, magc);
+            for (int it = 0; it < wmax; it++) {
+                const unsigned on = __ballot_sync(0xffffffffu, it < magc && !neg);
+                const unsigned off = __ballot_sync(0xffffffffu, it < magc && neg);
+                if (lane == 0) {
+                    if (on) { if (2 * it < kSegSmem) atomicAdd(&s_hist[2 * it], __popc(on)); else atomicAdd(&hist[2 * it], __popc(on)); }
+                    if (off) { if (2 * it + 1 < kSegSmem) atomicAdd(&s_hist[2 * it + 1], __popc(off)); else atomicAdd(&hist[2 * it + 1], __popc(off)); }
+                }
+            }
+            const unsigned son = __ballot_sync(0xffffffffu, flags & 1), soff = __ballot_sync(0xffffffffu, flags & 2);
+            if (lane == 0) {
+                if (son) atomicAdd(&s_hist[kSegSmem], __popc(son));
+                if (soff) atomicAdd(&s_hist[kSegSmem + 1], __popc(soff));
+            }
+        }
+    }
+    local_max = warp_reduce_max(local_max);
+    if (lane == 0 && local_max > 0) atomicMax(&s_max, local_max);
+    __syncthreads();
+    if (tid == 0 && s_max > 0) atomicMax(&d.ctrl[f].max_n, s_max);
+    if (tid < kBlkSeg) {
+        const uint32_t v = s_hist[tid];
+        blk_cnt[(size_t)blockIdx.x * kBlkSeg + tid] = v;
+        if (v) atomicAdd(&hist[tid < kSegSmem ? tid : 2 * d.iter_cap + (tid - kSegSmem)], v);
+    }
+}
+
+// plan of all T frames: one block. max_vec (nullable): the frame maxima reduced over the ranks of a pixel-sharded clip.
+__global__ void __launch_bounds__(kThreads)
+emu_fused_plan_kernel(EmuDev d, const FrameParams *__restrict__ fp, int T, uint64_t ev_base_start, uint64_t capacity,
+                      const int32_t *__restrict__ max_vec) {
+    extern __shared__ uint32_t s_tot[];          // [T] rows of each frame
+    __shared__ int s_bad;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_bad = 0x7fffffff;
+    __syncthreads();
+    for (int f = warp; f < T; f += kWarps) {
+        FrameCtrl *c = d.ctrl + f;
+        int32_t max_n = max_vec ? max_vec[f] : *(volatile int32_t *)&c->max_n;
+        const FrameParams p = fp[f];
+        bool bad = max_n > kFusedMaxN || max_n > d.iter_cap;
+        if (d.refr_on && max_n > 0 && d.refr_d > p.dt / (double)max_n) bad = true;    // emulator.py:792, 830
+        const uint32_t *h = d.hist_pre + (size_t)f * d.seg_stride;
+        uint32_t *off = d.segoff + (size_t)f * d.seg_stride;
+        const int nseg = bad ? 0 : 2 * max_n;
+        const int s0 = 2 * lane, s1 = 2 * lane + 1;
+        const uint32_t v0 = s0 < nseg ? h[s0] : 0u, v1 = s1 < nseg ? h[s1] : 0u;
+        uint32_t incl = v0 + v1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const uint32_t excl = incl - (v0 + v1);
+        if (s0 < nseg) off[s0] = excl;
+        if (s1 < nseg) off[s1] = excl + v0;
+        const uint32_t sig = __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t sig_on = __reduce_add_sync(0xffffffffu, v0);
+        if (lane == 0) {
+            const uint32_t shot_on = h[2 * d.iter_cap], shot_off = h[2 * d.iter_cap + 1];
+            off[2 * d.iter_cap] = sig;
+            off[2 * d.iter_cap + 1] = sig + shot_on;
+            const uint32_t total = sig + shot_on + shot_off;
+            c->max_n = max_n;
+            c->filter_active = 0;
+            c->n_on = sig_on + shot_on;
+            c->n_off = (sig - sig_on) + shot_off;
+            c->n_shot_on = shot_on;
+            c->n_shot_off = shot_off;
+            c->n_events = total;
+            s_tot[f] = total;
+            if (bad) atomicMin(&s_bad, f);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        uint64_t base = ev_base_start;
+        for (int f = 0; f < T; f++) {
+            d.ctrl[f].ev_base = base;
+            base += s_tot[f];
+        }
+        d.ctrl[T].ev_base = base;
+        if (s_bad != 0x7fffffff) {
+            if (atomicCAS(d.abort_flag, 0, kFusedFallback) == 0) d.abort_flag[1] = s_bad;
+        } else if (base > capacity) {
+            if (atomicCAS(d.abort_flag, 0, V2E_E_CAPACITY) == 0) d.abort_flag[1] = 0;
+        } else {
+            for (int f = 0; f < T; f++) d.ctrl[f].planned = 1;
+        }
+        __threadfence();
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+emu_fused_emit_kernel(EmuDev d, const FrameParams *__restrict__ fp, int T, int groups,
+                      const uint16_t *__restrict__ rec_list, const uint32_t *__restrict__ rec_cnt,
+                      const uint32_t *__restrict__ blk_cnt, float4 *__restrict__ events) {
+    __shared__ uint32_t s_cnt[kBlkSeg];
+    __shared__ uint32_t s_base[kBlkSeg];
+    if (*(volatile int32_t *)d.abort_flag) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int f = blockIdx.x / groups, g = blockIdx.x - f * groups;
+    const FrameCtrl *c = d.ctrl + f;
+    if (!c->planned || c->n_events == 0) return;
+    const TsParams ts = make_ts(fp[f], c->max_n, d.refr_d);
+    const float ts_last = linspace_f32(ts, ts.steps - 1);
+    const uint32_t *segoff = d.segoff + (size_t)f * d.seg_stride;
+    uint32_t *cursor = d.cursor + (size_t)f * d.seg_stride;
+    const uint64_t ev_base = c->ev_base;
+    if (tid < kBlkSeg) {
+        const uint32_t nb = blk_cnt[(size_t)blockIdx.x * kBlkSeg + tid];
+        s_cnt[tid] = 0;
+        if (nb) {
+            const int seg = tid < kSegSmem ? tid : 2 * d.iter_cap + (tid - kSegSmem);
+            s_base[tid] = segoff[seg] + atomicAdd(&cursor[seg], nb);
+        }
+    }
+    __syncthreads();
+    auto claim = [&](int seg_smem, int seg, unsigned count) -> uint32_t {
+        if (seg_smem >= 0) return s_base[seg_smem] + atomicAdd(&s_cnt[seg_smem], count);
+        return segoff[seg] + atomicAdd(&cursor[seg], count);
+    };
+    const int ue = min(d.units, (g + 1) * kFusedGroup);
+    for (int u = g * kFusedGroup + warp; u < ue; u += kWarps) {
+        const uint32_t n = rec_cnt[(size_t)f * d.units + u];
+        const uint16_t *seg = rec_list + ((size_t)f * d.units + u) * kUnitPx;
+        for (uint32_t b0 = 0; b0 < n; b0 += 32) {
+            const uint32_t r = b0 + lane < n ? (uint32_t)seg[b0 + lane] : 0u;
+            const int mag = (int)(r >> 10), neg = (int)((r >> 7) & 1u), flags = (int)((r >> 8) & 3u);
+            const int idx = u * kUnitPx + (int)(r & 127u);
+            const float fx = (float)(idx % d.W), fy = (float)(idx / d.W);
+            const float pv = neg ? -1.0f : 1.0f;
+            const int wmax = __reduce_max_sync(0xffffffffu, mag);
+            for (int it = 0; it < wmax; it++) {
+                const float t = linspace_f32(ts, it);
+                const bool pass = it < mag;
+                const unsigned on = __ballot_sync(0xffffffffu, pass && !neg);
+                const unsigned off = __ballot_sync(0xffffffffu, pass && neg);
+                uint32_t b_on = 0, b_off = 0;
+                if (lane == 0) {
+                    if (on) b_on = claim(2 * it < kSegSmem ? 2 * it : -1, 2 * it, __popc(on));
+                    if (off) b_off = claim(2 * it + 1 < kSegSmem ? 2 * it + 1 : -1, 2 * it + 1, __popc(off));
+                }
+                b_on = __shfl_sync(0xffffffffu, b_on, 0);
+                b_off = __shfl_sync(0xffffffffu, b_off, 0);
+                if (pass) {
+                    const uint64_t row = ev_base + (neg ? b_off + __popc(off & lt_mask) : b_on + __popc(on & lt_mask));
+                    events[row] = make_float4(t, fx, fy, pv);
+                }
+            }
+            const unsigned son = __ballot_sync(0xffffffffu, flags & 1), soff = __ballot_sync(0xffffffffu, flags & 2);
+            if (son | soff) {
+                uint32_t b_on = 0, b_off = 0;
+                if (lane == 0) {
+                    if (son) b_on = claim(kSegSmem, 0, __popc(son));
+                    if (soff) b_off = claim(kSegSmem + 1, 0, __popc(soff));
+                }
+                b_on = __shfl_sync(0xffffffffu, b_on, 0);
+                b_off = __shfl_sync(0xffffffffu, b_off, 0);
+                if (flags & 1) events[ev_base + b_on + __popc(son & lt_mask)] = make_float4(ts_last, fx, fy, 1.0f);
+                if (flags & 2) events[ev_base + b_off + __popc(soff & lt_mask)] = make_float4(ts_last, fx, fy, -1.0f);
+            }
+        }
+    }
+}
+
+// accepted chunk: the alternate lp / base arrays become the state
+__global__ void __launch_bounds__(kThreads)
+emu_fused_commit_kernel(EmuDev d, const uint4 *__restrict__ lp_alt, const uint4 *__restrict__ base_alt, size_t n16) {
+    if (*(volatile int32_t *)d.abort_flag) return;
+    uint4 *lp = (uint4 *)d.lp, *base = (uint4 *)d.base;
+    for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n16; i += (size_t)gridDim.x * kThreads) {
+        lp[i] = lp_alt[i];
+        base[i] = base_alt[i];
+    }
+}
+
 // measurement floor: what an event bracket reports around a kernel that does nothing (v2e_emu_profile_read4)
 __global__ void emu_null_kernel() {}
 
@@ -1257,6 +1693,22 @@ struct V2eEmu {
     FrameCtrl *ctrl_host;       // pinned
     int32_t *abort_host;        // pinned [2]
     size_t state_elem;
+    // fused multi-frame path (allocated on first use)
+    int fused_enable;           // v2e_emu_set_option(h, 0, x)
+    int fused_max_T;            // frames per fused chunk the record lists hold (0: not allocated)
+    void *lp_alt, *base_alt;    // where pass 1 stores the new state until the chunk is accepted
+    uint16_t *rec_list;         // [fused_max_T][units][128]
+    uint32_t *rec_cnt;          // [fused_max_T][units]
+    uint32_t *blk_cnt;          // [fused_max_T * groups][kBlkSeg]
+    FusedFrame *ff_dev;         // [max_slots]
+    FrameParams *fp_dev;        // [max_slots]
+    int32_t *max_vec;           // [max_slots] frame maxima, contiguous (all-reduced over ranks when sharded)
+    int last_fused;             // the last step went through the fused path: 1 = v2e_emu_step, 2 = phase functions
+    struct {                    // arguments of that step, for the frame-by-frame replay of a rejected chunk
+        const void *frames; int dtype, T; double t_previous; float *events; uint64_t capacity, ev_base_start;
+        double *t_frames;       // [max_slots]
+    } ls;
+    long long n_fused_chunks, n_fused_rejected;
 };
 
 thread_local char g_err[512] = "";
@@ -1272,7 +1724,14 @@ static int fail(int code, const char *fmt, const char *detail = "") {
 
 int v2e_set_error(int code, const char *fmt, const char *detail) { return fail(code, fmt, detail); }
 extern "C" const char *v2e_last_error(void) { return g_err; }
-extern "C" int v2e_version(void) { return 100; }
+extern "C" int v2e_version(void) { return 200; }
+extern "C" int v2e_abi_info(int *version, int *emu_cfg_size, int *frame_info_size, int *unet_weights_size) {
+    if (version) *version = 200;
+    if (emu_cfg_size) *emu_cfg_size = (int)sizeof(V2eEmuCfg);
+    if (frame_info_size) *frame_info_size = (int)sizeof(V2eFrameInfo);
+    if (unet_weights_size) *unet_weights_size = (int)sizeof(V2eUNetWeights);
+    return V2E_OK;
+}
 
 static FrameParams make_params(const V2eEmu *h, double t_frame, double t_prev, uint32_t frame_index,
                                uint64_t capacity) {
@@ -1306,6 +1765,8 @@ static FrameParams make_params(const V2eEmu *h, double t_frame, double t_prev, u
         if ((double)hi > 1.0 - p.shot_bound) hi = nextafterf(hi, -INFINITY);
         p.shot_lo_f = lo;
         p.shot_hi_f = hi;
+        const double pl = ceil(p.shot_bound * 4096.0);
+        p.pref_lo = pl >= 2048.0 ? 2048u : (uint32_t)pl;
     }
     p.capacity = capacity;
     if (h->cfg.photoreceptor_noise && h->cfg.cutoff_hz > 0) {
@@ -1361,6 +1822,9 @@ extern "C" int v2e_emu_create(const V2eEmuCfg *cfg, V2eEmu **out) {
     d.seed = cfg->seed;
     h->state_elem = d.state_f64 ? 8 : 4;
     h->min_thres = 0.01;
+    h->fused_enable = 1;
+    h->ls.t_frames = new double[cfg->max_frames_per_step]();
+    d.px_off = cfg->rng_pixel_offset;
     d.units = (d.n + kUnitPx - 1) / kUnitPx;
     // state arrays are staged in whole 128-pixel units by the update kernel's bulk copies
     size_t np = (size_t)d.units * kUnitPx;
@@ -1430,6 +1894,9 @@ extern "C" int v2e_emu_destroy(V2eEmu *h) {
     if (!h) return V2E_OK;
     EmuDev &d = h->d;
     delete[] h->pr_vrms;
+    delete[] h->ls.t_frames;
+    void *fused_ptrs[] = {h->lp_alt, h->base_alt, h->rec_list, h->rec_cnt, h->blk_cnt, h->ff_dev, h->fp_dev, h->max_vec};
+    for (void *p : fused_ptrs) if (p) cudaFree(p);
     void *ptrs[] = {d.hp, d.prev_photo, d.tau_arr, d.noise_arr, d.pr_eff,
                     d.lp, d.base, d.rec, d.pos_thres, d.neg_thres, d.noise_rate, d.tmem, d.surround,
                     h->lut_dev, d.ctrl, d.hist_pre, d.hist_post, d.segoff, d.cursor, d.abort_flag, d.act_list, d.act_count, d.surround2, d.cs_cur, d.cs_max};
@@ -1668,7 +2135,192 @@ static int reset_slots(V2eEmu *h, int first, int count, cudaStream_t st) {
     return V2E_OK;
 }
 
-extern "C" int v2e_emu_step(V2eEmu *h, const void *frames, int dtype, int T, const double *t_frames,
+
+// ---- fused multi-frame path, host side ------------------------------------------------------------
+static int fused_groups(const EmuDev &d) { return (d.units + kFusedGroup - 1) / kFusedGroup; }
+
+static bool fused_config_ok(const V2eEmu *h, int dtype) {
+    const EmuDev &d = h->d;
+    return dtype == V2E_U8 && !d.hdr && !d.csdvs && !d.scidvs && !d.pr_noise &&
+           (d.rng_mode == 1 || (!d.leak_on && !d.shot_on)) && (d.state_f64 ? d.lowpass_on : !d.lowpass_on);
+}
+
+static int fused_alloc(V2eEmu *h) {
+    if (h->fused_max_T) return V2E_OK;
+    const EmuDev &d = h->d;
+    // record lists: 2 bytes per pixel and frame of capacity (sparsely written); bounded at 1.5 GB
+    size_t per_frame = (size_t)d.units * kUnitPx * sizeof(uint16_t);
+    int maxT = (int)((size_t)1536 * 1024 * 1024 / per_frame);
+    if (maxT > d.max_slots) maxT = d.max_slots;
+    if (maxT < 2) { h->fused_max_T = -1; return V2E_OK; }
+    const size_t np = (size_t)d.units * kUnitPx;
+#define FALLOC(ptr, bytes)                                                                  \
+    do {                                                                                    \
+        cudaError_t e_ = cudaMalloc((void **)&(ptr), (bytes));                              \
+        if (e_ != cudaSuccess) return fail(V2E_E_CUDA, "cudaMalloc (fused path): %s", cudaGetErrorString(e_)); \
+    } while (0)
+    FALLOC(h->lp_alt, np * h->state_elem);
+    FALLOC(h->base_alt, np * h->state_elem);
+    FALLOC(h->rec_list, (size_t)maxT * per_frame);
+    FALLOC(h->rec_cnt, (size_t)maxT * d.units * sizeof(uint32_t));
+    FALLOC(h->blk_cnt, (size_t)maxT * fused_groups(d) * kBlkSeg * sizeof(uint32_t));
+    FALLOC(h->ff_dev, (size_t)d.max_slots * sizeof(FusedFrame));
+    FALLOC(h->fp_dev, (size_t)d.max_slots * sizeof(FrameParams));
+    FALLOC(h->max_vec, (size_t)d.max_slots * sizeof(int32_t));
+#undef FALLOC
+    CU(cudaMemset(h->lp_alt, 0, np * h->state_elem));
+    CU(cudaMemset(h->base_alt, 0, np * h->state_elem));
+    h->fused_max_T = maxT;
+    return V2E_OK;
+}
+
+template <typename S>
+static int launch_fused_update(V2eEmu *h, const uint8_t *frames, int T, cudaStream_t st) {
+    const EmuDev &d = h->d;
+    const size_t sm = (size_t)T * sizeof(FusedFrame);
+    const bool fast = sizeof(S) == 8 && d.rng_mode == 1 && d.per_pixel_thres && d.leak_on && d.shot_on;
+    if (sm > 40 * 1024) return fail(V2E_E_INVALID, "fused path: too many frames per step");
+    if (fast)
+        emu_fused_update_kernel<S, true><<<d.n_blocks, kThreads, sm, st>>>(d, h->ff_dev, frames, T, (S *)h->lp_alt,
+                                                                            (S *)h->base_alt, h->rec_list, h->rec_cnt);
+    else
+        emu_fused_update_kernel<S, false><<<d.n_blocks, kThreads, sm, st>>>(d, h->ff_dev, frames, T, (S *)h->lp_alt,
+                                                                             (S *)h->base_alt, h->rec_list, h->rec_cnt);
+    return V2E_OK;
+}
+
+// uploads the per-frame parameters of a chunk; returns them in `fp_host` too
+static int fused_upload_params(V2eEmu *h, int T, const double *t_frames, double t_previous, uint32_t frame_base,
+                               uint64_t capacity, cudaStream_t st) {
+    static thread_local FusedFrame *ffh = nullptr;
+    static thread_local FrameParams *fph = nullptr;
+    static thread_local int cap = 0;
+    if (cap < T) {
+        delete[] ffh; delete[] fph;
+        cap = T > 64 ? T : 64;
+        ffh = new FusedFrame[cap];
+        fph = new FrameParams[cap];
+    }
+    for (int f = 0; f < T; f++) {
+        const double tp = f == 0 ? t_previous : t_frames[f - 1];
+        if (t_frames[f] < tp) return fail(V2E_E_INVALID, "frame times must be non-decreasing");
+        fph[f] = make_params(h, t_frames[f], tp, frame_base + (uint32_t)f, capacity);
+        memset(&ffh[f], 0, sizeof(FusedFrame));
+        ffh[f].eps_scale = fph[f].eps_scale;
+        ffh[f].shot_c = fph[f].shot_c;
+        ffh[f].dt_f = fph[f].dt_f;
+        ffh[f].frame_index = fph[f].frame_index;
+        ffh[f].pref_lo = fph[f].pref_lo;
+    }
+    // pageable sources: the runtime stages them before the call returns, so the buffers can be reused at once
+    CU(cudaMemcpyAsync(h->ff_dev, ffh, (size_t)T * sizeof(FusedFrame), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(h->fp_dev, fph, (size_t)T * sizeof(FrameParams), cudaMemcpyHostToDevice, st));
+    return V2E_OK;
+}
+
+static int enqueue_fused_count(V2eEmu *h, const void *frames, int T, cudaStream_t st) {
+    const EmuDev &d = h->d;
+    int rc;
+    {
+        ProfScope ps(h, 0, 0, st);
+        rc = d.state_f64 ? launch_fused_update<double>(h, (const uint8_t *)frames, T, st)
+                         : launch_fused_update<float>(h, (const uint8_t *)frames, T, st);
+    }
+    if (rc) return rc;
+    {
+        ProfScope ps(h, 0, 1, st);
+        emu_fused_count_kernel<<<T * fused_groups(d), kThreads, 0, st>>>(d, T, fused_groups(d), h->rec_list, h->rec_cnt, h->blk_cnt);
+    }
+    return V2E_OK;
+}
+
+static int enqueue_fused_emit(V2eEmu *h, int T, float *events, uint64_t capacity, uint64_t ev_base_start,
+                              const int32_t *max_vec, bool commit, cudaStream_t st) {
+    const EmuDev &d = h->d;
+    {
+        ProfScope ps(h, 0, 1, st);
+        emu_fused_plan_kernel<<<1, kThreads, (size_t)T * sizeof(uint32_t), st>>>(d, h->fp_dev, T, ev_base_start, capacity, max_vec);
+    }
+    {
+        ProfScope ps(h, 0, 2, st);
+        emu_fused_emit_kernel<<<T * fused_groups(d), kThreads, 0, st>>>(d, h->fp_dev, T, fused_groups(d), h->rec_list,
+                                                                         h->rec_cnt, h->blk_cnt, (float4 *)events);
+    }
+    if (commit) {
+        const size_t n16 = (size_t)d.units * kUnitPx * h->state_elem / 16;
+        emu_fused_commit_kernel<<<296, kThreads, 0, st>>>(d, (const uint4 *)h->lp_alt, (const uint4 *)h->base_alt, n16);
+    }
+    return V2E_OK;
+}
+
+static void remember_step(V2eEmu *h, const void *frames, int dtype, int T, const double *t_frames, double t_previous,
+                          float *events, uint64_t capacity, uint64_t ev_base_start) {
+    h->ls.frames = frames; h->ls.dtype = dtype; h->ls.T = T; h->ls.t_previous = t_previous;
+    h->ls.events = events; h->ls.capacity = capacity; h->ls.ev_base_start = ev_base_start;
+    if (t_frames != h->ls.t_frames) memcpy(h->ls.t_frames, t_frames, sizeof(double) * (size_t)T);
+}
+
+extern "C" int v2e_emu_set_option(V2eEmu *h, int option, int value) {
+    if (!h) return fail(V2E_E_INVALID, "null handle");
+    if (option == 0) { h->fused_enable = value ? 1 : 0; return V2E_OK; }
+    return fail(V2E_E_INVALID, "unknown option");
+}
+extern "C" int v2e_emu_fused_stats(V2eEmu *h, long long *chunks, long long *rejected) {
+    if (!h) return fail(V2E_E_INVALID, "null handle");
+    if (chunks) *chunks = h->n_fused_chunks;
+    if (rejected) *rejected = h->n_fused_rejected;
+    return V2E_OK;
+}
+extern "C" int32_t *v2e_emu_max_vec_dev(V2eEmu *h) { return h ? h->max_vec : nullptr; }
+
+__global__ void emu_gather_max_kernel(EmuDev d, int T, int32_t *max_vec) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f < T) max_vec[f] = d.ctrl[f].max_n;
+}
+
+extern "C" int v2e_emu_fused_count(V2eEmu *h, const void *frames, int dtype, int T, const double *t_frames,
+                                   double t_previous, void *stream) {
+    if (!h || !frames || !t_frames) return fail(V2E_E_INVALID, "null argument");
+    if (!h->first_done) return fail(V2E_E_STATE, "v2e_emu_first_frame must run first");
+    if (T < 1 || T > h->d.max_slots) return fail(V2E_E_INVALID, "bad T");
+    if (!fused_config_ok(h, dtype)) return fail(V2E_E_UNSUPPORTED, "configuration does not qualify for the fused path");
+    int rc;
+    if ((rc = fused_alloc(h))) return rc;
+    if (h->fused_max_T < T) return fail(V2E_E_UNSUPPORTED, "fused path: T exceeds the record lists");
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = reset_slots(h, 0, T, st))) return rc;
+    if (h->profile) { memset(h->prof_used, 0, (size_t)h->d.max_slots * kProfKinds); h->prof_frames = T; }
+    h->step_base = h->frame_counter;
+    h->frame_counter += (uint32_t)T;
+    if ((rc = fused_upload_params(h, T, t_frames, t_previous, h->step_base, 0, st))) return rc;
+    if ((rc = enqueue_fused_count(h, frames, T, st))) return rc;
+    emu_gather_max_kernel<<<(T + 127) / 128, 128, 0, st>>>(h->d, T, h->max_vec);
+    CU(cudaGetLastError());
+    remember_step(h, frames, dtype, T, t_frames, t_previous, nullptr, 0, 0);
+    h->last_T = T;
+    h->last_fused = 2;
+    h->n_fused_chunks++;
+    return V2E_OK;
+}
+
+extern "C" int v2e_emu_fused_emit(V2eEmu *h, float *events, uint64_t capacity, uint64_t ev_base_start, void *stream) {
+    if (!h || (!events && capacity)) return fail(V2E_E_INVALID, "null argument");
+    if (h->last_fused != 2) return fail(V2E_E_STATE, "v2e_emu_fused_count must precede v2e_emu_fused_emit");
+    if (((uintptr_t)events & 15) != 0) return fail(V2E_E_INVALID, "events_out must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const EmuDev &d = h->d;
+    const int T = h->ls.T;
+    // a second call after V2E_E_CAPACITY: same records, new plan
+    CU(cudaMemsetAsync(d.abort_flag, 0, 2 * sizeof(int32_t), st));
+    CU(cudaMemsetAsync(d.cursor, 0, (size_t)T * d.seg_stride * 4, st));
+    h->ls.events = events; h->ls.capacity = capacity; h->ls.ev_base_start = ev_base_start;
+    int rc = enqueue_fused_emit(h, T, events, capacity, ev_base_start, h->max_vec, true, st);
+    if (rc) return rc;
+    CU(cudaGetLastError());
+    return V2E_OK;
+}
+
+static int step_classic(V2eEmu *h, const void *frames, int dtype, int T, const double *t_frames,
                             double t_previous, const float *leak_randn, const float *shot_rand,
                             float *events, uint64_t capacity, uint64_t ev_base_start, int first,
                             int resume_emit, void *stream) {
@@ -1724,6 +2376,52 @@ extern "C" int v2e_emu_step(V2eEmu *h, const void *frames, int dtype, int T, con
     return V2E_OK;
 }
 
+
+extern "C" int v2e_emu_step(V2eEmu *h, const void *frames, int dtype, int T, const double *t_frames,
+                            double t_previous, const float *leak_randn, const float *shot_rand,
+                            float *events, uint64_t capacity, uint64_t ev_base_start, int first,
+                            int resume_emit, void *stream) {
+    if (!h || !frames || !t_frames || (!events && capacity)) return fail(V2E_E_INVALID, "null argument");
+    if (!h->first_done) return fail(V2E_E_STATE, "v2e_emu_first_frame must run before v2e_emu_step");
+    if (T < 1 || T > h->d.max_slots || first < 0 || first >= T) return fail(V2E_E_INVALID, "bad T / first");
+    if (((uintptr_t)events & 15) != 0) return fail(V2E_E_INVALID, "events_out must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const EmuDev &d = h->d;
+    int rc;
+    if (resume_emit && h->last_fused == 1 && first == 0) {
+        // capacity abort of a fused chunk: the records are still there; plan again into the larger buffer
+        CU(cudaMemsetAsync(d.abort_flag, 0, 2 * sizeof(int32_t), st));
+        CU(cudaMemsetAsync(d.cursor, 0, (size_t)T * d.seg_stride * 4, st));
+        remember_step(h, frames, dtype, T, t_frames, t_previous, events, capacity, ev_base_start);
+        if ((rc = enqueue_fused_emit(h, T, events, capacity, ev_base_start, nullptr, true, st))) return rc;
+        CU(cudaGetLastError());
+        return V2E_OK;
+    }
+    const bool want_fused = h->fused_enable && T >= 2 && first == 0 && !resume_emit && !leak_randn && !shot_rand &&
+                            fused_config_ok(h, dtype);
+    if (want_fused) {
+        if ((rc = fused_alloc(h))) return rc;
+        if (h->fused_max_T >= T) {
+            if ((rc = reset_slots(h, 0, T, st))) return rc;
+            if (h->profile) { memset(h->prof_used, 0, (size_t)d.max_slots * kProfKinds); h->prof_frames = T; }
+            h->step_base = h->frame_counter;
+            h->frame_counter += (uint32_t)T;
+            if ((rc = fused_upload_params(h, T, t_frames, t_previous, h->step_base, capacity, st))) return rc;
+            if ((rc = enqueue_fused_count(h, frames, T, st))) return rc;
+            if ((rc = enqueue_fused_emit(h, T, events, capacity, ev_base_start, nullptr, true, st))) return rc;
+            CU(cudaGetLastError());
+            remember_step(h, frames, dtype, T, t_frames, t_previous, events, capacity, ev_base_start);
+            h->last_T = T;
+            h->last_fused = 1;
+            h->n_fused_chunks++;
+            return V2E_OK;
+        }
+    }
+    h->last_fused = 0;
+    return step_classic(h, frames, dtype, T, t_frames, t_previous, leak_randn, shot_rand, events, capacity,
+                        ev_base_start, first, resume_emit, stream);
+}
+
 extern "C" int v2e_emu_collect(V2eEmu *h, V2eFrameInfo *info, int T, int *frames_done,
                                uint64_t *rows_total, void *stream) {
     if (!h || !info || T < 1 || T > h->d.max_slots) return fail(V2E_E_INVALID, "bad argument");
@@ -1731,6 +2429,22 @@ extern "C" int v2e_emu_collect(V2eEmu *h, V2eFrameInfo *info, int T, int *frames
     CU(cudaMemcpyAsync(h->ctrl_host, h->d.ctrl, (size_t)(T + 1) * sizeof(FrameCtrl), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(h->abort_host, h->d.abort_flag, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    if (h->abort_host[0] == kFusedFallback) {
+        // the fused chunk was rejected on the device (refractory filter active or more than kFusedMaxN events of
+        // one pixel in some frame): nothing was emitted or committed. Same frames, same Philox frame indices,
+        // frame by frame:
+        h->n_fused_rejected++;
+        h->frame_counter = h->step_base;
+        const int mode = h->last_fused;
+        h->last_fused = 0;
+        if (mode == 2) return fail(V2E_E_FALLBACK, "fused chunk rejected: replay it frame by frame");
+        int rc = step_classic(h, h->ls.frames, h->ls.dtype, h->ls.T, h->ls.t_frames, h->ls.t_previous, nullptr, nullptr,
+                              h->ls.events, h->ls.capacity, h->ls.ev_base_start, 0, 0, stream);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(h->ctrl_host, h->d.ctrl, (size_t)(T + 1) * sizeof(FrameCtrl), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(h->abort_host, h->d.abort_flag, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
     int status = h->abort_host[0], done = status ? h->abort_host[1] : T;
     uint64_t rows = 0;
     for (int f = 0; f < T; f++) {
@@ -1749,6 +2463,48 @@ extern "C" int v2e_emu_collect(V2eEmu *h, V2eFrameInfo *info, int T, int *frames
     if (rows_total) *rows_total = rows;
     if (status == V2E_E_CAPACITY) return fail(V2E_E_CAPACITY, "event buffer too small");
     if (status == V2E_E_ITER_CAP) return fail(V2E_E_ITER_CAP, "a pixel exceeded iter_cap events in one frame");
+    return V2E_OK;
+}
+
+extern "C" int v2e_emu_time_fused(V2eEmu *h, const void *frames, int dtype, int T, const double *t_frames,
+                                  double t_previous, float *events, uint64_t capacity, int K, float *us_chunk,
+                                  float *us_update, void *stream) {
+    if (!h || !frames || !t_frames || !events || K < 1 || !us_chunk) return fail(V2E_E_INVALID, "bad argument");
+    if (!h->first_done) return fail(V2E_E_STATE, "v2e_emu_first_frame must run first");
+    if (T < 2 || T > h->d.max_slots) return fail(V2E_E_INVALID, "bad T");
+    if (!fused_config_ok(h, dtype)) return fail(V2E_E_UNSUPPORTED, "configuration does not qualify for the fused path");
+    int rc;
+    if ((rc = fused_alloc(h))) return rc;
+    if (h->fused_max_T < T) return fail(V2E_E_UNSUPPORTED, "fused path: T exceeds the record lists");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaEvent_t e[4];
+    for (int i = 0; i < 4; i++) cudaEventCreate(&e[i]);
+    rc = fused_upload_params(h, T, t_frames, t_previous, h->frame_counter, capacity, st);
+    const int prof = h->profile;
+    h->profile = 0;
+    for (int k = -1; k < K && !rc; k++) {          // k = -1: warm-up
+        if (k == 0) cudaEventRecord(e[0], st);
+        rc = reset_slots(h, 0, T, st);
+        if (!rc) rc = enqueue_fused_count(h, frames, T, st);
+        if (!rc) rc = enqueue_fused_emit(h, T, events, capacity, 0, nullptr, false, st);
+    }
+    cudaEventRecord(e[1], st);
+    cudaEventRecord(e[2], st);
+    for (int k = 0; k < K && !rc; k++)
+        rc = h->d.state_f64 ? launch_fused_update<double>(h, (const uint8_t *)frames, T, st)
+                            : launch_fused_update<float>(h, (const uint8_t *)frames, T, st);
+    cudaEventRecord(e[3], st);
+    h->profile = prof;
+    if (!rc) rc = reset_slots(h, 0, T, st);
+    cudaError_t ce = cudaStreamSynchronize(st);
+    float ms0 = 0.f, ms1 = 0.f;
+    cudaEventElapsedTime(&ms0, e[0], e[1]);
+    cudaEventElapsedTime(&ms1, e[2], e[3]);
+    for (int i = 0; i < 4; i++) cudaEventDestroy(e[i]);
+    if (rc) return rc;
+    if (ce != cudaSuccess) return fail(V2E_E_CUDA, "v2e_emu_time_fused: %s", cudaGetErrorString(ce));
+    *us_chunk = ms0 * 1e3f / (float)K;
+    if (us_update) *us_update = ms1 * 1e3f / (float)K;
     return V2E_OK;
 }
 

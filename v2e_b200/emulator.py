@@ -15,12 +15,19 @@ Two RNG modes:
       per-frame noise is enabled, statistically equivalent otherwise.
 
 Extra keywords (not in the reference): rng_mode, rng (draw source object), iter_cap,
-max_frames_per_step, exact_order.
+max_frames_per_step, exact_order, shard, fused.
+
+Sink keywords (dvs_h5, dvs_aedat2, dvs_aedat4, dvs_text; emulator.py:325-357): file writers are out of
+scope here, so they are DELEGATED to the reference's own writer classes (v2ecore.output.*, h5py) when
+those import, exactly as the reference drives them (emulator.py:953-975); when they do not import the
+keyword is ignored with a warning. show_dvs_model_state / record_single_pixel_states (GUI / debug
+probes) are ignored with a warning.
 """
-import atexit
 import ctypes
 import logging
 import math
+import os
+import weakref
 
 import numpy as np
 import torch
@@ -62,6 +69,92 @@ def _linlog_lut():
     y = torch.where(x <= 20, x * f, torch.log(x))
     y = torch.round(y * 1e8) / 1e8
     return y.float().contiguous()
+
+
+class _Sinks:
+    """The reference's event writers, driven the way emulator.py:325-357 / :953-975 / :401-421 drives them."""
+
+    def __init__(self, output_folder, dvs_h5, dvs_aedat2, dvs_aedat4, dvs_text, output_width, output_height,
+                 label_signal_noise):
+        self.h5 = self.h5_dataset = self.aedat2 = self.aedat4 = self.text = None
+        self.label_signal_noise = label_signal_noise
+        folder = output_folder if output_folder is not None else "."
+
+        def suffix(path, sfx):        # v2e_utils.checkAddSuffix
+            return path if path.endswith(sfx) else path + sfx
+        if dvs_h5:
+            try:
+                import h5py
+                self.h5 = h5py.File(suffix(os.path.join(folder, dvs_h5), ".h5"), "w")
+                self.h5_dataset = self.h5.create_dataset(name="events", shape=(0, 4), maxshape=(None, 4),
+                                                         dtype="uint32", compression="gzip")
+            except ImportError as e:
+                logger.warning("dvs_h5 ignored: h5py is not importable (%s)", e)
+        if dvs_aedat2:
+            try:
+                from v2ecore.output.aedat2_output import AEDat2Output
+                self.aedat2 = AEDat2Output(suffix(os.path.join(folder, dvs_aedat2), ".aedat"),
+                                           output_width=output_width, output_height=output_height,
+                                           label_signal_noise=label_signal_noise)
+            except ImportError as e:
+                logger.warning("dvs_aedat2 ignored: v2ecore.output.aedat2_output is not importable (%s)", e)
+        if dvs_aedat4:
+            try:
+                from v2ecore.output.aedat4_output import AEDat4Output
+                self.aedat4 = AEDat4Output(suffix(os.path.join(folder, dvs_aedat4), ".aedat4"))
+            except ImportError as e:
+                logger.warning("dvs_aedat4 ignored: v2ecore.output.aedat4_output is not importable (%s)", e)
+        if dvs_text:
+            try:
+                from v2ecore.output.ae_text_output import DVSTextOutput
+                self.text = DVSTextOutput(suffix(os.path.join(folder, dvs_text), ".txt"),
+                                          label_signal_noise=label_signal_noise)
+            except ImportError as e:
+                logger.warning("dvs_text ignored: v2ecore.output.ae_text_output is not importable (%s)", e)
+
+    def any(self):
+        return any(x is not None for x in (self.h5, self.aedat2, self.aedat4, self.text))
+
+    def append(self, events):
+        """emulator.py:953-975 (rows are a host float32 [N,4] array)."""
+        if events is None or len(events) == 0:
+            return
+        if self.h5 is not None:
+            tmp = np.array(events, dtype=np.float32)
+            tmp[:, 0] = tmp[:, 0] * 1e6
+            tmp[tmp[:, 3] == -1, 3] = 0
+            tmp = tmp.astype(np.uint32)
+            self.h5_dataset.resize(self.h5_dataset.shape[0] + tmp.shape[0], axis=0)
+            self.h5_dataset[-tmp.shape[0]:] = tmp
+        if self.aedat2 is not None:
+            self.aedat2.appendEvents(events, signnoise_label=None)
+        if self.aedat4 is not None:
+            self.aedat4.appendEvents(events, signnoise_label=None)
+        if self.text is not None:
+            self.text.appendEvents(events)
+
+    def close(self):
+        for w in (self.h5, self.aedat2, self.aedat4, self.text):
+            if w is not None:
+                try:
+                    w.close()
+                except Exception:
+                    pass
+        self.h5 = self.h5_dataset = self.aedat2 = self.aedat4 = self.text = None
+
+
+def _finalize(lib, box, sinks):
+    """weakref.finalize callback: frees the library handle and closes the writers of a collected (or
+    exiting) emulator without keeping it alive (the reference registers cleanup with atexit, emulator.py:372)."""
+    h = box[0]
+    box[0] = None
+    if h:
+        try:
+            lib.v2e_emu_destroy(h)
+        except Exception:
+            pass
+    if sinks is not None:
+        sinks.close()
 
 
 _STATE_IDS = {"lp_log_frame": 0, "base_log_frame": 1, "pos_thres": 2, "neg_thres": 3,
@@ -112,6 +205,7 @@ class EventEmulator(object):
             max_frames_per_step: int = 64,
             exact_order: bool = True,
             shard=None,
+            fused: bool = True,
     ):
         if not str(device).startswith("cuda"):
             raise RuntimeError("v2e_b200.EventEmulator runs on a CUDA device only (device=%r); "
@@ -122,11 +216,18 @@ class EventEmulator(object):
             raise SystemExit(1)
         if (photoreceptor_noise or scidvs) and shard is not None:
             raise NotImplementedError("pixel sharding with scidvs / photoreceptor_noise is not built")
-        if dvs_h5 or dvs_aedat2 or dvs_aedat4 or dvs_text or show_dvs_model_state or \
-                record_single_pixel_states is not None:
-            raise NotImplementedError("file sinks / state display are the caller's job here "
-                                      "(out of scope, SURVEY.md 8f); write the returned rows with "
-                                      "the reference's v2ecore.output classes")
+        if record_single_pixel_states is not None:          # emulator.py:279-290: same argument checks
+            if not (type(record_single_pixel_states) is tuple):
+                raise ValueError(f'--record_single_pixel_states {record_single_pixel_states} should be a tuple, e.g. (10,20)')
+            if len(record_single_pixel_states) != 2:
+                raise ValueError(f'--record_single_pixel_states {record_single_pixel_states} should have two pixel addresses (x,y)')
+            for i in record_single_pixel_states:
+                if not (type(i) is int):
+                    raise ValueError(f'--record_single_pixel_states {record_single_pixel_states} should have two integer-value pixel addresses (x,y)')
+        if show_dvs_model_state or save_dvs_model_state or record_single_pixel_states is not None:
+            logger.warning("show_dvs_model_state / save_dvs_model_state / record_single_pixel_states are GUI / debug "
+                           "probes of the reference (out of scope, SURVEY.md 2): ignored; the state tensors are "
+                           "available by the same attribute names")
         if rng_mode not in ("replay", "device"):
             raise ValueError("rng_mode must be 'replay' or 'device'")
         logger.info("ON/OFF log_e temporal contrast thresholds: {} / {} +/- {}".format(
@@ -175,13 +276,33 @@ class EventEmulator(object):
             torch.manual_seed(seed)
             np.random.seed(seed)
             random.seed(seed)
+        self.fused = bool(fused)
         self._lib = _lib.load()
-        self._h = None
+        self._hbox = [None]          # the library handle, shared with the finalizer
         self._ev_dev = None
         self._ev_pin = None
+        # sink keywords: delegated to the reference's writers when they import (emulator.py:325-357)
+        self.dvs_h5 = self.dvs_aedat2 = self.dvs_aedat4 = self.dvs_text = None
+        self._sinks = None
+        if dvs_h5 or dvs_aedat2 or dvs_aedat4 or dvs_text:
+            sk = _Sinks(output_folder, dvs_h5, dvs_aedat2, dvs_aedat4, dvs_text, output_width, output_height,
+                        label_signal_noise)
+            if sk.any():
+                self._sinks = sk
+                self.dvs_h5, self.dvs_aedat2, self.dvs_aedat4, self.dvs_text = sk.h5, sk.aedat2, sk.aedat4, sk.text
         self.reset()
         self.t_previous = 0
-        atexit.register(self.cleanup)
+        # the reference registers cleanup with atexit (emulator.py:372), which would keep every instance alive
+        # until exit; a finalizer frees the device memory when the object is collected AND runs at exit
+        self._finalizer = weakref.finalize(self, _finalize, self._lib, self._hbox, self._sinks)
+
+    @property
+    def _h(self):
+        return self._hbox[0]
+
+    @_h.setter
+    def _h(self, v):
+        self._hbox[0] = v
 
     # ------------------------------------------------------------------------------------------
     def reset(self):
@@ -196,6 +317,8 @@ class EventEmulator(object):
 
     def cleanup(self):
         self._destroy_handle()
+        if self._sinks is not None:
+            self._sinks.close()
 
     def prepare_storage(self, n_frames, frame_ts):
         return None  # HDF5 frame storage is a sink (out of scope); kept for call compatibility
@@ -226,12 +349,13 @@ class EventEmulator(object):
             raise RuntimeError("set_dvs_params must be called before the first frame (or after reset())")
 
     def _destroy_handle(self):
-        if getattr(self, "_h", None):
+        box = getattr(self, "_hbox", None)
+        if box and box[0]:
             try:
-                self._lib.v2e_emu_destroy(self._h)
+                self._lib.v2e_emu_destroy(box[0])
             except Exception:
                 pass
-            self._h = None
+            box[0] = None
 
     # ------------------------------------------------------------------------------------------
     def _stream(self):
@@ -255,7 +379,7 @@ class EventEmulator(object):
         code = {torch.uint8: _lib.U8, torch.float32: _lib.F32, torch.float64: _lib.F64}[t.dtype]
         return t, code
 
-    def _create(self, H, W):
+    def _create(self, H, W, px_offset=0):
         cfg = _lib.V2eEmuCfg()
         cfg.width, cfg.height = W, H
         cfg.per_pixel_thres = 1 if self.sigma_thres > 0 else 0
@@ -274,6 +398,7 @@ class EventEmulator(object):
         cfg.max_frames_per_step = self.max_frames_per_step
         cfg.scidvs = 1 if self.scidvs else 0
         cfg.photoreceptor_noise = 1 if self.photoreceptor_noise else 0
+        cfg.rng_pixel_offset = int(px_offset)
         if self.csdvs_enabled:
             abs_min_tau_p = 1e-9  # emulator.py:1068-1073
             cfg.cs_tau_p_s = abs_min_tau_p if (self.cs_tau_p_ms is None or self.cs_tau_p_ms == 0) \
@@ -284,6 +409,8 @@ class EventEmulator(object):
         with torch.cuda.device(self.device):
             _lib.check(self._lib.v2e_emu_create(ctypes.byref(cfg), ctypes.byref(h)))
             self._h = h
+            if not self.fused:
+                _lib.check(self._lib.v2e_emu_set_option(h, 0, 0))
             lut = _linlog_lut()
             _lib.check(self._lib.v2e_emu_set_linlog_lut(h, ctypes.c_void_p(lut.data_ptr()), self._stream()))
         self._H, self._W = H, W
@@ -363,6 +490,8 @@ class EventEmulator(object):
             ev = self._rows_to_host(total)
         self.t_previous = t_frame
         if ev is not None and len(ev) > 0:
+            if self._sinks is not None:
+                self._sinks.append(ev)
             return ev
         return None
 
@@ -437,26 +566,31 @@ class EventEmulator(object):
                 _lib.check(L.v2e_emu_phase_shot(h, fp, code, t_frame, tp, ctypes.c_void_p(sr_dev.data_ptr()),
                                                 cap, st))
             _lib.check(L.v2e_emu_phase_emit(h, t_frame, tp, ctypes.c_void_p(self._ev_dev.data_ptr()), cap, st))
-            info = (_lib.V2eFrameInfo * 1)()
-            done, rows = ctypes.c_int(0), ctypes.c_uint64(0)
-            rc = L.v2e_emu_collect(h, info, 1, ctypes.byref(done), ctypes.byref(rows), st)
-            if rc == _lib.V2E_E_CAPACITY:
-                # grow and re-run only the emission of this frame
-                self._ensure_event_buffers(int(info[0].n_events) + 1024)
-                ts = (ctypes.c_double * 1)(t_frame)
-                _lib.check(L.v2e_emu_step(h, fp, code, 1, ts, tp, None, None,
-                                          ctypes.c_void_p(self._ev_dev.data_ptr()), self._ev_dev.shape[0], 0,
-                                          0, 1, st))
-                _lib.check(L.v2e_emu_collect(h, info, 1, ctypes.byref(done), ctypes.byref(rows), st))
-            else:
-                _lib.check(rc)
-            fi = info[0]
+            fi = self._collect_one(fp, code, t_frame, tp, st)
             self.last_frame_info = fi
             ev = self._rows_to_host(int(fi.n_events))
         self._account(fi)
         if fi.n_events == 0:
             return None
         return self._canonical_then_shuffle(ev, counts, perms, int(fi.n_shot_on), int(fi.n_shot_off))
+
+    def _collect_one(self, fp, code, t_frame, tp, st):
+        """Control block of the single frame just emitted. On V2E_E_CAPACITY (the frame is counted, its state
+        advanced, nothing emitted) the buffer grows and only the emission is re-run (v2e_emu_step resume)."""
+        L, h = self._lib, self._h
+        info = (_lib.V2eFrameInfo * 1)()
+        done, rows = ctypes.c_int(0), ctypes.c_uint64(0)
+        rc = L.v2e_emu_collect(h, info, 1, ctypes.byref(done), ctypes.byref(rows), st)
+        if rc == _lib.V2E_E_CAPACITY:
+            self._ensure_event_buffers(int(info[0].n_events) + 1024)
+            ts = (ctypes.c_double * 1)(t_frame)
+            _lib.check(L.v2e_emu_step(h, fp, code, 1, ts, tp, None, None,
+                                      ctypes.c_void_p(self._ev_dev.data_ptr()), self._ev_dev.shape[0], 0,
+                                      0, 1, st))
+            _lib.check(L.v2e_emu_collect(h, info, 1, ctypes.byref(done), ctypes.byref(rows), st))
+        else:
+            _lib.check(rc)
+        return info[0]
 
     # pixel-sharded path (SURVEY.md 8e, BASELINE config 5): this rank owns rows [y0, y1) ---------------
     def _band(self, H):
@@ -500,7 +634,7 @@ class EventEmulator(object):
             raise ValueError("more ranks than pixel rows")
         L = self._lib
         if not self._initialized:
-            self._create(hb, W)
+            self._create(hb, W, px_offset=y0 * W)       # Philox counters index the whole frame
             with torch.cuda.device(self.device):
                 _lib.check(L.v2e_emu_first_frame(self._h, ctypes.c_void_p(fr.data_ptr()), code, float(t_frame),
                                                  float(self.t_previous), self._stream()))
@@ -557,10 +691,7 @@ class EventEmulator(object):
                 sr_dev = self._full_then_band(self.rng.rand, H, W, y0, y1).to(self.device)
                 _lib.check(L.v2e_emu_phase_shot(h, fp, code, t_frame, tp, ctypes.c_void_p(sr_dev.data_ptr()), cap, st))
             _lib.check(L.v2e_emu_phase_emit(h, t_frame, tp, ctypes.c_void_p(self._ev_dev.data_ptr()), cap, st))
-            info = (_lib.V2eFrameInfo * 1)()
-            done, rows = ctypes.c_int(0), ctypes.c_uint64(0)
-            _lib.check(L.v2e_emu_collect(h, info, 1, ctypes.byref(done), ctypes.byref(rows), st))
-            fi = info[0]
+            fi = self._collect_one(fp, code, t_frame, tp, st)
             self.last_frame_info = fi
             ev = self._rows_to_host(int(fi.n_events))
         self._account(fi)
@@ -574,6 +705,102 @@ class EventEmulator(object):
             self.exact_order = saved
         ev[:, 2] += y0
         return ev
+
+    def generate_events_band_batch(self, band_frames, t_frames, full_height, return_device=False):
+        """Pixel-sharded, batched (BASELINE config 5 without per-frame host work): band_frames [T, y1-y0, W] uint8,
+        this rank's rows of T consecutive frames. The multi-frame kernels run the whole chunk with per-pixel state in
+        registers; the only exchange is ONE all-reduce(MAX) of the T frame maxima (SURVEY.md 8e "batch as a [T]
+        vector"). A chunk in which the refractory filter would run is replayed frame by frame (one all-reduce per
+        frame), identically on every rank. Needs rng_mode='device' when leak / shot noise is on.
+        Returns (rows [N,4] float32 with global y, offsets [T+1]) like generate_events_batch."""
+        import torch.distributed as dist
+        if self.shard is None:
+            raise RuntimeError("generate_events_band_batch needs shard=(rank, world, group)")
+        if self.rng_mode == "replay" and (self.leak_rate_hz > 0 or self.shot_noise_rate_hz > 0):
+            raise RuntimeError("batched sharded operation with per-frame noise needs rng_mode='device'")
+        rank, world, group = self.shard
+        fr, code = self._to_device_frames(band_frames)
+        H = int(full_height)
+        y0, y1 = self._band(H)
+        if fr.dim() != 3 or fr.shape[1] != y1 - y0:
+            raise ValueError("band_frames must be [T, %d, W]: rows [%d, %d) of every frame" % (y1 - y0, y0, y1))
+        t_frames = [float(t) for t in t_frames]
+        T = fr.shape[0]
+        if len(t_frames) != T:
+            raise ValueError("t_frames length mismatch")
+        for a, b in zip([self.t_previous] + t_frames[:-1], t_frames):
+            if b < a:
+                raise ValueError("this frame time={} must be later than previous frame time={}".format(b, a))
+        L = self._lib
+        out, offs = [], [0]
+        start = 0
+        if not self._initialized:
+            self.frame_counter += 1
+            self._generate_sharded(fr[0], code, t_frames[0], full_height=H)
+            offs.append(0)
+            start = 1
+        f = start
+        total = 0
+        n = (y1 - y0) * fr.shape[2]
+        while f < T:
+            e = min(T, f + self.max_frames_per_step)
+            Tc = e - f
+            chunk = fr[f:e]
+            ts = (ctypes.c_double * Tc)(*t_frames[f:e])
+            fell_back = Tc < 2 or not self.fused
+            if not fell_back:
+                with torch.cuda.device(self.device):
+                    st = self._stream()
+                    self._ensure_event_buffers(self.event_rows_hint or max(2 * n, 1 << 16))
+                    rc = L.v2e_emu_fused_count(self._h, ctypes.c_void_p(chunk.data_ptr()), code, Tc, ts,
+                                               float(self.t_previous), st)
+                    if rc == _lib.V2E_E_UNSUPPORTED:
+                        fell_back = True
+                    else:
+                        _lib.check(rc)
+                        mx = torch.as_tensor(_DevView(L.v2e_emu_max_vec_dev(self._h), (Tc,), "<i4", self),
+                                             device=self.device)
+                        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+                        info = (_lib.V2eFrameInfo * Tc)()
+                        done, rows = ctypes.c_int(0), ctypes.c_uint64(0)
+                        while True:
+                            _lib.check(L.v2e_emu_fused_emit(self._h, ctypes.c_void_p(self._ev_dev.data_ptr()),
+                                                            self._ev_dev.shape[0], 0, st))
+                            rc = L.v2e_emu_collect(self._h, info, Tc, ctypes.byref(done), ctypes.byref(rows), st)
+                            if rc != _lib.V2E_E_CAPACITY:
+                                break
+                            need = max(int(info[k].ev_base) + int(info[k].n_events) for k in range(Tc))
+                            self._ev_dev = None
+                            self._ensure_event_buffers(2 * need)
+                        if rc == _lib.V2E_E_FALLBACK:
+                            fell_back = True
+                        else:
+                            _lib.check(rc)
+                            for k in range(Tc):
+                                self._account(info[k])
+                                offs.append(total + int(info[k].ev_base) + int(info[k].n_events))
+                            nrows = int(rows.value)
+                            ev = self._ev_dev[:nrows].clone()
+                            ev[:, 2] += y0
+                            out.append(ev)
+                            total += nrows
+                            self.last_frame_info = info[Tc - 1]
+                            self.t_previous = t_frames[e - 1]
+                            self.frame_counter += Tc
+            if fell_back:
+                for k in range(f, e):
+                    self.frame_counter += 1
+                    evk = self._generate_sharded(fr[k], code, t_frames[k], full_height=H)
+                    if evk is not None:
+                        out.append(torch.from_numpy(evk).to(self.device))
+                        total += len(evk)
+                    offs.append(total)
+            f = e
+        offs = np.asarray(offs, np.int64)
+        rows = torch.cat(out, 0) if out else torch.zeros((0, 4), dtype=torch.float32, device=self.device)
+        if return_device:
+            return rows, offs
+        return rows.cpu().numpy(), offs
 
     def _canonical_then_shuffle(self, ev, counts, perms, shot_on, shot_off):
         """Device rows of one (iteration, polarity) group come in no particular order. The reference
@@ -641,7 +868,9 @@ class EventEmulator(object):
                 # grow (keeping rows already written) and resume at the frame that did not fit
                 first, resume = done.value, 1
                 base = int(info[first].ev_base)
-                need = base + int(info[first].n_events)
+                # a multi-frame (fused) step reports the rows of every frame of the chunk; the frame-by-frame
+                # kernels only those up to the frame that did not fit
+                need = max(int(info[f].ev_base) + int(info[f].n_events) for f in range(first, T))
                 old = self._ev_dev
                 self._ev_dev = None
                 self._ensure_event_buffers(max(2 * need, 2 * old.shape[0]))
@@ -708,7 +937,8 @@ class EventEmulator(object):
         f64 = (which in (0, 1, 7) and self._state_f64) or which == 6
         view = _DevView(ptr, (self._H, self._W), "<f8" if f64 else "<f4", self)
         torch.cuda.current_stream(self.device).synchronize()
-        return torch.as_tensor(view, device=self.device)
+        # a copy: the library owns the memory and frees it at reset() / cleanup()
+        return torch.as_tensor(view, device=self.device).clone()
 
     lp_log_frame = property(lambda self: self._state("lp_log_frame"))
     base_log_frame = property(lambda self: self._state("base_log_frame"))

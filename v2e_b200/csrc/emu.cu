@@ -87,6 +87,7 @@ struct EmuDev {                         // passed by value to every kernel
     FrameCtrl *ctrl;                    // [max_slots+1]
     uint32_t *hist_pre, *hist_post, *segoff, *cursor;   // [max_slots][seg_stride]
     int32_t *abort_flag;                // [2]: status, slot
+    unsigned long long *chain_base;     // row at which the frames after a multi-frame chunk continue
 };
 
 struct FrameParams {
@@ -1557,6 +1558,7 @@ emu_fused_plan_kernel(EmuDev d, const FrameParams *__restrict__ fp, int T, uint6
             base += s_tot[f];
         }
         d.ctrl[T].ev_base = base;
+        *d.chain_base = base;
         if (s_bad != 0x7fffffff) {
             if (atomicCAS(d.abort_flag, 0, kFusedFallback) == 0) d.abort_flag[1] = s_bad;
         } else if (base > capacity) {
@@ -1659,6 +1661,10 @@ __global__ void emu_null_kernel() {}
 __global__ void emu_begin_step_kernel(EmuDev d, int slot, uint64_t ev_base) {
     d.ctrl[slot].ev_base = ev_base;
 }
+// the frame-by-frame kernels continue where a multi-frame chunk of the same step stopped writing
+__global__ void emu_chain_step_kernel(EmuDev d, int slot) {
+    d.ctrl[slot].ev_base = *d.chain_base;
+}
 
 __global__ void __launch_bounds__(kThreads) emu_plan_kernel(EmuDev d, FrameParams p, int slot) {
     plan_frame(d, p, slot);
@@ -1704,6 +1710,7 @@ struct V2eEmu {
     FrameParams *fp_dev;        // [max_slots]
     int32_t *max_vec;           // [max_slots] frame maxima, contiguous (all-reduced over ranks when sharded)
     int last_fused;             // the last step went through the fused path: 1 = v2e_emu_step, 2 = phase functions
+    int fused_T;                // frames of that step the fused kernels covered (the rest went frame by frame)
     struct {                    // arguments of that step, for the frame-by-frame replay of a rejected chunk
         const void *frames; int dtype, T; double t_previous; float *events; uint64_t capacity, ev_base_start;
         double *t_frames;       // [max_slots]
@@ -1880,6 +1887,7 @@ extern "C" int v2e_emu_create(const V2eEmuCfg *cfg, V2eEmu **out) {
     ALLOC(d.act_count, slots * d.n_blocks * sizeof(uint32_t));
     ALLOC(d.act_list, (size_t)d.n_blocks * d.seg_px * sizeof(uint32_t));
     ALLOC(d.abort_flag, 2 * sizeof(int32_t));
+    ALLOC(d.chain_base, sizeof(unsigned long long));
 #undef ALLOC
     if (cudaMallocHost((void **)&h->ctrl_host, (slots + 1) * sizeof(FrameCtrl)) != cudaSuccess ||
         cudaMallocHost((void **)&h->abort_host, 2 * sizeof(int32_t)) != cudaSuccess) {
@@ -1899,7 +1907,7 @@ extern "C" int v2e_emu_destroy(V2eEmu *h) {
     for (void *p : fused_ptrs) if (p) cudaFree(p);
     void *ptrs[] = {d.hp, d.prev_photo, d.tau_arr, d.noise_arr, d.pr_eff,
                     d.lp, d.base, d.rec, d.pos_thres, d.neg_thres, d.noise_rate, d.tmem, d.surround,
-                    h->lut_dev, d.ctrl, d.hist_pre, d.hist_post, d.segoff, d.cursor, d.abort_flag, d.act_list, d.act_count, d.surround2, d.cs_cur, d.cs_max};
+                    h->lut_dev, d.ctrl, d.hist_pre, d.hist_post, d.segoff, d.cursor, d.abort_flag, d.chain_base, d.act_list, d.act_count, d.surround2, d.cs_cur, d.cs_max};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->ctrl_host) cudaFreeHost(h->ctrl_host);
     if (h->abort_host) cudaFreeHost(h->abort_host);
@@ -2123,7 +2131,7 @@ static void enqueue_null_bracket(V2eEmu *h, int slot, cudaStream_t st) {
     emu_null_kernel<<<1, 32, 0, st>>>();
 }
 
-static int reset_slots(V2eEmu *h, int first, int count, cudaStream_t st) {
+static int reset_slots(V2eEmu *h, int first, int count, cudaStream_t st, bool clear_abort = true) {
     EmuDev &d = h->d;
     size_t off = (size_t)first * d.seg_stride * 4, bytes = (size_t)count * d.seg_stride * 4;
     CU(cudaMemsetAsync((char *)d.hist_pre + off, 0, bytes, st));
@@ -2131,12 +2139,13 @@ static int reset_slots(V2eEmu *h, int first, int count, cudaStream_t st) {
     CU(cudaMemsetAsync((char *)d.cursor + off, 0, bytes, st));
     CU(cudaMemsetAsync(d.ctrl + first, 0, (size_t)(count + 1) * sizeof(FrameCtrl), st));
     CU(cudaMemsetAsync(d.act_count + (size_t)first * d.n_blocks, 0, (size_t)count * d.n_blocks * sizeof(uint32_t), st));
-    CU(cudaMemsetAsync(d.abort_flag, 0, 2 * sizeof(int32_t), st));
+    if (clear_abort) CU(cudaMemsetAsync(d.abort_flag, 0, 2 * sizeof(int32_t), st));
     return V2E_OK;
 }
 
 
 // ---- fused multi-frame path, host side ------------------------------------------------------------
+constexpr uint64_t kChainBase = ~0ull;      // step_classic: start at the row the multi-frame chunk ended at
 static int fused_groups(const EmuDev &d) { return (d.units + kFusedGroup - 1) / kFusedGroup; }
 
 static bool fused_config_ok(const V2eEmu *h, int dtype) {
@@ -2238,7 +2247,7 @@ static int enqueue_fused_emit(V2eEmu *h, int T, float *events, uint64_t capacity
                               const int32_t *max_vec, bool commit, cudaStream_t st) {
     const EmuDev &d = h->d;
     {
-        ProfScope ps(h, 0, 1, st);
+        ProfScope ps(h, 1, 1, st);       // slot 1: v2e_emu_profile_read sums count + plan under "filter"
         emu_fused_plan_kernel<<<1, kThreads, (size_t)T * sizeof(uint32_t), st>>>(d, h->fp_dev, T, ev_base_start, capacity, max_vec);
     }
     {
@@ -2247,6 +2256,7 @@ static int enqueue_fused_emit(V2eEmu *h, int T, float *events, uint64_t capacity
                                                                          h->rec_cnt, h->blk_cnt, (float4 *)events);
     }
     if (commit) {
+        ProfScope ps(h, 1, 2, st);       // emit + commit under "emit"
         const size_t n16 = (size_t)d.units * kUnitPx * h->state_elem / 16;
         emu_fused_commit_kernel<<<296, kThreads, 0, st>>>(d, (const uint4 *)h->lp_alt, (const uint4 *)h->base_alt, n16);
     }
@@ -2258,6 +2268,20 @@ static void remember_step(V2eEmu *h, const void *frames, int dtype, int T, const
     h->ls.frames = frames; h->ls.dtype = dtype; h->ls.T = T; h->ls.t_previous = t_previous;
     h->ls.events = events; h->ls.capacity = capacity; h->ls.ev_base_start = ev_base_start;
     if (t_frames != h->ls.t_frames) memcpy(h->ls.t_frames, t_frames, sizeof(double) * (size_t)T);
+}
+
+// multi-frame kernels over the first Tf frames of the remembered step (h->ls), Philox frame indices from step_base
+static int fused_run(V2eEmu *h, int Tf, cudaStream_t st) {
+    int rc;
+    if ((rc = reset_slots(h, 0, Tf, st))) return rc;
+    if (h->profile) { memset(h->prof_used, 0, (size_t)h->d.max_slots * kProfKinds); h->prof_frames = Tf; }
+    if ((rc = fused_upload_params(h, Tf, h->ls.t_frames, h->ls.t_previous, h->step_base, h->ls.capacity, st))) return rc;
+    if ((rc = enqueue_fused_count(h, h->ls.frames, Tf, st))) return rc;
+    if ((rc = enqueue_fused_emit(h, Tf, h->ls.events, h->ls.capacity, h->ls.ev_base_start, nullptr, true, st))) return rc;
+    CU(cudaGetLastError());
+    h->last_fused = 1;
+    h->fused_T = Tf;
+    return V2E_OK;
 }
 
 extern "C" int v2e_emu_set_option(V2eEmu *h, int option, int value) {
@@ -2299,6 +2323,7 @@ extern "C" int v2e_emu_fused_count(V2eEmu *h, const void *frames, int dtype, int
     remember_step(h, frames, dtype, T, t_frames, t_previous, nullptr, 0, 0);
     h->last_T = T;
     h->last_fused = 2;
+    h->fused_T = T;
     h->n_fused_chunks++;
     return V2E_OK;
 }
@@ -2338,7 +2363,8 @@ static int step_classic(V2eEmu *h, const void *frames, int dtype, int T, const d
         if (first + 1 < T && (rc = reset_slots(h, first + 1, T - first - 1, st))) return rc;
         CU(cudaMemsetAsync(d.abort_flag, 0, 2 * sizeof(int32_t), st));
     } else {
-        if ((rc = reset_slots(h, first, T - first, st))) return rc;
+        // continuing after a multi-frame chunk of the same step: its capacity abort (if any) must stay sticky
+        if ((rc = reset_slots(h, first, T - first, st, ev_base_start != kChainBase))) return rc;
     }
     if (resume_emit && h->pr_T == 0) h->pr_T = h->pr_T_last;
     if (h->profile) { memset(h->prof_used, 0, (size_t)d.max_slots * kProfKinds); h->prof_frames = T - first; }
@@ -2346,7 +2372,8 @@ static int step_classic(V2eEmu *h, const void *frames, int dtype, int T, const d
         h->step_base = h->frame_counter;
         h->frame_counter += (uint32_t)T;
     }
-    emu_begin_step_kernel<<<1, 1, 0, st>>>(d, first, ev_base_start);
+    if (ev_base_start == kChainBase) emu_chain_step_kernel<<<1, 1, 0, st>>>(d, first);
+    else emu_begin_step_kernel<<<1, 1, 0, st>>>(d, first, ev_base_start);
     for (int f = first; f < T; f++) {
         double tp = f == 0 ? t_previous : t_frames[f - 1];
         if (t_frames[f] < tp) return fail(V2E_E_INVALID, "frame times must be non-decreasing");
@@ -2389,12 +2416,18 @@ extern "C" int v2e_emu_step(V2eEmu *h, const void *frames, int dtype, int T, con
     const EmuDev &d = h->d;
     int rc;
     if (resume_emit && h->last_fused == 1 && first == 0) {
-        // capacity abort of a fused chunk: the records are still there; plan again into the larger buffer
+        // capacity abort inside the multi-frame part of the step: its records are still there; plan again into the
+        // larger buffer, then the frames that follow it (none of them ran: the abort is sticky)
         CU(cudaMemsetAsync(d.abort_flag, 0, 2 * sizeof(int32_t), st));
-        CU(cudaMemsetAsync(d.cursor, 0, (size_t)T * d.seg_stride * 4, st));
+        CU(cudaMemsetAsync(d.cursor, 0, (size_t)h->fused_T * d.seg_stride * 4, st));
         remember_step(h, frames, dtype, T, t_frames, t_previous, events, capacity, ev_base_start);
-        if ((rc = enqueue_fused_emit(h, T, events, capacity, ev_base_start, nullptr, true, st))) return rc;
+        if ((rc = enqueue_fused_emit(h, h->fused_T, events, capacity, ev_base_start, nullptr, true, st))) return rc;
         CU(cudaGetLastError());
+        if (h->fused_T < T) {
+            h->frame_counter = h->step_base;
+            return step_classic(h, frames, dtype, T, t_frames, t_previous, nullptr, nullptr, events, capacity,
+                                kChainBase, h->fused_T, 0, stream);
+        }
         return V2E_OK;
     }
     const bool want_fused = h->fused_enable && T >= 2 && first == 0 && !resume_emit && !leak_randn && !shot_rand &&
@@ -2402,17 +2435,11 @@ extern "C" int v2e_emu_step(V2eEmu *h, const void *frames, int dtype, int T, con
     if (want_fused) {
         if ((rc = fused_alloc(h))) return rc;
         if (h->fused_max_T >= T) {
-            if ((rc = reset_slots(h, 0, T, st))) return rc;
-            if (h->profile) { memset(h->prof_used, 0, (size_t)d.max_slots * kProfKinds); h->prof_frames = T; }
             h->step_base = h->frame_counter;
-            h->frame_counter += (uint32_t)T;
-            if ((rc = fused_upload_params(h, T, t_frames, t_previous, h->step_base, capacity, st))) return rc;
-            if ((rc = enqueue_fused_count(h, frames, T, st))) return rc;
-            if ((rc = enqueue_fused_emit(h, T, events, capacity, ev_base_start, nullptr, true, st))) return rc;
-            CU(cudaGetLastError());
             remember_step(h, frames, dtype, T, t_frames, t_previous, events, capacity, ev_base_start);
+            if ((rc = fused_run(h, T, st))) return rc;
+            h->frame_counter = h->step_base + (uint32_t)T;
             h->last_T = T;
-            h->last_fused = 1;
             h->n_fused_chunks++;
             return V2E_OK;
         }
@@ -2430,16 +2457,29 @@ extern "C" int v2e_emu_collect(V2eEmu *h, V2eFrameInfo *info, int T, int *frames
     CU(cudaMemcpyAsync(h->abort_host, h->d.abort_flag, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     if (h->abort_host[0] == kFusedFallback) {
-        // the fused chunk was rejected on the device (refractory filter active or more than kFusedMaxN events of
-        // one pixel in some frame): nothing was emitted or committed. Same frames, same Philox frame indices,
-        // frame by frame:
+        // the multi-frame chunk was rejected on the device at frame fb (refractory filter active, or more than
+        // kFusedMaxN events of one pixel): nothing was emitted or committed. The frames before fb go through the
+        // multi-frame kernels again (accepted by construction), the rest frame by frame -- same frames, same Philox
+        // frame indices, continuing at the row where the first part ends.
+        const int fb = h->abort_host[1];
         h->n_fused_rejected++;
-        h->frame_counter = h->step_base;
         const int mode = h->last_fused;
         h->last_fused = 0;
-        if (mode == 2) return fail(V2E_E_FALLBACK, "fused chunk rejected: replay it frame by frame");
-        int rc = step_classic(h, h->ls.frames, h->ls.dtype, h->ls.T, h->ls.t_frames, h->ls.t_previous, nullptr, nullptr,
+        h->frame_counter = h->step_base;
+        if (mode == 2) {
+            if (frames_done) *frames_done = fb;
+            return fail(V2E_E_FALLBACK, "fused chunk rejected: replay it frame by frame");
+        }
+        int rc;
+        if (fb >= 2) {
+            if ((rc = fused_run(h, fb, st))) return rc;
+            h->frame_counter = h->step_base;
+            rc = step_classic(h, h->ls.frames, h->ls.dtype, h->ls.T, h->ls.t_frames, h->ls.t_previous, nullptr, nullptr,
+                              h->ls.events, h->ls.capacity, kChainBase, fb, 0, stream);
+        } else {
+            rc = step_classic(h, h->ls.frames, h->ls.dtype, h->ls.T, h->ls.t_frames, h->ls.t_previous, nullptr, nullptr,
                               h->ls.events, h->ls.capacity, h->ls.ev_base_start, 0, 0, stream);
+        }
         if (rc) return rc;
         CU(cudaMemcpyAsync(h->ctrl_host, h->d.ctrl, (size_t)(T + 1) * sizeof(FrameCtrl), cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(h->abort_host, h->d.abort_flag, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -2489,6 +2529,7 @@ extern "C" int v2e_emu_time_fused(V2eEmu *h, const void *frames, int dtype, int 
         if (!rc) rc = enqueue_fused_emit(h, T, events, capacity, 0, nullptr, false, st);
     }
     cudaEventRecord(e[1], st);
+    if (!rc) rc = reset_slots(h, 0, T, st);
     cudaEventRecord(e[2], st);
     for (int k = 0; k < K && !rc; k++)
         rc = h->d.state_f64 ? launch_fused_update<double>(h, (const uint8_t *)frames, T, st)

@@ -733,68 +733,78 @@ class EventEmulator(object):
                 raise ValueError("this frame time={} must be later than previous frame time={}".format(b, a))
         L = self._lib
         out, offs = [], [0]
-        start = 0
-        if not self._initialized:
-            self.frame_counter += 1
-            self._generate_sharded(fr[0], code, t_frames[0], full_height=H)
-            offs.append(0)
-            start = 1
-        f = start
-        total = 0
+        state = {"total": 0}
         n = (y1 - y0) * fr.shape[2]
+
+        def fused_piece(a, b):
+            """Multi-frame kernels over frames [a, b). Returns None when accepted, else the index (relative to a)
+            of the first frame that breaks the assumption (-1: the configuration does not qualify)."""
+            Tc = b - a
+            chunk = fr[a:b]
+            ts = (ctypes.c_double * Tc)(*t_frames[a:b])
+            with torch.cuda.device(self.device):
+                st = self._stream()
+                self._ensure_event_buffers(self.event_rows_hint or max(2 * n, 1 << 16))
+                rc = L.v2e_emu_fused_count(self._h, ctypes.c_void_p(chunk.data_ptr()), code, Tc, ts,
+                                           float(self.t_previous), st)
+                if rc == _lib.V2E_E_UNSUPPORTED:
+                    return -1
+                _lib.check(rc)
+                # the one exchange of the chunk: frame maxima (emulator.py:773-775), MAX over the ranks
+                mx = torch.as_tensor(_DevView(L.v2e_emu_max_vec_dev(self._h), (Tc,), "<i4", self), device=self.device)
+                dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+                info = (_lib.V2eFrameInfo * Tc)()
+                done, rows = ctypes.c_int(0), ctypes.c_uint64(0)
+                while True:
+                    _lib.check(L.v2e_emu_fused_emit(self._h, ctypes.c_void_p(self._ev_dev.data_ptr()),
+                                                    self._ev_dev.shape[0], 0, st))
+                    rc = L.v2e_emu_collect(self._h, info, Tc, ctypes.byref(done), ctypes.byref(rows), st)
+                    if rc != _lib.V2E_E_CAPACITY:
+                        break
+                    need = max(int(info[k].ev_base) + int(info[k].n_events) for k in range(Tc))
+                    self._ev_dev = None
+                    self._ensure_event_buffers(2 * need)
+                if rc == _lib.V2E_E_FALLBACK:
+                    return int(done.value)
+                _lib.check(rc)
+                for k in range(Tc):
+                    self._account(info[k])
+                    offs.append(state["total"] + int(info[k].ev_base) + int(info[k].n_events))
+                nrows = int(rows.value)
+                ev = self._ev_dev[:nrows].clone()
+                ev[:, 2] += y0
+                out.append(ev)
+                state["total"] += nrows
+                self.last_frame_info = info[Tc - 1]
+                self.t_previous = t_frames[b - 1]
+                self.frame_counter += Tc
+            return None
+
+        def frame_by_frame(a, b):
+            for k in range(a, b):
+                self.frame_counter += 1
+                evk = self._generate_sharded(fr[k], code, t_frames[k], full_height=H)
+                if evk is not None:
+                    out.append(torch.from_numpy(evk).to(self.device))
+                    state["total"] += len(evk)
+                offs.append(state["total"])
+
+        f = 0
+        if not self._initialized:
+            frame_by_frame(0, 1)
+            f = 1
         while f < T:
             e = min(T, f + self.max_frames_per_step)
-            Tc = e - f
-            chunk = fr[f:e]
-            ts = (ctypes.c_double * Tc)(*t_frames[f:e])
-            fell_back = Tc < 2 or not self.fused
-            if not fell_back:
-                with torch.cuda.device(self.device):
-                    st = self._stream()
-                    self._ensure_event_buffers(self.event_rows_hint or max(2 * n, 1 << 16))
-                    rc = L.v2e_emu_fused_count(self._h, ctypes.c_void_p(chunk.data_ptr()), code, Tc, ts,
-                                               float(self.t_previous), st)
-                    if rc == _lib.V2E_E_UNSUPPORTED:
-                        fell_back = True
-                    else:
-                        _lib.check(rc)
-                        mx = torch.as_tensor(_DevView(L.v2e_emu_max_vec_dev(self._h), (Tc,), "<i4", self),
-                                             device=self.device)
-                        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
-                        info = (_lib.V2eFrameInfo * Tc)()
-                        done, rows = ctypes.c_int(0), ctypes.c_uint64(0)
-                        while True:
-                            _lib.check(L.v2e_emu_fused_emit(self._h, ctypes.c_void_p(self._ev_dev.data_ptr()),
-                                                            self._ev_dev.shape[0], 0, st))
-                            rc = L.v2e_emu_collect(self._h, info, Tc, ctypes.byref(done), ctypes.byref(rows), st)
-                            if rc != _lib.V2E_E_CAPACITY:
-                                break
-                            need = max(int(info[k].ev_base) + int(info[k].n_events) for k in range(Tc))
-                            self._ev_dev = None
-                            self._ensure_event_buffers(2 * need)
-                        if rc == _lib.V2E_E_FALLBACK:
-                            fell_back = True
-                        else:
-                            _lib.check(rc)
-                            for k in range(Tc):
-                                self._account(info[k])
-                                offs.append(total + int(info[k].ev_base) + int(info[k].n_events))
-                            nrows = int(rows.value)
-                            ev = self._ev_dev[:nrows].clone()
-                            ev[:, 2] += y0
-                            out.append(ev)
-                            total += nrows
-                            self.last_frame_info = info[Tc - 1]
-                            self.t_previous = t_frames[e - 1]
-                            self.frame_counter += Tc
-            if fell_back:
-                for k in range(f, e):
-                    self.frame_counter += 1
-                    evk = self._generate_sharded(fr[k], code, t_frames[k], full_height=H)
-                    if evk is not None:
-                        out.append(torch.from_numpy(evk).to(self.device))
-                        total += len(evk)
-                    offs.append(total)
+            bad = -1 if (e - f < 2 or not self.fused) else fused_piece(f, e)
+            if bad is not None:
+                # rejected (identically on every rank): the frames before the first offending one go through the
+                # multi-frame kernels again, the rest of the chunk frame by frame (one all-reduce per frame)
+                g = f
+                if bad >= 2:
+                    again = fused_piece(f, f + bad)
+                    assert again is None, "a prefix of a rejected chunk must be accepted"
+                    g = f + bad
+                frame_by_frame(g, e)
             f = e
         offs = np.asarray(offs, np.int64)
         rows = torch.cat(out, 0) if out else torch.zeros((0, 4), dtype=torch.float32, device=self.device)

@@ -3,10 +3,11 @@ import ctypes, sys, numpy as np, torch
 sys.path.insert(0, '.')
 import bench
 from v2e_b200 import EventEmulator, _lib
+only_fused = '--fused-only' in sys.argv
 for (H, W, T) in ((720, 1280, 80), (260, 346, 300)):
     fr = bench.source_clip(H, W, T + 1, px_per_frame=1)          # loops: frame T equals frame 0
     frd = torch.from_numpy(fr).cuda()
-    for fused in (True, False):
+    for fused in ((True,) if only_fused else (True, False)):
         em = EventEmulator(device="cuda:0", rng_mode="device", seed=3, max_frames_per_step=T, fused=fused, **bench.CLI_DEFAULTS)
         em.event_rows_hint = 40 * 1024 * 1024
         k = 0

@@ -24,6 +24,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/v2e_b200.h"
@@ -222,29 +223,18 @@ __device__ __forceinline__ bool shot_candidate(uint32_t pref, uint32_t pref_lo) 
     return pref < pref_lo || pref >= 4096u - pref_lo;
 }
 // noise of the 4 consecutive pixels starting at GLOBAL index g0: one call when g0 is quad-aligned (always, unless a
-// row band of a sharded clip starts at an odd offset), two otherwise
-__device__ __forceinline__ void noise_px4(uint64_t seed, uint32_t g0, uint32_t frame_index, float n[4], uint32_t pref[4]) {
+// row band of a sharded clip starts at an odd offset); otherwise two calls, out of line
+__device__ __noinline__ void noise_px4_unaligned(uint64_t seed, uint32_t g0, uint32_t frame_index, float *n, uint32_t *pref) {
     const uint32_t q = g0 >> 2, r = g0 & 3u;
-    if (r == 0) {
-        noise_quad(seed, q, frame_index, n, pref);
-        return;
-    }
-    float na[4], nb[4];
-    uint32_t pa[4], pb[4];
+    float na[8];
+    uint32_t pa[8];
     noise_quad(seed, q, frame_index, na, pa);
-    noise_quad(seed, q + 1, frame_index, nb, pb);
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const uint32_t j = r + (uint32_t)k;
-        float nv = 0.f;
-        uint32_t pv = 0u;
-#pragma unroll
-        for (int m = 0; m < 4; m++) {
-            if ((j & 3u) == (uint32_t)m) { nv = j < 4u ? na[m] : nb[m]; pv = j < 4u ? pa[m] : pb[m]; }
-        }
-        n[k] = nv;
-        pref[k] = pv;
-    }
+    noise_quad(seed, q + 1, frame_index, na + 4, pa + 4);
+    for (int k = 0; k < 4; k++) { n[k] = na[r + k]; pref[k] = pa[r + k]; }
+}
+__device__ __forceinline__ void noise_px4(uint64_t seed, uint32_t g0, uint32_t frame_index, float n[4], uint32_t pref[4]) {
+    if ((g0 & 3u) == 0) noise_quad(seed, g0 >> 2, frame_index, n, pref);
+    else noise_px4_unaligned(seed, g0, frame_index, n, pref);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1300,7 +1290,6 @@ struct FusedFrame {                     // what pass 1 needs of one frame
     uint32_t frame_index, pref_lo, pad;
 };
 static_assert(sizeof(FusedFrame) == 32, "FusedFrame layout");
-constexpr int kFusedPrefetch = 4;
 constexpr int kFusedGroup = 64;                     // 128-pixel units per block of the count / emit kernels
 constexpr int kFusedMaxN = 31;                      // largest per-frame maximum the fused plan accepts
 constexpr int kFusedFallback = 100;                 // abort_flag value: chunk rejected (internal)
@@ -1310,53 +1299,80 @@ __device__ __forceinline__ uint32_t make_rec16(int px_local, int neg, int flags,
     return (uint32_t)px_local | ((uint32_t)neg << 7) | ((uint32_t)flags << 8) | ((uint32_t)(mag > 63 ? 63 : mag) << 10);
 }
 
-template <typename S, bool FAST>
-__global__ void __launch_bounds__(kThreads, 3)
+// rare paths of pass 1, kept out of line so that the frame loop stays small (instruction cache)
+template <typename S>
+__device__ __noinline__ int32_t fused_deep_count(S a, S b) {
+    int32_t mag = div_floor_count<S>(a, b);
+    return mag > kRecMaxCount ? kRecMaxCount : mag;
+}
+// (scalar arguments: a reference to the kernel-parameter struct would force a copy of it into local memory)
+__device__ __noinline__ int fused_shot_flags(uint64_t seed, double shot_inten_m1, int per_pixel_thres, double pos_nom,
+                                             double neg_nom, double shot_c, uint32_t gpx, uint32_t frame_index,
+                                             uint32_t pref, int code, float thp, float thn) {
+    const float r = shot_uniform(seed, gpx >> 2, frame_index, (int)(gpx & 3u), pref);
+    EmuDev dd;
+    dd.shot_inten_m1 = shot_inten_m1;
+    dd.per_pixel_thres = per_pixel_thres;
+    dd.pos_nom = pos_nom;
+    dd.neg_nom = neg_nom;
+    return shot_flags(dd, shot_c, (double)code, r, thp, thn);
+}
+
+// frame bytes of a quad that is not 4-byte aligned in its frame, or crosses the end of the frame
+__device__ __noinline__ uint32_t fused_load_codes_slow(const uint8_t *pf, int valid) {
+    uint32_t v = 0;
+    for (int k = 0; k < valid; k++) v |= (uint32_t)pf[k] << (8 * k);
+    return v;
+}
+
+// WARPS warps per block, MINB blocks per SM: the register budget / occupancy / tail trade-off is picked on the host
+// (launch_fused_update). Units are dealt evenly to blocks and, inside a block, to warps.
+template <typename S, bool FAST, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
 emu_fused_update_kernel(EmuDev d, const FusedFrame *__restrict__ ff, const uint8_t *__restrict__ frames, int T,
                         S *__restrict__ lp_out, S *__restrict__ base_out, uint16_t *__restrict__ rec_list,
                         uint32_t *__restrict__ rec_cnt) {
     const bool f_pp = FAST || d.per_pixel_thres, f_leak = FAST || d.leak_on, f_shot = FAST || d.shot_on;
     constexpr bool f_lp = sizeof(S) == 8;        // no hdr here: float64 state <=> the low-pass is on
     extern __shared__ __align__(16) unsigned char s_dyn[];
-    FusedFrame *s_ff = (FusedFrame *)s_dyn;
-    __shared__ double s_ln[256];                 // lin_log(code), float32 value widened
-    __shared__ double s_in[256];                 // inten01(code) = (code + 20) / 275 (emulator_utils.py:48-54)
+    const FusedFrame *s_ff = (const FusedFrame *)s_dyn;
+    __shared__ double2 s_tab[256];               // x: lin_log(code) (float32 value widened), y: inten01(code) =
+                                                 // (code + 20) / 275 (emulator_utils.py:48-54)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     {
         const uint4 *src = (const uint4 *)ff;
         uint4 *dst = (uint4 *)s_dyn;
-        for (int i = tid; i < T * 2; i += kThreads) dst[i] = src[i];
-        s_ln[tid] = (double)d.lut[tid];
-        s_in[tid] = ((double)tid + 20.0) / 275.0;
+        for (int i = tid; i < T * 2; i += WARPS * 32) dst[i] = src[i];
+        for (int i = tid; i < 256; i += WARPS * 32) s_tab[i] = make_double2((double)d.lut[i], ((double)i + 20.0) / 275.0);
     }
     __syncthreads();
     if (*(volatile int32_t *)d.abort_flag) return;
-    const int u0 = (int)(((long long)blockIdx.x * d.units) / d.n_blocks);
-    const int u1 = (int)(((long long)(blockIdx.x + 1) * d.units) / d.n_blocks);
+    const int u0 = (int)(((long long)blockIdx.x * d.units) / gridDim.x);
+    const int u1 = (int)(((long long)(blockIdx.x + 1) * d.units) / gridDim.x);
     const size_t n = (size_t)d.n;
-    for (int unit = u0 + warp; unit < u1; unit += kWarps) {
+    const bool use_rng = (f_leak || f_shot) && d.rng_mode == 1;
+    const S tp_nom = (S)d.pos_nom, tn_nom = (S)d.neg_nom;
+    // every frame's row of bytes at a quad is 4-byte aligned iff the frame size is a multiple of 4 (and the base is)
+    const bool al = ((n & 3) == 0) && ((((uintptr_t)frames) & 3) == 0);
+    for (int unit = u0 + warp; unit < u1; unit += WARPS) {
         const int i0 = unit * kUnitPx + lane * kVec;
-        const bool t_on = i0 < d.n;
-        const bool full = i0 + 4 <= d.n;
+        const int valid = i0 < d.n ? min(4, d.n - i0) : 0;          // pixels of this quad inside the frame
+        const uint8_t *pf0 = frames + i0;
         auto load_codes = [&](int f) -> uint32_t {
-            if (!t_on) return 0u;
-            const uint8_t *pf = frames + (size_t)f * n + i0;
-            if (full && (((uintptr_t)pf) & 3) == 0) return __ldg((const uint32_t *)pf);
-            uint32_t v = 0;
-#pragma unroll
-            for (int k = 0; k < 4; k++) if (i0 + k < d.n) v |= (uint32_t)pf[k] << (8 * k);
-            return v;
+            const uint8_t *pf = pf0 + (size_t)f * n;
+            if (al && valid == 4) return __ldg((const uint32_t *)pf);
+            return fused_load_codes_slow(pf, valid);
         };
-        uint32_t ring[kFusedPrefetch];
-#pragma unroll
-        for (int q = 0; q < kFusedPrefetch; q++) ring[q] = q < T ? load_codes(q) : 0u;
-        // per-pixel state -> registers for the whole clip chunk
+        // the next frame's bytes are requested before this frame's arithmetic: a frame takes a warp thousands of
+        // cycles, one frame of look-ahead hides the load
+        uint32_t c_next = load_codes(0);
+        // per-pixel state -> registers for the whole chunk
         S lp[4] = {(S)0, (S)0, (S)0, (S)0}, base[4] = {(S)0, (S)0, (S)0, (S)0};
         float thp[4], thn[4], lnr[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int k = 0; k < 4; k++) { thp[k] = (float)d.pos_nom; thn[k] = (float)d.neg_nom; }
-        if (t_on) {
+        if (valid) {
             if (f_lp) ld4((const S *)d.lp, i0, lp);
             ld4((const S *)d.base, i0, base);
             if (f_pp) { ld4(d.pos_thres, i0, thp); ld4(d.neg_thres, i0, thn); }
@@ -1367,85 +1383,78 @@ emu_fused_update_kernel(EmuDev d, const FusedFrame *__restrict__ ff, const uint8
             }
         }
         const uint32_t g0 = (uint32_t)i0 + d.px_off;
-        const bool use_rng = (f_leak || f_shot) && d.rng_mode == 1;
-        for (int fb = 0; fb < T; fb += kFusedPrefetch) {
+        uint16_t *seg = rec_list + (size_t)unit * kUnitPx;               // + f * units * kUnitPx per frame
+        uint32_t *cntp = rec_cnt + unit;
+        const size_t seg_stride = (size_t)d.units * kUnitPx;
+#pragma unroll 1
+        for (int f = 0; f < T; f++) {
+            const uint32_t codes = c_next;
+            if (f + 1 < T) c_next = load_codes(f + 1);
+            const double eps_scale = s_ff[f].eps_scale;
+            const float dt_f = s_ff[f].dt_f;
+            const uint32_t frame_index = s_ff[f].frame_index, pref_lo = s_ff[f].pref_lo;
+            uint32_t r16[4];
+            float lr[4] = {0.f, 0.f, 0.f, 0.f};
+            uint32_t pref[4] = {0u, 0u, 0u, 0u};
+            if (use_rng) noise_px4(d.seed, g0, frame_index, lr, pref);
 #pragma unroll
-            for (int q = 0; q < kFusedPrefetch; q++) {
-                const int f = fb + q;
-                if (f >= T) break;
-                const uint32_t codes = ring[q];
-                if (f + kFusedPrefetch < T) ring[q] = load_codes(f + kFusedPrefetch);
-                const FusedFrame fr = s_ff[f];
-                uint32_t r16[4] = {0u, 0u, 0u, 0u};
-                int act[4] = {0, 0, 0, 0};
-                if (t_on) {
-                    float lr[4] = {0.f, 0.f, 0.f, 0.f};
-                    uint32_t pref[4] = {0u, 0u, 0u, 0u};
-                    if (use_rng) noise_px4(d.seed, g0, fr.frame_index, lr, pref);
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const int code = (int)((codes >> (8 * k)) & 0xffu);
-                        // photoreceptor low-pass (emulator_utils.py:57-109)
-                        const double ln = s_ln[code];
-                        if (f_lp) {
-                            double eps = s_in[code] * fr.eps_scale;
-                            if (eps > 1.0) eps = 1.0;
-                            lp[k] = (S)((1.0 - eps) * (double)lp[k] + eps * ln);
-                        } else {
-                            lp[k] = (S)ln;
-                        }
-                        // leak (emulator_utils.py:114-134): float32 products, subtract in S
-                        if (f_leak) {
-                            const float rate = lnr[k] * (1.0f - d.leak_jit_f * lr[k]);
-                            const float delta = (fr.dt_f * rate) * thp[k];
-                            base[k] = base[k] - (S)delta;
-                        }
-                        // difference and event count (emulator.py:748-772, emulator_utils.py:137-173)
-                        const S diff = lp[k] - base[k];
-                        S tp, tn;
-                        if (sizeof(S) == 8 && !f_pp) { tp = (S)d.pos_nom; tn = (S)d.neg_nom; }
-                        else { tp = (S)thp[k]; tn = (S)thn[k]; }
-                        const bool neg = diff < (S)0;
-                        const S a = neg ? -diff : diff, b = neg ? tn : tp, b2 = b + b;
-                        const int ge1 = a >= b, ge2 = a >= b2;
-                        int32_t mag = ge1 + ge2;
-                        if (ge2 && !(a - b2 < b)) {                  // >= 3 events: rare
-                            mag = div_floor_count<S>(a, b);
-                            if (mag > kRecMaxCount) mag = kRecMaxCount;
-                        }
-                        int flags = 0;
-                        if (f_shot && shot_candidate(pref[k], fr.pref_lo)) {        // rare
-                            const float r = shot_uniform(d.seed, (g0 + k) >> 2, fr.frame_index, (int)((g0 + k) & 3u), pref[k]);
-                            flags = shot_flags(d, fr.shot_c, (double)code, r, thp[k], thn[k]);
-                        }
-                        if (i0 + k >= d.n) { mag = 0; flags = 0; }
-                        // the refractory filter does not run (checked by the plan): every event is emitted
-                        // (emulator.py:936-942: int32 * float32 -> float32, then the state's dtype)
-                        if (mag | flags) {
-                            const float prod = (float)mag * (neg ? thn[k] : thp[k]);
-                            S bb = neg ? base[k] - (S)prod : base[k] + (S)prod;
-                            if (flags) bb = lp[k];
-                            base[k] = bb;
-                            act[k] = 1;
-                            r16[k] = make_rec16(lane * kVec + k, neg, flags, mag);
-                        }
-                    }
+            for (int k = 0; k < 4; k++) {
+                const int code = (int)((codes >> (8 * k)) & 0xffu);
+                // photoreceptor low-pass (emulator_utils.py:57-109)
+                const double2 tb = s_tab[code];
+                if (f_lp) {
+                    const double eps = fmin(tb.y * eps_scale, 1.0);             // clamp(max=1), eps is never NaN
+                    lp[k] = (S)((1.0 - eps) * (double)lp[k] + eps * tb.x);
+                } else {
+                    lp[k] = (S)tb.x;
                 }
-                // compaction of this frame's active pixels into the (frame, unit) list segment
-                uint32_t cnt = 0;
-                if (__any_sync(0xffffffffu, act[0] | act[1] | act[2] | act[3])) {
-                    uint16_t *seg = rec_list + ((size_t)f * d.units + unit) * kUnitPx;
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const unsigned m = __ballot_sync(0xffffffffu, act[k]);
-                        if (act[k]) seg[cnt + __popc(m & lt_mask)] = (uint16_t)r16[k];
-                        cnt += __popc(m);
-                    }
+                // leak (emulator_utils.py:114-134): float32 products, subtract in S
+                if (f_leak) {
+                    const float rate = lnr[k] * (1.0f - d.leak_jit_f * lr[k]);
+                    const float delta = (dt_f * rate) * thp[k];
+                    base[k] = base[k] - (S)delta;
                 }
-                if (lane == 0) rec_cnt[(size_t)f * d.units + unit] = cnt;
+                // difference and event count (emulator.py:748-772, emulator_utils.py:137-173)
+                const S diff = lp[k] - base[k];
+                const bool neg = diff < (S)0;
+                const float thf = neg ? thn[k] : thp[k];
+                S b;
+                if (sizeof(S) == 8 && !f_pp) b = neg ? tn_nom : tp_nom;
+                else b = (S)thf;
+                const S a = neg ? -diff : diff, b2 = b + b;
+                const int ge2 = a >= b2;
+                int32_t mag = (int)(a >= b) + ge2;
+                if (ge2 && !(a - b2 < b)) mag = fused_deep_count<S>(a, b);          // >= 3 events: rare
+                int flags = 0;
+                if (f_shot && shot_candidate(pref[k], pref_lo))                        // rare
+                    flags = fused_shot_flags(d.seed, d.shot_inten_m1, d.per_pixel_thres, d.pos_nom, d.neg_nom,
+                                             s_ff[f].shot_c, g0 + k, frame_index, pref[k], code, thp[k], thn[k]);
+                if (k >= valid) { mag = 0; flags = 0; }
+                // the refractory filter does not run (checked by the plan): every event is emitted
+                // (emulator.py:936-942: int32 * float32 -> float32, then the state's dtype). Selects, not
+                // branches: x + 0.0 would turn a -0.0 into +0.0
+                const S prod = (S)((float)mag * thf);
+                const S moved = base[k] + (neg ? -prod : prod);          // x - p == x + (-p) exactly
+                S bb = mag ? moved : base[k];
+                bb = flags ? lp[k] : bb;
+                base[k] = bb;
+                r16[k] = (mag | flags) ? make_rec16(lane * kVec + k, neg, flags, mag) : 0u;      // active => non-zero
             }
+            // compaction of this frame's active pixels into the (frame, unit) list segment
+            uint32_t cnt = 0;
+            if (__any_sync(0xffffffffu, (r16[0] | r16[1] | r16[2] | r16[3]) != 0u)) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const unsigned m = __ballot_sync(0xffffffffu, r16[k] != 0u);
+                    if (r16[k]) seg[cnt + __popc(m & lt_mask)] = (uint16_t)r16[k];
+                    cnt += __popc(m);
+                }
+            }
+            if (lane == 0) *cntp = cnt;
+            seg += seg_stride;
+            cntp += d.units;
         }
-        if (t_on) {
+        if (valid) {
             st4(lp_out, i0, lp);
             st4(base_out, i0, base);
         }
@@ -2183,18 +2192,48 @@ static int fused_alloc(V2eEmu *h) {
     return V2E_OK;
 }
 
+// Block shape of pass 1. The kernel is bound by dependent-instruction latency, so what matters is (resident warps)
+// against (units per warp, an integer): 0 = 8 warps x 3 blocks/SM (24 warps, 80 registers), 1 = 4 x 5 (20 warps,
+// 96 registers), 2 = 4 x 7 (28 warps, 72 registers), 3 = 8 x 2 (16 warps, 128 registers). V2E_FUSED_CFG overrides.
+static int fused_cfg() {
+    static int cfg = -1;
+    if (cfg < 0) {
+        const char *e = getenv("V2E_FUSED_CFG");
+        cfg = e ? atoi(e) : 1;
+        if (cfg < 0 || cfg > 3) cfg = 1;
+    }
+    return cfg;
+}
+template <typename S, bool FAST, int WARPS, int MINB>
+static void launch_fused_update_cfg(V2eEmu *h, const uint8_t *frames, int T, size_t sm, cudaStream_t st) {
+    const EmuDev &d = h->d;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int blocks = sms * MINB;
+    const int min_units = 2 * WARPS;                       // small frames: at least two units per warp
+    if (blocks > (d.units + min_units - 1) / min_units) blocks = (d.units + min_units - 1) / min_units;
+    if (blocks < 1) blocks = 1;
+    emu_fused_update_kernel<S, FAST, WARPS, MINB><<<blocks, WARPS * 32, sm, st>>>(d, h->ff_dev, frames, T, (S *)h->lp_alt,
+                                                                                   (S *)h->base_alt, h->rec_list, h->rec_cnt);
+}
+template <typename S, bool FAST>
+static void launch_fused_update_f(V2eEmu *h, const uint8_t *frames, int T, size_t sm, cudaStream_t st) {
+    switch (fused_cfg()) {
+        case 1: launch_fused_update_cfg<S, FAST, 4, 5>(h, frames, T, sm, st); break;
+        case 2: launch_fused_update_cfg<S, FAST, 4, 7>(h, frames, T, sm, st); break;
+        case 3: launch_fused_update_cfg<S, FAST, 8, 2>(h, frames, T, sm, st); break;
+        default: launch_fused_update_cfg<S, FAST, 8, 3>(h, frames, T, sm, st); break;
+    }
+}
 template <typename S>
 static int launch_fused_update(V2eEmu *h, const uint8_t *frames, int T, cudaStream_t st) {
     const EmuDev &d = h->d;
     const size_t sm = (size_t)T * sizeof(FusedFrame);
     const bool fast = sizeof(S) == 8 && d.rng_mode == 1 && d.per_pixel_thres && d.leak_on && d.shot_on;
     if (sm > 40 * 1024) return fail(V2E_E_INVALID, "fused path: too many frames per step");
-    if (fast)
-        emu_fused_update_kernel<S, true><<<d.n_blocks, kThreads, sm, st>>>(d, h->ff_dev, frames, T, (S *)h->lp_alt,
-                                                                            (S *)h->base_alt, h->rec_list, h->rec_cnt);
-    else
-        emu_fused_update_kernel<S, false><<<d.n_blocks, kThreads, sm, st>>>(d, h->ff_dev, frames, T, (S *)h->lp_alt,
-                                                                             (S *)h->base_alt, h->rec_list, h->rec_cnt);
+    if (fast) launch_fused_update_f<S, true>(h, frames, T, sm, st);
+    else launch_fused_update_f<S, false>(h, frames, T, sm, st);
     return V2E_OK;
 }
 

@@ -323,6 +323,10 @@ int v2e_resize_create(int src_w, int src_h, int dst_w, int dst_h, int filter, in
                       V2eResizer **out);
 int v2e_resize_destroy(V2eResizer *r);
 int v2e_resize_run(V2eResizer *r, const uint8_t *src_dev, uint8_t *dst_dev, int n_images, void *stream);
+/* Same, destination image i at dst_dev + i * dst_image_stride bytes (>= dst_w * dst_h): the interpolated frame of
+ * pair b at time step k goes straight to its place U*b + k of the output clip (slomo.py:440), no gather copy. */
+int v2e_resize_run_strided(V2eResizer *r, const uint8_t *src_dev, uint8_t *dst_dev, int n_images,
+                           long dst_image_stride, void *stream);
 
 /* ------------------------------------------------------------------------- */
 /* Event-sink row conversions: packed rows [t, x, y, p] float32 -> what the reference's writers

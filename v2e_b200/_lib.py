@@ -96,6 +96,7 @@ _SIGS = {
     "v2e_resize_create": (_i, [_i, _i, _i, _i, _i, _i, ctypes.POINTER(_vp)]),
     "v2e_resize_destroy": (_i, [_vp]),
     "v2e_resize_run": (_i, [_vp, _vp, _vp, _i, _vp]),
+    "v2e_resize_run_strided": (_i, [_vp, _vp, _vp, _i, ctypes.c_long, _vp]),
     "v2e_emu_set_scidvs_tau": (_i, [_vp, _vp]),
     "v2e_emu_set_pr_noise": (_i, [_vp, _vp, ctypes.POINTER(_d), _i]),
     "v2e_events_to_h5_rows": (_i, [_vp, _u64, _vp, _vp]),

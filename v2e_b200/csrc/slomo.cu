@@ -254,8 +254,10 @@ __global__ void max_speed_kernel(const float *__restrict__ flow, long n, float *
 // ImagingResampleVertical_8bpc): 22-bit fixed-point coefficients computed on the host in double
 // exactly like precompute_coeffs() + normalize_coeffs_8bpc(), integer accumulation here.
 // ---------------------------------------------------------------------------------------------
+// dst_stride: distance in bytes between consecutive destination images (dense: rows * width)
 __global__ void resample_h_u8_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int n_img, int sw,
-                                     int sh, int dw, const int *__restrict__ bounds, const int *__restrict__ kk, int ksize) {
+                                     int sh, int dw, const int *__restrict__ bounds, const int *__restrict__ kk, int ksize,
+                                     long dst_stride) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long)n_img * sh * dw) return;
     const int xx = (int)(i % dw);
@@ -266,10 +268,12 @@ __global__ void resample_h_u8_kernel(const uint8_t *__restrict__ src, uint8_t *_
     int ss = 1 << 21;
     for (int x = 0; x < xmax; x++) ss += (int)s[x] * k[x];
     ss >>= 22;
-    dst[i] = (uint8_t)(ss < 0 ? 0 : (ss > 255 ? 255 : ss));
+    const long per = (long)sh * dw;
+    dst[(i / per) * dst_stride + i % per] = (uint8_t)(ss < 0 ? 0 : (ss > 255 ? 255 : ss));
 }
 __global__ void resample_v_u8_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int n_img, int w,
-                                     int sh, int dh, const int *__restrict__ bounds, const int *__restrict__ kk, int ksize) {
+                                     int sh, int dh, const int *__restrict__ bounds, const int *__restrict__ kk, int ksize,
+                                     long dst_stride) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long)n_img * dh * w) return;
     const int x = (int)(i % w);
@@ -282,7 +286,7 @@ __global__ void resample_v_u8_kernel(const uint8_t *__restrict__ src, uint8_t *_
     int ss = 1 << 21;
     for (int y = 0; y < ymax; y++) ss += (int)s[(long)y * w] * k[y];
     ss >>= 22;
-    dst[i] = (uint8_t)(ss < 0 ? 0 : (ss > 255 ? 255 : ss));
+    dst[img * dst_stride + (long)yy * w + x] = (uint8_t)(ss < 0 ? 0 : (ss > 255 ? 255 : ss));
 }
 
 static double bilinear_filter(double x) { if (x < 0.0) x = -x; return x < 1.0 ? 1.0 - x : 0.0; }
@@ -738,27 +742,38 @@ extern "C" int v2e_resize_destroy(V2eResizer *r) {
     return V2E_OK;
 }
 
-extern "C" int v2e_resize_run(V2eResizer *r, const uint8_t *src_dev, uint8_t *dst_dev, int n_images, void *stream) {
+extern "C" int v2e_resize_run_strided(V2eResizer *r, const uint8_t *src_dev, uint8_t *dst_dev, int n_images,
+                                      long dst_image_stride, void *stream) {
     if (!r || !src_dev || !dst_dev || n_images < 1 || n_images > r->max_images)
         return v2e_set_error(V2E_E_INVALID, "bad resize arguments%s", "");
+    const long dense = (long)r->dw * r->dh;
+    if (dst_image_stride < dense) return v2e_set_error(V2E_E_INVALID, "destination image stride smaller than an image%s", "");
     cudaStream_t st = (cudaStream_t)stream;
     const bool nh = r->sw != r->dw, nv = r->sh != r->dh;
     if (!nh && !nv) {
-        CU(cudaMemcpyAsync(dst_dev, src_dev, (size_t)n_images * r->sw * r->sh, cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpy2DAsync(dst_dev, (size_t)dst_image_stride, src_dev, (size_t)dense, (size_t)dense, (size_t)n_images,
+                             cudaMemcpyDeviceToDevice, st));
         return V2E_OK;
     }
     const uint8_t *cur = src_dev;
     if (nh) {
         uint8_t *d = nv ? r->tmp : dst_dev;
         const long n = (long)n_images * r->sh * r->dw;
-        resample_h_u8_kernel<<<cdiv(n, 256), 256, 0, st>>>(cur, d, n_images, r->sw, r->sh, r->dw, r->bounds_h, r->kk_h, r->ks_h);
+        resample_h_u8_kernel<<<cdiv(n, 256), 256, 0, st>>>(cur, d, n_images, r->sw, r->sh, r->dw, r->bounds_h, r->kk_h, r->ks_h,
+                                                           nv ? (long)r->sh * r->dw : dst_image_stride);
         cur = d;
     }
     if (nv) {
         const long n = (long)n_images * r->dh * r->dw;
-        resample_v_u8_kernel<<<cdiv(n, 256), 256, 0, st>>>(cur, dst_dev, n_images, r->dw, r->sh, r->dh, r->bounds_v, r->kk_v, r->ks_v);
+        resample_v_u8_kernel<<<cdiv(n, 256), 256, 0, st>>>(cur, dst_dev, n_images, r->dw, r->sh, r->dh, r->bounds_v, r->kk_v, r->ks_v,
+                                                           dst_image_stride);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return v2e_set_error(V2E_E_CUDA, "v2e_resize_run: %s", cudaGetErrorString(e));
     return V2E_OK;
+}
+
+extern "C" int v2e_resize_run(V2eResizer *r, const uint8_t *src_dev, uint8_t *dst_dev, int n_images, void *stream) {
+    if (!r) return v2e_set_error(V2E_E_INVALID, "bad resize arguments%s", "");
+    return v2e_resize_run_strided(r, src_dev, dst_dev, n_images, (long)r->dw * r->dh, stream);
 }

@@ -116,15 +116,17 @@ class SloMoEngine:
         return float(v.value)
 
     def interp(self, t, out_u8_dev, ft_f32_dev=None):
-        """out_u8_dev: [B, ori_h, ori_w] uint8 device tensor (a contiguous view)."""
+        """out_u8_dev: [B, ori_h, ori_w] uint8 device view whose images are contiguous; the images themselves may
+        be strided (out[k::U] of the output clip: frame of pair b at step k lands at U*b + k, slomo.py:440)."""
         b = self.cur_b
-        assert out_u8_dev.shape == (b, self.ori_h, self.ori_w) and out_u8_dev.is_contiguous()
+        assert out_u8_dev.shape == (b, self.ori_h, self.ori_w) and out_u8_dev[0].is_contiguous()
+        stride = out_u8_dev.stride(0) if b > 1 else self.ori_h * self.ori_w
         with torch.cuda.device(self.device):
             _lib.check(self.lib.v2e_slomo_interp(self._h, float(t), ctypes.c_void_p(self._net_out.data_ptr()),
                                                  None if ft_f32_dev is None else ctypes.c_void_p(ft_f32_dev.data_ptr()),
                                                  self._stream()))
-            _lib.check(self.lib.v2e_resize_run(self._rout, ctypes.c_void_p(self._net_out.data_ptr()),
-                                               ctypes.c_void_p(out_u8_dev.data_ptr()), b, self._stream()))
+            _lib.check(self.lib.v2e_resize_run_strided(self._rout, ctypes.c_void_p(self._net_out.data_ptr()),
+                                                       ctypes.c_void_p(out_u8_dev.data_ptr()), b, stride, self._stream()))
 
     def _view(self, ptr_fn):
         from .emulator import _DevView
@@ -190,6 +192,37 @@ class SuperSloMo(object):
         return self._engine
 
     # -- in-memory path ------------------------------------------------------------------------
+    def _batches(self, get_frames, n, H, W, out=None):
+        """The reference's loop over batches of consecutive frame pairs (slomo.py:330-444). get_frames(a, b) returns
+        source frames a .. b-1 as a uint8 [b-a, H, W] tensor (host or device). Yields, per batch,
+        (frames [U*b, H, W] uint8 device, interpTimes of the batch, U): with `out` (fixed U) the frames are a view of
+        out[U*in_ctr : U*(in_ctr+b)], otherwise a fresh block."""
+        bs = max(1, min(int(self.batch_size), n - 1))
+        eng = self._engine_for((W, H), bs)
+        in_ctr = 0
+        while in_ctr < n - 1:
+            b = min(bs, n - 1 - in_ctr)
+            fr = get_frames(in_ctr, in_ctr + b + 1).to(self.device, non_blocking=True).contiguous()
+            eng.set_pairs(fr)
+            if self.auto_upsample:
+                U = int(np.ceil(eng.max_flow()))                      # slomo.py:366-372
+                if self.upsampling_factor is not None and self.upsampling_factor > U:
+                    U = self.upsampling_factor
+            else:
+                U = self.upsampling_factor
+            if U < 2:
+                U = 2                                                   # slomo.py:383-385
+            if out is not None:
+                blk = out[U * in_ctr: U * (in_ctr + b)]
+            else:
+                blk = torch.empty((U * b, H, W), dtype=torch.uint8, device=self.device)
+            for k in range(U):
+                t = (k + 0.5) / U                                       # slomo.py:405
+                # frame of pair bi at step k goes to index U*bi + k of the batch (slomo.py:440): written in place
+                eng.interp(t, blk[k: U * b: U])
+            yield blk, in_ctr + np.array(range(U * b)) * (1 / U), U      # slomo.py:391-395
+            in_ctr += b
+
     def interpolate_frames(self, frames, out=None):
         """frames: [N, H, W] uint8 (ndarray or tensor, host or device), N >= 2.
         Returns (out_u8 [M, H, W] device tensor, interpTimes [M] float64, avgUpsampling).
@@ -202,52 +235,23 @@ class SuperSloMo(object):
         n, H, W = frames.shape
         if n < 2:
             raise ValueError("need at least two frames")
-        fr = frames.to(self.device, non_blocking=True).contiguous()
-        bs = max(1, min(int(self.batch_size), n - 1))
-        eng = self._engine_for((W, H), bs)
-        chunks, times = [], []
-        ups_sum, ups_n = 0, 0
-        in_ctr = 0
-        total_fixed = None if self.auto_upsample else (n - 1) * int(self.upsampling_factor)
-        if out is None and total_fixed is not None:
-            out = torch.empty((total_fixed, H, W), dtype=torch.uint8, device=fr.device)
-        out_ctr = 0
-        while in_ctr < n - 1:
-            b = min(bs, n - 1 - in_ctr)
-            eng.set_pairs(fr[in_ctr:in_ctr + b + 1])
-            if self.auto_upsample:
-                U = int(np.ceil(eng.max_flow()))                      # slomo.py:366-372
-                if self.upsampling_factor is not None and self.upsampling_factor > U:
-                    U = self.upsampling_factor
-            else:
-                U = self.upsampling_factor
-            if U < 2:
-                U = 2                                                   # slomo.py:383-385
-            ups_sum += U
-            ups_n += 1
-            if total_fixed is None:
-                blk = torch.empty((U * b, H, W), dtype=torch.uint8, device=fr.device)
-                base = 0
-            else:
-                blk, base = out, out_ctr
-            tmp = torch.empty((b, H, W), dtype=torch.uint8, device=fr.device)
-            for k in range(U):
-                t = (k + 0.5) / U                                       # slomo.py:405
-                eng.interp(t, tmp)
-                # frame of pair bi at step k goes to index base + U*bi + k (slomo.py:440)
-                blk[base + k: base + U * b: U] = tmp
-            times.append(in_ctr + np.array(range(U * b)) * (1 / U))    # slomo.py:391-395
-            if total_fixed is None:
+        if out is None and not self.auto_upsample:
+            out = torch.empty(((n - 1) * int(self.upsampling_factor), H, W), dtype=torch.uint8, device=self.device)
+        fixed = out if not self.auto_upsample else None
+        chunks, times, ups = [], [], []
+        for blk, tt, U in self._batches(lambda a, b: frames[a:b], n, H, W, out=fixed):
+            times.append(tt)
+            ups.append(U)
+            if fixed is None:
                 chunks.append(blk)
-            in_ctr += b
-            out_ctr += U * b
-        if total_fixed is None:
+        if fixed is None:
             out = torch.cat(chunks, 0)
-        return out, np.concatenate(times), ups_sum / ups_n
+        return out, np.concatenate(times), sum(ups) / len(ups)
 
     # -- reference file API ----------------------------------------------------------------------
     def interpolate(self, source_frame_path, output_folder, frame_size):
-        """slomo.py:231: .npy frames in, <idx>.png frames out; returns (interpTimes, avgUpsampling)."""
+        """slomo.py:231: .npy frames in, <idx>.png frames out; returns (interpTimes, avgUpsampling). Streams batch by
+        batch like the reference: only one batch of source frames and its interpolated frames are resident."""
         from PIL import Image
         if not output_folder:
             raise ValueError('output_folder is None; it must be supplied to store the interpolated frames')
@@ -263,17 +267,25 @@ class SuperSloMo(object):
             raise Exception('there are only {} batches in {} and we need at least 2; maybe you need to '
                             'reduce batch size or increase number of input frames'.format(
                                 0 if self.batch_size < 1 else -(-n_pairs // self.batch_size), source_frame_path))
-        frames = np.stack([np.load(f) for f in files])
         W, H = int(frame_size[0]), int(frame_size[1])
-        if frames.shape[1:] != (H, W):
-            raise ValueError("frames on disk are %s, frame_size says %s" % (frames.shape[1:], (H, W)))
-        out, interp_times, avg = self.interpolate_frames(frames.astype(np.uint8, copy=False))
-        out_host = out.cpu().numpy()
+
+        def get_frames(a, b):
+            fr = np.stack([np.load(f) for f in files[a:b]])
+            if fr.shape[1:] != (H, W):
+                raise ValueError("frames on disk are %s, frame_size says %s" % (fr.shape[1:], (H, W)))
+            return torch.from_numpy(np.ascontiguousarray(fr.astype(np.uint8, copy=False)))
         os.makedirs(output_folder, exist_ok=True)
-        for i in range(out_host.shape[0]):
-            Image.fromarray(out_host[i]).save(os.path.join(output_folder, str(i) + ".png"))
+        times, ups, out_ctr = [], [], 0
+        for blk, tt, U in self._batches(get_frames, len(files), H, W):
+            host = blk.cpu().numpy()
+            for i in range(host.shape[0]):
+                Image.fromarray(host[i]).save(os.path.join(output_folder, str(out_ctr + i) + ".png"))
+            out_ctr += host.shape[0]
+            times.append(tt)
+            ups.append(U)
+        interp_times, avg = np.concatenate(times), sum(ups) / len(ups)
         logger.info('Wrote {} frames and returning {} frame times.\nAverage upsampling factor={:5.1f}'.format(
-            out_host.shape[0], len(interp_times), avg))
+            out_ctr, len(interp_times), avg))
         return interp_times, avg
 
     def get_interpolated_timestamps(self, ts):

@@ -74,7 +74,14 @@ typedef struct V2eEmuCfg {
     uint32_t rng_pixel_offset;      /* rng_mode 1: index, in the WHOLE frame, of this handle's pixel 0. 0 unless the
                                        handle owns a row band of a pixel-sharded clip (y0 * width): the Philox counters
                                        use whole-frame pixel indices, so the bands draw what one GPU would draw */
-    uint32_t reserved0;
+    uint32_t full_frame_px;         /* pixels of the WHOLE frame when the handle owns a row band (0: width * height):
+                                       the reference's float32 conv2d sums in a size-dependent order (centre-surround) */
+    int32_t own_row0, own_rows;     /* rows [own_row0, own_row0 + own_rows) of the handle emit events; the rest are halo
+                                       rows of a pixel-sharded centre-surround handle (own_rows = 0: all rows) */
+    int32_t cs_halo_rows;           /* K > 0: pixel-sharded centre-surround model -- K halo rows either side of the own
+                                       rows (absent at the image border), Euler steps in chunks of K between halo
+                                       exchanges (v2e_emu_cs_*); 0: single-GPU surround */
+    int32_t reserved1;
 } V2eEmuCfg;
 
 typedef struct V2eEmu V2eEmu;
@@ -187,6 +194,31 @@ int v2e_emu_phase_update(V2eEmu *h, const void *frame_dev, int frame_dtype, doub
                          double t_previous, const float *leak_randn_dev, const float *shot_rand_dev,
                          uint64_t capacity, uint64_t ev_base_start, void *stream);
 int32_t *v2e_emu_max_n_dev(V2eEmu *h);
+/* Pixel-sharded centre-surround model (emulator.py:1061-1124 over row bands; BASELINE config 5). The handle holds
+ * the rank's own rows plus cs_halo_rows = K rows of each neighbour; lp is computed on all of them (it is a per-pixel
+ * function of the frames), the surround on the halo rows comes from the neighbours. Per frame:
+ *   v2e_emu_cs_begin      low-pass of the band, Euler-step plan (*num_steps, emulator.py:1076-1078)
+ *   for chunks [s0, s1) of at most K steps:
+ *       v2e_emu_cs_pack        own edge rows of the current surround -> v2e_emu_cs_send_dev()  [2][K][W] float64
+ *       (caller: exchange with the neighbours; into v2e_emu_cs_recv_dev(): [0] = the rows above, [1] = below)
+ *       v2e_emu_cs_unpack      received rows -> halo rows
+ *       v2e_emu_cs_chunk       steps s0 .. s1-1 (each into its own ring buffer; maxima over the own rows)
+ *       (caller: all-reduce MAX of the uint64 at v2e_emu_cs_max_dev()[s0 .. s1) -- non-negative doubles order
+ *        like their bit patterns)
+ *       v2e_emu_cs_advance     first step with max|change| <= 1e-5 ends the iteration (device side, no host sync)
+ *   v2e_emu_cs_update     the update kernel on the converged surround (then v2e_emu_max_n_dev ... as above)
+ * Everything is enqueued on `stream`; nothing synchronises. */
+int v2e_emu_cs_begin(V2eEmu *h, const void *frame_dev, int frame_dtype, double t_frame, double t_previous,
+                     uint64_t capacity, uint64_t ev_base_start, int *num_steps, void *stream);
+int v2e_emu_cs_pack(V2eEmu *h, void *stream);
+int v2e_emu_cs_unpack(V2eEmu *h, void *stream);
+double *v2e_emu_cs_send_dev(V2eEmu *h);
+double *v2e_emu_cs_recv_dev(V2eEmu *h);
+int v2e_emu_cs_chunk(V2eEmu *h, int s0, int s1, void *stream);
+uint64_t *v2e_emu_cs_max_dev(V2eEmu *h);
+int v2e_emu_cs_advance(V2eEmu *h, int s0, int s1, void *stream);
+int v2e_emu_cs_update(V2eEmu *h, const void *frame_dev, int frame_dtype, const float *leak_randn_dev,
+                      const float *shot_rand_dev, void *stream);
 int v2e_emu_phase_filter(V2eEmu *h, double t_frame, double t_previous, uint64_t capacity, int do_plan,
                          void *stream);
 /* per-(iteration,polarity) row counts of the frame just counted: counts_host[2*max_n]

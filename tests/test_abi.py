@@ -38,8 +38,8 @@ def test_version_call_without_gpu():
 
 
 def test_struct_sizes_match_header_layout():
-    # V2eEmuCfg: 4 int32, 8 double, 2 int32, uint64, 2 int32, 2 double, 2 int32, 2 uint32
-    assert ctypes.sizeof(_lib.V2eEmuCfg) == 16 + 64 + 8 + 8 + 8 + 16 + 8 + 8
+    # V2eEmuCfg: 4 int32, 8 double, 2 int32, uint64, 2 int32, 2 double, 2 int32, 2 uint32, 4 int32
+    assert ctypes.sizeof(_lib.V2eEmuCfg) == 16 + 64 + 8 + 8 + 8 + 16 + 8 + 8 + 16
     assert ctypes.sizeof(_lib.V2eFrameInfo) == 40
 
 

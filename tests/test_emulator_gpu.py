@@ -536,3 +536,71 @@ def test_pixel_sharded_batched_equals_single_gpu_device_rng(case):
     for r in (0, 1):
         chunks, rejected = res[r][3]
         assert chunks >= 2 and (rejected > 0) == expect_reject
+
+
+def _cs_sharded_worker(rank, world, port, frames, times, kwargs, tape, chunk_steps, q):
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from v2e_b200 import EventEmulator
+        extra = dict(rng=TapeRNG(tape)) if tape is not None else dict(seed=31)
+        em = EventEmulator(device="cuda:0", shard=(rank, world, None), **extra, **kwargs)
+        em.cs_chunk_steps = chunk_steps
+        out = [em.generate_events(f, float(t)) for f, t in zip(frames, times)]
+        q.put((rank, out, em.num_events_total, list(em.cs_steps_taken)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case", [("emu_csdvs_120x176", 2, 6), ("emu_csdvs_120x176", 3, 20), ("emu_csdvs", 2, 7),
+                                  ("settling", 2, 4)])
+def test_pixel_sharded_centre_surround_matches_reference(case):
+    """BASELINE config 5's pixel model: the centre-surround Euler iteration (emulator.py:1061-1124) over row bands,
+    K halo rows exchanged every K steps, the per-step max|change| reduced over the ranks once per chunk. The union of
+    the ranks' events must equal the unmodified reference's output per frame (golden fixtures), and every rank must
+    report the reference's number of Euler steps per frame (`cs_steps_taken`). emu_csdvs also has leak + shot noise
+    (replay mode: every rank draws the full fields from the tape and keeps its rows). "settling": a scene that stops
+    moving, so that the iteration ends early, inside a chunk, at different steps per frame -- against the oracle."""
+    import socket
+    import torch.multiprocessing as mp
+    name, world, chunk = case
+    if name == "settling":
+        from emu_oracle import OracleEmulator
+        kwargs = dict(cs_lambda_pixels=4, cs_tau_p_ms=2.0, cutoff_hz=2000, leak_rate_hz=0, shot_noise_rate_hz=0,
+                      sigma_thres=0.02)
+        mov = texture_frames(60, 80, 3, seed=6, speed=2.0)
+        frames = np.concatenate([mov, np.repeat(mov[-1:], 9, 0)])
+        times = np.concatenate([np.arange(3) * 5e-4, 1e-3 + (1 + np.arange(9)) * 4e-3])     # oracle: 20, 20, 160, 161, 84, 1 ... steps
+        orc = OracleEmulator(seed=31, **kwargs)
+        want = [orc.generate_events(f, float(t)) for f, t in zip(frames, times)]
+        steps_want, n_want, tape = list(orc.cs_steps_taken), orc.num_events_total, None
+        assert 1 in steps_want and 84 in steps_want and max(steps_want) > 100, steps_want     # ends inside chunks
+    else:
+        g = load_golden(name)
+        frames, times, kwargs, tape = g["frames"], g["times"], g["kwargs"], g["tape"]
+        want = split_events(g["events"], g["event_counts"])
+        steps_want, n_want = list(g["cs_steps_taken"]), int(g["num_on"]) + int(g["num_off"])
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_cs_sharded_worker, args=(r, world, port, frames, times, kwargs, tape, chunk, q))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict()
+    for _ in range(world):
+        r, out, n, steps = q.get(timeout=600)
+        res[r] = (out, n, steps)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sum(res[r][1] for r in res) == n_want
+    for r in res:
+        assert res[r][2] == steps_want, (r, res[r][2], steps_want)
+    for i in range(len(want)):
+        parts = [res[r][0][i] for r in sorted(res) if res[r][0][i] is not None]
+        got = np.concatenate(parts) if parts else None
+        assert_events_equal(got, want[i], exact_order=False, ctx="%s frame %d" % (name, i))

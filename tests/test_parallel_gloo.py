@@ -124,3 +124,45 @@ def test_pair_range_covers_all_pairs_contiguously():
         for (a0, a1), (b0, b1) in zip(edges, edges[1:]):
             assert a1 == b0 and a1 >= a0
         assert max(b - a for a, b in edges) - min(b - a for a, b in edges) <= 1
+
+
+def _halo_worker(rank, world, port, q):
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from v2e_b200 import parallel
+        H, W = 23, 7
+        p0, p1 = parallel.pair_range(5, rank, world)
+        local = torch.stack([torch.full((H, W), 10 * k, dtype=torch.uint8) + torch.arange(H, dtype=torch.uint8)[:, None]
+                             for k in range(p0, p1)])
+        out = parallel.exchange_frame_bands(local, H, halo=3)
+        q.put((rank, out.numpy(), parallel.band_with_halo(H, rank, world, 3)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_frame_band_exchange_with_halo_rows():
+    """Centre-surround sharding (BASELINE config 5): every rank gets its rows PLUS `halo` rows of each neighbour,
+    clipped at the image border, of every frame of the clip in clip order."""
+    import socket
+    import torch.multiprocessing as mp
+    world = 3
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_halo_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    bands = {r: b for r, _, b in res}
+    assert bands[0][0] == 0 and bands[world - 1][1] == 23 and bands[1][0] < bands[0][1]     # overlap = the halo
+    for r, out, (y0, y1) in res:
+        assert out.shape == (5, y1 - y0, 7)
+        for k in range(5):
+            assert (out[k, :, 0] == (10 * k + np.arange(y0, y1)).astype(np.uint8)).all()

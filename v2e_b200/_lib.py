@@ -20,7 +20,9 @@ class V2eEmuCfg(ctypes.Structure):
         ("csdvs", ctypes.c_int32), ("max_frames_per_step", ctypes.c_int32),
         ("cs_tau_p_s", ctypes.c_double), ("cs_tau_h_s", ctypes.c_double),
         ("scidvs", ctypes.c_int32), ("photoreceptor_noise", ctypes.c_int32),
-        ("rng_pixel_offset", ctypes.c_uint32), ("reserved0", ctypes.c_uint32),
+        ("rng_pixel_offset", ctypes.c_uint32), ("full_frame_px", ctypes.c_uint32),
+        ("own_row0", ctypes.c_int32), ("own_rows", ctypes.c_int32),
+        ("cs_halo_rows", ctypes.c_int32), ("reserved1", ctypes.c_int32),
     ]
 
 
@@ -67,6 +69,15 @@ _SIGS = {
     "v2e_emu_phase_count": (_i, [_vp, _vp, _i, _d, _d, _vp, _vp, _i, _u64, _u64, _vp]),
     "v2e_emu_phase_update": (_i, [_vp, _vp, _i, _d, _d, _vp, _vp, _u64, _u64, _vp]),
     "v2e_emu_max_n_dev": (_vp, [_vp]),
+    "v2e_emu_cs_begin": (_i, [_vp, _vp, _i, _d, _d, _u64, _u64, ctypes.POINTER(_i), _vp]),
+    "v2e_emu_cs_pack": (_i, [_vp, _vp]),
+    "v2e_emu_cs_unpack": (_i, [_vp, _vp]),
+    "v2e_emu_cs_send_dev": (_vp, [_vp]),
+    "v2e_emu_cs_recv_dev": (_vp, [_vp]),
+    "v2e_emu_cs_chunk": (_i, [_vp, _i, _i, _vp]),
+    "v2e_emu_cs_max_dev": (_vp, [_vp]),
+    "v2e_emu_cs_advance": (_i, [_vp, _i, _i, _vp]),
+    "v2e_emu_cs_update": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "v2e_emu_phase_filter": (_i, [_vp, _d, _d, _u64, _i, _vp]),
     "v2e_emu_read_counts": (_i, [_vp, ctypes.POINTER(ctypes.c_int32), _vp, _i, _vp]),
     "v2e_emu_phase_shot": (_i, [_vp, _vp, _i, _d, _d, _vp, _u64, _vp]),

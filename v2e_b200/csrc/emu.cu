@@ -70,6 +70,13 @@ struct EmuDev {                         // passed by value to every kernel
     int32_t *cs_cur;                    // which buffer holds the current surround
     unsigned long long *cs_max;         // [cs_cap] max|change| of every Euler step of the current frame (double bits)
     int32_t cs_cap, cs_seq_order;
+    int32_t cs_ring;                    // buffers in the surround ring (2 unless pixel-sharded: steps per chunk + 1)
+    int32_t cs_y_lo, cs_y_hi;           // rows of this handle that count for max|change| (the rank's own rows)
+    int32_t own_lo, own_hi;             // pixels [own_lo, own_hi) emit events (a sharded centre-surround handle also
+                                        // carries halo rows above / below its own rows); 0 / n otherwise
+    int32_t *cs_done;                   // sharded: the Euler iteration of this frame ended in an earlier chunk
+    double *cs_bufs;                    // sharded: ring of cs_ring buffers of cs_stride doubles (replaces surround / surround2)
+    size_t cs_stride;
     int16_t *rec;
     uint32_t *act_list;                 // [n_pad] pixel indices with a non-zero record (built by the update kernel)
     uint32_t *act_count;                // [max_slots][n_blocks]: entries of each update-block's list segment
@@ -473,7 +480,7 @@ __global__ void __launch_bounds__(kThreads) emu_first_frame_kernel(EmuDev d, Fra
     st4((S *)d.lp, i0, lp);
     st4((S *)d.base, i0, base);
     if (d.refr_on) st4(d.tmem, i0, tm);
-    if (d.csdvs) st4(d.surround, i0, su);     // v2e_emu_first_frame resets cs_cur to 0
+    if (d.csdvs) st4(d.cs_bufs ? d.cs_bufs : d.surround, i0, su);     // v2e_emu_first_frame resets cs_cur to 0
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -513,28 +520,37 @@ __global__ void __launch_bounds__(kThreads) emu_lp_kernel(EmuDev d, FrameParams 
 // reference's CPU backend's (see oracle/emu_oracle.c); alpha_h meets a float32 tensor -> float32 product.
 // Step k runs only if every earlier step changed some pixel by more than 1e-5 (the reference's while
 // condition); the maxima are exchanged through cs_max.
+// Ring form: step `step` of the frame is step `i` of its chunk; it reads ring buffer (cs_cur + i) % cs_ring and writes
+// the next one. Single GPU: one chunk per frame, ring of 2 (ping-pong), and the cascade above. Pixel-sharded
+// (emulator.py:1102-1124 over row bands): the handle carries K halo rows of the neighbours above / below, a chunk is
+// K steps between two halo exchanges, step i of a chunk is valid on rows >= i from a halo edge; the maximum is taken
+// over the rank's own rows only and reduced over the ranks after the chunk, so the steps of a chunk run without
+// knowing whether an earlier step of the same chunk ended the iteration -- the ring (K + 1 buffers) keeps every
+// step's result and emu_csdvs_advance_kernel picks the right one.
 __global__ void __launch_bounds__(kThreads)
-emu_csdvs_step_kernel(EmuDev d, double alpha_p, float alpha_h, int step) {
+emu_csdvs_step_kernel(EmuDev d, double alpha_p, float alpha_h, int step, int i, int sharded) {
     if (*(volatile int32_t *)d.abort_flag) return;
-    if (step > 0 && __longlong_as_double((long long)d.cs_max[step - 1]) <= 1e-5) return;
-    const int cur = (*(volatile int32_t *)d.cs_cur + step) & 1;
-    const double *h = cur ? d.surround2 : d.surround;
-    double *hn = cur ? d.surround : d.surround2;
+    if (sharded) { if (*(volatile int32_t *)d.cs_done) return; }
+    else if (step > 0 && __longlong_as_double((long long)d.cs_max[step - 1]) <= 1e-5) return;
+    const int cur = (*(volatile int32_t *)d.cs_cur + i) % d.cs_ring;
+    const int nxt = (cur + 1) % d.cs_ring;
+    const double *h = d.cs_bufs ? d.cs_bufs + (size_t)cur * d.cs_stride : (cur ? d.surround2 : d.surround);
+    double *hn = d.cs_bufs ? d.cs_bufs + (size_t)nxt * d.cs_stride : (nxt ? d.surround2 : d.surround);
     const double *pp = (const double *)d.lp;
-    const int i = blockIdx.x * kThreads + threadIdx.x;
+    const int idx = blockIdx.x * kThreads + threadIdx.x;
     double a = 0.0;
-    if (i < d.n) {
-        const int y = i / d.W, x = i - y * d.W;
+    if (idx < d.n) {
+        const int y = idx / d.W, x = idx - y * d.W;
         const int ym = y > 0 ? y - 1 : 0, yp = y < d.H - 1 ? y + 1 : d.H - 1;
         const int xm = x > 0 ? x - 1 : 0, xp = x < d.W - 1 ? x + 1 : d.W - 1;
-        const double hc = h[i];
+        const double hc = h[idx];
         const float uu = (float)h[ym * d.W + x], ll = (float)h[y * d.W + xm], cc = -4.0f * (float)hc;
         const float rr = (float)h[y * d.W + xp], dd = (float)h[yp * d.W + x];
         const float acc = d.cs_seq_order ? ((((uu + ll) + cc) + rr) + dd) : (uu + ll) + (cc + (rr + dd));
         const float h_term = alpha_h * acc;
-        const double chg = alpha_p * (pp[i] - hc) + (double)h_term;
-        hn[i] = hc + chg;
-        a = fabs(chg);
+        const double chg = alpha_p * (pp[idx] - hc) + (double)h_term;
+        hn[idx] = hc + chg;
+        if (y >= d.cs_y_lo && y < d.cs_y_hi) a = fabs(chg);
     }
     // block max of |change| -> one atomicMax (non-negative doubles order like their bit patterns)
     unsigned long long bits = (unsigned long long)__double_as_longlong(a);
@@ -552,13 +568,46 @@ emu_csdvs_step_kernel(EmuDev d, double alpha_p, float alpha_h, int step) {
     }
 }
 
+// sharded: after the chunk's maxima have been reduced over the ranks. Steps [s0, s1) ran from ring position cs_cur;
+// the iteration ends with the first step whose global max|change| <= 1e-5 (that step is applied, emulator.py:1105-1121).
+__global__ void emu_csdvs_advance_kernel(EmuDev d, int s0, int s1, int slot) {
+    if (*(volatile int32_t *)d.abort_flag) return;
+    if (*d.cs_done) return;
+    int taken = s1 - s0;
+    for (int k = s0; k < s1; k++)
+        if (__longlong_as_double((long long)d.cs_max[k]) <= 1e-5) { taken = k - s0 + 1; *d.cs_done = 1; break; }
+    *d.cs_cur = (*d.cs_cur + taken) % d.cs_ring;
+    d.ctrl[slot].cs_steps = s0 + taken;
+}
+// sharded halo exchange: the K own rows next to each band edge of the current surround buffer -> send[2][K][W];
+// recv[2][K][W] (the neighbours' rows) -> the halo rows of the current buffer
+__global__ void emu_csdvs_pack_kernel(EmuDev d, double *send, int K) {
+    const double *h = d.cs_bufs + (size_t)(*d.cs_cur) * d.cs_stride;
+    const int per = K * d.W;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * per; i += gridDim.x * blockDim.x) {
+        const int side = i / per, r = (i - side * per) / d.W, x = i % d.W;
+        const int y = side == 0 ? d.cs_y_lo + r : d.cs_y_hi - K + r;        // top K / bottom K own rows
+        send[i] = h[(size_t)y * d.W + x];
+    }
+}
+__global__ void emu_csdvs_unpack_kernel(EmuDev d, const double *recv, int K) {
+    double *h = d.cs_bufs + (size_t)(*d.cs_cur) * d.cs_stride;
+    const int per = K * d.W;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * per; i += gridDim.x * blockDim.x) {
+        const int side = i / per, r = (i - side * per) / d.W, x = i % d.W;
+        // side 0: halo above the own rows (present iff cs_y_lo > 0), side 1: halo below
+        if (side == 0 && d.cs_y_lo >= K) h[(size_t)(d.cs_y_lo - K + r) * d.W + x] = recv[i];
+        if (side == 1 && d.cs_y_hi + K <= d.H) h[(size_t)(d.cs_y_hi + r) * d.W + x] = recv[i];
+    }
+}
+
 __global__ void emu_csdvs_finish_kernel(EmuDev d, int num_steps, int slot) {
     if (*(volatile int32_t *)d.abort_flag) return;
     int steps = num_steps;
     for (int k = 0; k < num_steps; k++)
         if (__longlong_as_double((long long)d.cs_max[k]) <= 1e-5) { steps = k + 1; break; }
     d.ctrl[slot].cs_steps = steps;
-    *d.cs_cur = (*d.cs_cur + steps) & 1;
+    *d.cs_cur = (*d.cs_cur + steps) % d.cs_ring;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -798,7 +847,11 @@ emu_update_kernel(EmuDev d, FrameParams p, const void *frame, const float *leak_
     }
     FrameCtrl *c = d.ctrl + slot;
     uint32_t *hist = d.hist_pre + (size_t)slot * d.seg_stride;
-    const double *su_ptr = f_cs ? (*(volatile int32_t *)d.cs_cur ? d.surround2 : d.surround) : nullptr;
+    const double *su_ptr = nullptr;
+    if (f_cs) {
+        const int cur = *(volatile int32_t *)d.cs_cur;
+        su_ptr = d.cs_bufs ? d.cs_bufs + (size_t)cur * d.cs_stride : (cur ? d.surround2 : d.surround);
+    }
     const bool shot_here = f_shot && (RNG == 1 || shot_rand != nullptr);
     const uint32_t seg_base = (uint32_t)blockIdx.x * (uint32_t)d.seg_px;
     const int so = lane * kVec;                          // element offset inside the stage arrays
@@ -920,10 +973,10 @@ emu_update_kernel(EmuDev d, FrameParams p, const void *frame, const float *leak_
                 mags[k] = mag;
                 pols[k] = neg;
             }
-            if (i0 + 4 > d.n) {                            // the frame's last, partial quad
+            if (i0 + 4 > d.own_hi || i0 < d.own_lo) {      // the frame's last, partial quad; halo rows of a sharded handle
 #pragma unroll
                 for (int k = 0; k < 4; k++)
-                    if (i0 + k >= d.n) { recs[k] = 0; mags[k] = 0; }
+                    if (i0 + k >= d.own_hi || i0 + k < d.own_lo) { recs[k] = 0; mags[k] = 0; cand[k] = false; }
             }
             if (shot_maybe) {                              // rare
 #pragma unroll
@@ -1118,7 +1171,7 @@ emu_shot_kernel(EmuDev d, FrameParams p, const void *frame, const float *shot_ra
         }
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            if (i0 + k >= d.n) continue;
+            if (i0 + k >= d.own_hi || i0 + k < d.own_lo) continue;
             int flags = shot_flags(d, p.shot_c, x[k], sr[k], thp[k], thn[k]);
             if (flags) {
                 const short old = d.rec[i0 + k];
@@ -1725,6 +1778,13 @@ struct V2eEmu {
         double *t_frames;       // [max_slots]
     } ls;
     long long n_fused_chunks, n_fused_rejected;
+    // pixel-sharded centre-surround model: plan of the current frame (v2e_emu_cs_begin) and the exchange buffers
+    int cs_K;                   // halo rows = Euler steps per chunk (0: not sharded)
+    double *cs_send, *cs_recv;  // [2][K][W]
+    int cs_num_steps;
+    double cs_alpha_p; float cs_alpha_h;
+    FrameParams cs_p;
+    int cs_pending;             // v2e_emu_cs_begin ran, v2e_emu_cs_update not yet
 };
 
 thread_local char g_err[512] = "";
@@ -1865,13 +1925,39 @@ extern "C" int v2e_emu_create(const V2eEmuCfg *cfg, V2eEmu **out) {
         ALLOC(d.pr_eff, np * h->state_elem);
         h->pr_vrms = new double[cfg->max_frames_per_step]();
     }
+    d.own_lo = 0;
+    d.own_hi = d.n;
+    d.cs_y_lo = 0;
+    d.cs_y_hi = d.H;
+    d.cs_ring = 2;
+    if (cfg->own_rows > 0) {
+        if (cfg->own_row0 < 0 || cfg->own_row0 + cfg->own_rows > d.H) { v2e_emu_destroy(h); return fail(V2E_E_INVALID, "own rows outside the handle"); }
+        d.own_lo = cfg->own_row0 * d.W;
+        d.own_hi = (cfg->own_row0 + cfg->own_rows) * d.W;
+        d.cs_y_lo = cfg->own_row0;
+        d.cs_y_hi = cfg->own_row0 + cfg->own_rows;
+    }
     if (d.csdvs) {
-        ALLOC(d.surround, np * 8);
-        ALLOC(d.surround2, np * 8);
         ALLOC(d.cs_cur, sizeof(int32_t));
         d.cs_cap = 8192;
         ALLOC(d.cs_max, (size_t)d.cs_cap * sizeof(unsigned long long));
-        d.cs_seq_order = d.n >= 20000;      // float32 conv2d summation order of the reference's CPU backend
+        // float32 conv2d summation order of the reference's CPU backend: decided by the size of the WHOLE frame
+        const long long full_px = cfg->full_frame_px ? (long long)cfg->full_frame_px : (long long)d.n;
+        d.cs_seq_order = full_px >= 20000;
+        if (cfg->cs_halo_rows > 0) {
+            const int K = cfg->cs_halo_rows;
+            if (K > d.cs_y_hi - d.cs_y_lo) { v2e_emu_destroy(h); return fail(V2E_E_INVALID, "cs_halo_rows larger than the band"); }
+            h->cs_K = K;
+            d.cs_ring = K + 1;
+            d.cs_stride = np;
+            ALLOC(d.cs_bufs, (size_t)d.cs_ring * np * 8);
+            ALLOC(d.cs_done, sizeof(int32_t));
+            ALLOC(h->cs_send, (size_t)2 * K * d.W * 8);
+            ALLOC(h->cs_recv, (size_t)2 * K * d.W * 8);
+        } else {
+            ALLOC(d.surround, np * 8);
+            ALLOC(d.surround2, np * 8);
+        }
     }
     ALLOC(h->lut_dev, 256 * 4);
     d.lut = h->lut_dev;
@@ -1912,6 +1998,8 @@ extern "C" int v2e_emu_destroy(V2eEmu *h) {
     EmuDev &d = h->d;
     delete[] h->pr_vrms;
     delete[] h->ls.t_frames;
+    void *cs_ptrs[] = {d.cs_bufs, d.cs_done, h->cs_send, h->cs_recv};
+    for (void *p : cs_ptrs) if (p) cudaFree(p);
     void *fused_ptrs[] = {h->lp_alt, h->base_alt, h->rec_list, h->rec_cnt, h->blk_cnt, h->ff_dev, h->fp_dev, h->max_vec};
     for (void *p : fused_ptrs) if (p) cudaFree(p);
     void *ptrs[] = {d.hp, d.prev_photo, d.tau_arr, d.noise_arr, d.pr_eff,
@@ -2061,6 +2149,23 @@ struct ProfScope {
 
 static size_t frame_elem(int dt) { return dt == V2E_U8 ? 1 : (dt == V2E_F32 ? 4 : 8); }
 
+// Euler-step plan of one frame of the centre-surround model (emulator.py:1068-1096)
+static int cs_plan(const V2eEmu *h, const FrameParams &p, int *num_steps, double *alpha_p, float *alpha_h) {
+    const double tau_p = h->cfg.cs_tau_p_s, tau_h = h->cfg.cs_tau_h_s;
+    const double min_tau = tau_p < tau_h ? tau_p : tau_h;
+    const int n = (int)ceil((p.dt / min_tau) * 5);                          // emulator.py:1076-1078
+    if (n < 1) return fail(V2E_E_INVALID, "csdvs: delta_time must be positive");
+    if (n > h->d.cs_cap) return fail(V2E_E_UNSUPPORTED, "csdvs: more Euler steps per frame than cs_cap (8192)");
+    const double adt = p.dt / n;
+    const double ap = adt / tau_p, ah = adt / tau_h;
+    if (ap >= 1 || ah >= 1)                                                  // emulator.py:1091-1096 quits
+        return fail(V2E_E_INVALID, "CSDVS update alpha (of IIR update) is too large; simulation would explode");
+    *num_steps = n;
+    *alpha_p = ap;
+    *alpha_h = (float)ah;
+    return V2E_OK;
+}
+
 // enqueue the counting kernels of one frame into `slot`
 static int enqueue_count(V2eEmu *h, const FrameParams &p, const void *frame, int dtype, const float *lr,
                          const float *sr, int shot_pending, int slot, cudaStream_t st, const float *pr_randn = nullptr) {
@@ -2099,19 +2204,15 @@ static int enqueue_count(V2eEmu *h, const FrameParams &p, const void *frame, int
         lp_done = 1;
     }
     if (d.csdvs) {
-        const double tau_p = h->cfg.cs_tau_p_s, tau_h = h->cfg.cs_tau_h_s;
-        const double min_tau = tau_p < tau_h ? tau_p : tau_h;
-        const int num_steps = (int)ceil((p.dt / min_tau) * 5);              // emulator.py:1076-1078
-        if (num_steps < 1) return fail(V2E_E_INVALID, "csdvs: delta_time must be positive");
-        if (num_steps > d.cs_cap) return fail(V2E_E_UNSUPPORTED, "csdvs: more Euler steps per frame than cs_cap (8192)");
-        const double adt = p.dt / num_steps;
-        const double alpha_p = adt / tau_p, alpha_h = adt / tau_h;
-        if (alpha_p >= 1 || alpha_h >= 1)                                    // emulator.py:1091-1096 quits
-            return fail(V2E_E_INVALID, "CSDVS update alpha (of IIR update) is too large; simulation would explode");
+        if (h->cs_K) return fail(V2E_E_STATE, "a pixel-sharded centre-surround handle is stepped with v2e_emu_cs_*");
+        int num_steps = 0;
+        double alpha_p = 0;
+        float alpha_h = 0;
+        if ((rc = cs_plan(h, p, &num_steps, &alpha_p, &alpha_h))) return rc;
         CU(cudaMemsetAsync(d.cs_max, 0, (size_t)num_steps * sizeof(unsigned long long), st));
         const int gs = (d.n + kThreads - 1) / kThreads;
         for (int k = 0; k < num_steps; k++)
-            emu_csdvs_step_kernel<<<gs, kThreads, 0, st>>>(d, alpha_p, (float)alpha_h, k);
+            emu_csdvs_step_kernel<<<gs, kThreads, 0, st>>>(d, alpha_p, alpha_h, k, k, 0);
         emu_csdvs_finish_kernel<<<1, 1, 0, st>>>(d, num_steps, slot);
     }
     {
@@ -2632,7 +2733,7 @@ extern "C" int v2e_emu_phase_update(V2eEmu *h, const void *frame, int dtype, dou
     // period; with one, the filter must wait for the reduced max, so launch the update kernel directly
     const EmuDev &d = h->d;
     if (d.rng_mode == 0 && d.leak_on && !lr) return fail(V2E_E_INVALID, "leak_randn field required in replay mode");
-    if (d.csdvs) return fail(V2E_E_UNSUPPORTED, "pixel sharding of the centre-surround model needs a halo exchange per Euler step (not built)");
+    if (d.csdvs) return fail(V2E_E_UNSUPPORTED, "centre-surround model: a pixel-sharded handle is stepped with v2e_emu_cs_* (cs_halo_rows > 0)");
     if (d.scidvs || d.pr_noise) return fail(V2E_E_UNSUPPORTED, "pixel sharding with scidvs / photoreceptor_noise is not built");
     rc = d.state_f64 ? launch_update<double>(h, p, frame, dtype, lr, sr, 0, 0, 0, st)
                      : launch_update<float>(h, p, frame, dtype, lr, sr, 0, 0, 0, st);
@@ -2643,6 +2744,84 @@ extern "C" int v2e_emu_phase_update(V2eEmu *h, const void *frame, int dtype, dou
 }
 
 extern "C" int32_t *v2e_emu_max_n_dev(V2eEmu *h) { return h ? &h->d.ctrl[0].max_n : nullptr; }
+
+// ---- pixel-sharded centre-surround model (see include/v2e_b200.h) ----------------------------------
+extern "C" int v2e_emu_cs_begin(V2eEmu *h, const void *frame, int dtype, double t_frame, double t_previous,
+                                uint64_t capacity, uint64_t ev_base_start, int *num_steps, void *stream) {
+    if (!h || !frame || !num_steps) return fail(V2E_E_INVALID, "null argument");
+    if (!h->first_done) return fail(V2E_E_STATE, "v2e_emu_first_frame must run first");
+    if (!h->d.csdvs || !h->cs_K) return fail(V2E_E_STATE, "not a pixel-sharded centre-surround handle (cs_halo_rows)");
+    if (h->d.scidvs || h->d.pr_noise) return fail(V2E_E_UNSUPPORTED, "pixel sharding with scidvs / photoreceptor_noise is not built");
+    if (t_frame < t_previous) return fail(V2E_E_INVALID, "frame times must be non-decreasing");
+    cudaStream_t st = (cudaStream_t)stream;
+    const EmuDev &d = h->d;
+    int rc;
+    if ((rc = reset_slots(h, 0, 1, st))) return rc;
+    emu_begin_step_kernel<<<1, 1, 0, st>>>(d, 0, ev_base_start);
+    FrameParams p = make_params(h, t_frame, t_previous, h->frame_counter++, capacity);
+    h->last_dt = p.dt;
+    if ((rc = cs_plan(h, p, &h->cs_num_steps, &h->cs_alpha_p, &h->cs_alpha_h))) return rc;
+    const int g = grid_for(d);
+    switch (dtype) {
+        case V2E_U8: emu_lp_kernel<V2E_U8><<<g, kThreads, 0, st>>>(d, p, frame); break;
+        case V2E_F32: emu_lp_kernel<V2E_F32><<<g, kThreads, 0, st>>>(d, p, frame); break;
+        case V2E_F64: emu_lp_kernel<V2E_F64><<<g, kThreads, 0, st>>>(d, p, frame); break;
+        default: return fail(V2E_E_INVALID, "bad frame dtype");
+    }
+    CU(cudaMemsetAsync(d.cs_max, 0, (size_t)h->cs_num_steps * sizeof(unsigned long long), st));
+    CU(cudaMemsetAsync(d.cs_done, 0, sizeof(int32_t), st));
+    CU(cudaGetLastError());
+    h->cs_p = p;
+    h->cs_pending = 1;
+    *num_steps = h->cs_num_steps;
+    h->last_T = 1;
+    h->last_fused = 0;
+    return V2E_OK;
+}
+extern "C" double *v2e_emu_cs_send_dev(V2eEmu *h) { return h ? h->cs_send : nullptr; }
+extern "C" double *v2e_emu_cs_recv_dev(V2eEmu *h) { return h ? h->cs_recv : nullptr; }
+extern "C" uint64_t *v2e_emu_cs_max_dev(V2eEmu *h) { return h ? (uint64_t *)h->d.cs_max : nullptr; }
+extern "C" int v2e_emu_cs_pack(V2eEmu *h, void *stream) {
+    if (!h || !h->cs_K) return fail(V2E_E_STATE, "not a pixel-sharded centre-surround handle");
+    emu_csdvs_pack_kernel<<<148, 256, 0, (cudaStream_t)stream>>>(h->d, h->cs_send, h->cs_K);
+    CU(cudaGetLastError());
+    return V2E_OK;
+}
+extern "C" int v2e_emu_cs_unpack(V2eEmu *h, void *stream) {
+    if (!h || !h->cs_K) return fail(V2E_E_STATE, "not a pixel-sharded centre-surround handle");
+    emu_csdvs_unpack_kernel<<<148, 256, 0, (cudaStream_t)stream>>>(h->d, h->cs_recv, h->cs_K);
+    CU(cudaGetLastError());
+    return V2E_OK;
+}
+extern "C" int v2e_emu_cs_chunk(V2eEmu *h, int s0, int s1, void *stream) {
+    if (!h || !h->cs_pending) return fail(V2E_E_STATE, "v2e_emu_cs_begin must precede v2e_emu_cs_chunk");
+    if (s0 < 0 || s1 <= s0 || s1 > h->cs_num_steps || s1 - s0 > h->cs_K) return fail(V2E_E_INVALID, "bad chunk of Euler steps");
+    const EmuDev &d = h->d;
+    const int gs = (d.n + kThreads - 1) / kThreads;
+    for (int s = s0; s < s1; s++)
+        emu_csdvs_step_kernel<<<gs, kThreads, 0, (cudaStream_t)stream>>>(d, h->cs_alpha_p, h->cs_alpha_h, s, s - s0, 1);
+    CU(cudaGetLastError());
+    return V2E_OK;
+}
+extern "C" int v2e_emu_cs_advance(V2eEmu *h, int s0, int s1, void *stream) {
+    if (!h || !h->cs_pending) return fail(V2E_E_STATE, "v2e_emu_cs_begin must precede v2e_emu_cs_advance");
+    emu_csdvs_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(h->d, s0, s1, 0);
+    CU(cudaGetLastError());
+    return V2E_OK;
+}
+extern "C" int v2e_emu_cs_update(V2eEmu *h, const void *frame, int dtype, const float *lr, const float *sr, void *stream) {
+    if (!h || !frame) return fail(V2E_E_INVALID, "null argument");
+    if (!h->cs_pending) return fail(V2E_E_STATE, "v2e_emu_cs_begin must precede v2e_emu_cs_update");
+    const EmuDev &d = h->d;
+    if (d.rng_mode == 0 && d.leak_on && !lr) return fail(V2E_E_INVALID, "leak_randn field required in replay mode");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = d.state_f64 ? launch_update<double>(h, h->cs_p, frame, dtype, lr, sr, 0, 0, 1, st)
+                         : launch_update<float>(h, h->cs_p, frame, dtype, lr, sr, 0, 0, 1, st);
+    if (rc) return rc;
+    CU(cudaGetLastError());
+    h->cs_pending = 0;
+    return V2E_OK;
+}
 
 extern "C" int v2e_emu_phase_filter(V2eEmu *h, double t_frame, double t_previous, uint64_t capacity, int do_plan,
                                     void *stream) {
@@ -2789,10 +2968,11 @@ extern "C" void *v2e_emu_state_ptr(V2eEmu *h, int which) {
         case 4: return h->d.noise_rate;
         case 5: return h->d.tmem;
         case 6: {
-            if (!h->d.surround) return nullptr;
+            if (!h->d.surround && !h->d.cs_bufs) return nullptr;
             int32_t cur = 0;
             cudaDeviceSynchronize();
             cudaMemcpy(&cur, h->d.cs_cur, sizeof(cur), cudaMemcpyDeviceToHost);
+            if (h->d.cs_bufs) return h->d.cs_bufs + (size_t)cur * h->d.cs_stride;
             return cur ? h->d.surround2 : h->d.surround;
         }
         case 7: return h->d.hp;

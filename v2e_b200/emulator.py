@@ -277,6 +277,7 @@ class EventEmulator(object):
             np.random.seed(seed)
             random.seed(seed)
         self.fused = bool(fused)
+        self.cs_chunk_steps = 64     # pixel-sharded centre-surround model: Euler steps per halo exchange
         self._lib = _lib.load()
         self._hbox = [None]          # the library handle, shared with the finalizer
         self._ev_dev = None
@@ -379,7 +380,7 @@ class EventEmulator(object):
         code = {torch.uint8: _lib.U8, torch.float32: _lib.F32, torch.float64: _lib.F64}[t.dtype]
         return t, code
 
-    def _create(self, H, W, px_offset=0):
+    def _create(self, H, W, px_offset=0, own=None, cs_halo=0, full_px=0):
         cfg = _lib.V2eEmuCfg()
         cfg.width, cfg.height = W, H
         cfg.per_pixel_thres = 1 if self.sigma_thres > 0 else 0
@@ -399,6 +400,10 @@ class EventEmulator(object):
         cfg.scidvs = 1 if self.scidvs else 0
         cfg.photoreceptor_noise = 1 if self.photoreceptor_noise else 0
         cfg.rng_pixel_offset = int(px_offset)
+        cfg.full_frame_px = int(full_px)
+        if own is not None:
+            cfg.own_row0, cfg.own_rows = int(own[0]), int(own[1])
+        cfg.cs_halo_rows = int(cs_halo)
         if self.csdvs_enabled:
             abs_min_tau_p = 1e-9  # emulator.py:1068-1073
             cfg.cs_tau_p_s = abs_min_tau_p if (self.cs_tau_p_ms is None or self.cs_tau_p_ms == 0) \
@@ -598,6 +603,22 @@ class EventEmulator(object):
         rank, world, _ = self.shard
         return row_band(H, rank, world)
 
+    def cs_halo_rows(self, H):
+        """Halo rows K of the pixel-sharded centre-surround model = Euler steps between two halo exchanges
+        (0 when this emulator is not a sharded centre-surround one). Bounded by the smallest band."""
+        if self.shard is None or not self.csdvs_enabled:
+            return 0
+        from .parallel import row_band
+        _, world, _ = self.shard
+        smallest = min(row_band(H, r, world)[1] - row_band(H, r, world)[0] for r in range(world))
+        return max(1, min(int(self.cs_chunk_steps), smallest))
+
+    def ext_band(self, H):
+        """Rows [ye0, ye1) this rank's handle covers: its own band plus the halo rows of the neighbours."""
+        y0, y1 = self._band(H)
+        K = self.cs_halo_rows(H)
+        return max(0, y0 - K), min(H, y1 + K)
+
     def _full_then_band(self, draw, H, W, y0, y1):
         """Every rank draws the FULL field from the same seeded generator (so the streams stay aligned
         with a single-GPU run) and keeps its rows."""
@@ -613,7 +634,7 @@ class EventEmulator(object):
         self.frame_counter += 1
         self._check_time(t_frame)
         fr, code = self._to_device_frames(band_frame)
-        y0, y1 = self._band(int(full_height))
+        y0, y1 = self.ext_band(int(full_height))       # the band (+ halo rows for the centre-surround model)
         if fr.dim() != 2 or fr.shape[0] != y1 - y0:
             raise ValueError("band_frame must hold rows [%d, %d) of the frame" % (y0, y1))
         return self._generate_sharded(fr, code, t_frame, full_height=int(full_height))
@@ -623,33 +644,42 @@ class EventEmulator(object):
         rank, world, group = self.shard
         if full_height is None:
             H, W = fr_full.shape
-            y0, y1 = self._band(H)
-            fr = fr_full[y0:y1].contiguous()
         else:
             H, W = full_height, fr_full.shape[1]
-            y0, y1 = self._band(H)
+        y0, y1 = self._band(H)
+        # rows the handle covers: the band itself, plus K halo rows either side for the centre-surround model
+        K = self.cs_halo_rows(H)
+        ye0, ye1 = self.ext_band(H)
+        if full_height is None:
+            fr = fr_full[ye0:ye1].contiguous()
+        else:
+            if fr_full.shape[0] != ye1 - ye0:
+                raise ValueError("band_frame must hold rows [%d, %d) of the frame (band + halo)" % (ye0, ye1))
             fr = fr_full.contiguous()
         hb = y1 - y0
         if hb == 0:
             raise ValueError("more ranks than pixel rows")
+        he = ye1 - ye0
         L = self._lib
         if not self._initialized:
-            self._create(hb, W, px_offset=y0 * W)       # Philox counters index the whole frame
+            # Philox counters and the conv2d summation order refer to the whole frame
+            self._create(he, W, px_offset=ye0 * W, own=(y0 - ye0, hb) if K else None, cs_halo=K, full_px=H * W)
+            self._cs_K = K
             with torch.cuda.device(self.device):
                 _lib.check(L.v2e_emu_first_frame(self._h, ctypes.c_void_p(fr.data_ptr()), code, float(t_frame),
                                                  float(self.t_previous), self._stream()))
                 pos = neg = nr = None
                 if self.sigma_thres > 0:
-                    pos = torch.clamp(self.rng.normal(self.pos_thres_nominal, self.sigma_thres, (H, W)), min=0.01)[y0:y1].contiguous()
-                    neg = torch.clamp(self.rng.normal(self.neg_thres_nominal, self.sigma_thres, (H, W)), min=0.01)[y0:y1].contiguous()
+                    pos = torch.clamp(self.rng.normal(self.pos_thres_nominal, self.sigma_thres, (H, W)), min=0.01)[ye0:ye1].contiguous()
+                    neg = torch.clamp(self.rng.normal(self.neg_thres_nominal, self.sigma_thres, (H, W)), min=0.01)[ye0:ye1].contiguous()
                 if self.leak_rate_hz > 0:
-                    nr = torch.exp(math.log(10) * self.noise_rate_cov_decades * self.rng.randn((H, W)))[y0:y1].contiguous()
+                    nr = torch.exp(math.log(10) * self.noise_rate_cov_decades * self.rng.randn((H, W)))[ye0:ye1].contiguous()
                 p = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
                 _lib.check(L.v2e_emu_set_fields(self._h, p(pos), p(neg), p(nr)))
             self._initialized = True
             self._full_h = H
             return None
-        n = hb * W
+        n = he * W
         h = self._h
         leak_on, shot_on = self.leak_rate_hz > 0, self.shot_noise_rate_hz > 0
         replay = self.rng_mode == "replay"
@@ -657,14 +687,16 @@ class EventEmulator(object):
             st = self._stream()
             lr_dev = None
             if leak_on and replay:
-                lr_dev = self._full_then_band(self.rng.randn, H, W, y0, y1).to(self.device)
+                lr_dev = self._full_then_band(self.rng.randn, H, W, ye0, ye1).to(self.device)
             self._ensure_event_buffers(self.event_rows_hint or max(4 * n, 1 << 16))
             cap = self._ev_dev.shape[0]
             tp = float(self.t_previous)
             fp = ctypes.c_void_p(fr.data_ptr())
-            _lib.check(L.v2e_emu_phase_update(h, fp, code, t_frame, tp,
-                                              None if lr_dev is None else ctypes.c_void_p(lr_dev.data_ptr()),
-                                              None, cap, 0, st))
+            lrp = None if lr_dev is None else ctypes.c_void_p(lr_dev.data_ptr())
+            if K:
+                self._cs_iterate(fp, code, t_frame, tp, cap, lrp, st, W)
+            else:
+                _lib.check(L.v2e_emu_phase_update(h, fp, code, t_frame, tp, lrp, None, cap, 0, st))
             # the frame-global maximum (emulator.py:773-775): in-place MAX over the ranks
             mx = torch.as_tensor(_DevView(L.v2e_emu_max_n_dev(h), (1,), "<i4", self), device=self.device)
             dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
@@ -688,7 +720,7 @@ class EventEmulator(object):
                     if k > 0:
                         self.rng.randperm(k)
             if shot_pending:
-                sr_dev = self._full_then_band(self.rng.rand, H, W, y0, y1).to(self.device)
+                sr_dev = self._full_then_band(self.rng.rand, H, W, ye0, ye1).to(self.device)
                 _lib.check(L.v2e_emu_phase_shot(h, fp, code, t_frame, tp, ctypes.c_void_p(sr_dev.data_ptr()), cap, st))
             _lib.check(L.v2e_emu_phase_emit(h, t_frame, tp, ctypes.c_void_p(self._ev_dev.data_ptr()), cap, st))
             fi = self._collect_one(fp, code, t_frame, tp, st)
@@ -703,8 +735,45 @@ class EventEmulator(object):
             ev = self._canonical_then_shuffle(ev, counts, [None] * m, int(fi.n_shot_on), int(fi.n_shot_off))
         finally:
             self.exact_order = saved
-        ev[:, 2] += y0
+        ev[:, 2] += ye0
         return ev
+
+    def _cs_iterate(self, fp, code, t_frame, tp, cap, lrp, st, W):
+        """Centre-surround model over row bands (emulator.py:1061-1124; BASELINE config 5): the Euler iteration in
+        chunks of K steps. Per chunk: the K own rows next to each band edge go to the neighbours (their halo rows),
+        K steps run on the band, then ONE all-reduce(MAX) of the chunk's per-step max|change| decides -- on the
+        device, identically on every rank -- whether the iteration ended inside the chunk (the first step whose
+        global maximum is <= 1e-5 is the last one applied: `cs_steps_taken` equals the single-GPU run's)."""
+        import torch.distributed as dist
+        rank, world, group = self.shard
+        L, h, K = self._lib, self._h, self._cs_K
+        ns = ctypes.c_int(0)
+        _lib.check(L.v2e_emu_cs_begin(h, fp, code, t_frame, tp, cap, 0, ctypes.byref(ns), st))
+        ns = ns.value
+        send = torch.as_tensor(_DevView(L.v2e_emu_cs_send_dev(h), (2, K, W), "<f8", self), device=self.device)
+        recv = torch.as_tensor(_DevView(L.v2e_emu_cs_recv_dev(h), (2, K, W), "<f8", self), device=self.device)
+        mxv = torch.as_tensor(_DevView(L.v2e_emu_cs_max_dev(h), (ns,), "<i8", self), device=self.device)
+        nccl = dist.get_backend(group) == "nccl"
+        if nccl:
+            gathered = torch.empty((world, 2, K, W), dtype=torch.float64, device=self.device)
+        for s0 in range(0, ns, K):
+            s1 = min(ns, s0 + K)
+            _lib.check(L.v2e_emu_cs_pack(h, st))
+            if nccl:
+                dist.all_gather_into_tensor(gathered, send, group=group)
+                parts = gathered
+            else:
+                parts = [torch.empty_like(send) for _ in range(world)]
+                dist.all_gather(parts, send.clone(), group=group)
+            if rank > 0:
+                recv[0].copy_(parts[rank - 1][1])          # the rows above: the upper neighbour's bottom edge
+            if rank < world - 1:
+                recv[1].copy_(parts[rank + 1][0])          # the rows below: the lower neighbour's top edge
+            _lib.check(L.v2e_emu_cs_unpack(h, st))
+            _lib.check(L.v2e_emu_cs_chunk(h, s0, s1, st))
+            dist.all_reduce(mxv[s0:s1], op=dist.ReduceOp.MAX, group=group)
+            _lib.check(L.v2e_emu_cs_advance(h, s0, s1, st))
+        _lib.check(L.v2e_emu_cs_update(h, fp, code, lrp, None, st))
 
     def generate_events_band_batch(self, band_frames, t_frames, full_height, return_device=False):
         """Pixel-sharded, batched (BASELINE config 5 without per-frame host work): band_frames [T, y1-y0, W] uint8,
@@ -721,7 +790,7 @@ class EventEmulator(object):
         rank, world, group = self.shard
         fr, code = self._to_device_frames(band_frames)
         H = int(full_height)
-        y0, y1 = self._band(H)
+        y0, y1 = self.ext_band(H)        # = the band, unless the centre-surround model adds halo rows
         if fr.dim() != 3 or fr.shape[1] != y1 - y0:
             raise ValueError("band_frames must be [T, %d, W]: rows [%d, %d) of every frame" % (y1 - y0, y0, y1))
         t_frames = [float(t) for t in t_frames]

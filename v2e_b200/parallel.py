@@ -45,12 +45,19 @@ def pair_range(n_pairs, rank, world):
     return p0, p0 + base + (1 if rank < extra else 0)
 
 
-def exchange_frame_bands(frames_local, height, group=None):
+def band_with_halo(height, rank, world, halo=0):
+    """row_band widened by `halo` rows either side, clipped to the frame (the centre-surround pixel model reads its
+    neighbours' rows: emulator.py:1102-1124)."""
+    y0, y1 = row_band(height, rank, world)
+    return max(0, y0 - halo), min(height, y1 + halo)
+
+
+def exchange_frame_bands(frames_local, height, group=None, halo=0):
     """frames_local: [M_r, H, W] uint8, the interpolated frames this rank synthesised (ranks hold consecutive
-    runs of the clip, in rank order). Returns [sum_r M_r, y1-y0, W]: rows `row_band(H, rank, world)` of EVERY
-    frame of the clip, in clip order. NCCL: one all-to-all of the row bands (rank r sends rank q the band q
-    of its frames). Backends without all-to-all (gloo, in the tests): every rank's frames are all-gathered
-    and cut locally."""
+    runs of the clip, in rank order). Returns [sum_r M_r, y1-y0, W]: rows `band_with_halo(H, rank, world, halo)`
+    of EVERY frame of the clip, in clip order. NCCL: one all-to-all of the row bands (rank r sends rank q the
+    band q of its frames). Backends without all-to-all (gloo, in the tests): every rank's frames are
+    all-gathered and cut locally."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     if frames_local.dim() != 3 or frames_local.dtype != torch.uint8 or frames_local.shape[1] != height:
@@ -61,9 +68,9 @@ def exchange_frame_bands(frames_local, height, group=None):
     ms = [torch.zeros_like(m) for _ in range(world)]
     dist.all_gather(ms, m, group=group)
     ms = [int(x.item()) for x in ms]
-    y0, y1 = row_band(height, rank, world)
+    y0, y1 = band_with_halo(height, rank, world, halo)
     if dist.get_backend(group) == "nccl":
-        send = [frames_local[:, a:b, :].contiguous() for a, b in (row_band(height, q, world) for q in range(world))]
+        send = [frames_local[:, a:b, :].contiguous() for a, b in (band_with_halo(height, q, world, halo) for q in range(world))]
         recv = [torch.empty((ms[r], y1 - y0, W), dtype=torch.uint8, device=dev) for r in range(world)]
         dist.all_to_all(recv, send, group=group)
         return torch.cat(recv, 0)

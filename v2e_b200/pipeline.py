@@ -54,9 +54,15 @@ class V2EPipeline:
         U = int(self.slomo.upsampling_factor)
         times = np.arange((n - 1) * U) * (1.0 / U)                       # slomo.py:391-395 for the whole clip
         assert np.allclose(times_l + p0, times[p0 * U:p1 * U])
-        bands = parallel.exchange_frame_bands(local, H, group=group)
+        bands = parallel.exchange_frame_bands(local, H, group=group, halo=self.emulator.cs_halo_rows(H))
         f = src_duration_s / (np.max(times) - np.min(times))            # v2e.py:794-797
         t = t_offset + f * times
+        if self.emulator.rng_mode == "device" or not (self.emulator.leak_rate_hz > 0 or self.emulator.shot_noise_rate_hz > 0):
+            # chunks of frames through the multi-frame kernels: one all-reduce(MAX) of the frame maxima per chunk
+            # (frame by frame -- one all-reduce each -- for a chunk the refractory filter touches, and for the
+            # centre-surround model, whose Euler iteration exchanges halo rows)
+            rows, _ = self.emulator.generate_events_band_batch(bands, t, H)
+            return rows, t, bands.shape[0]
         out = []
         for k in range(bands.shape[0]):
             ev = self.emulator.generate_events_band(bands[k], t[k], H)

@@ -956,9 +956,13 @@ emu_update_kernel(EmuDev d, FrameParams p, const void *frame, const float *leak_
                 int32_t mag = ge1 + ge2;
                 if (ge2 && !(a - b2 < b)) {                  // >= 3 events: rare
                     mag = div_floor_count<S>(a, b);
-                    local_max = max(local_max, mag);         // before the clamps: the plan reports > iter_cap
+                    // before the clamps: the plan reports > iter_cap. Own pixels only (not the halo rows of a
+                    // sharded centre-surround handle, nor the padding after the frame's last pixel)
+                    if (i0 + k >= d.own_lo && i0 + k < d.own_hi) {
+                        local_max = max(local_max, mag);
+                        deep = 1;
+                    }
                     if (mag > kRecMaxCount) mag = kRecMaxCount;
-                    deep = 1;
                 }
                 // shot noise: the exact test (below) only when the draw can possibly cross. Replay: shot_lo_f /
                 // shot_hi_f are float32 bounds rounded outwards from shot_bound >= any per-pixel probability;

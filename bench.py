@@ -120,11 +120,9 @@ def slomo_weights():
     """Seeded variance-preserving weights in the reference's checkpoint layout ('state_dictFC' /
     'state_dictAT'); the real SuperSloMo39.ckpt is not available offline (README.md:95-96)."""
     import slomo_ref
-    # flow head gain 2: sub-pixel random flows, so that the frames synthesised either side of a shared source frame
-    # agree (as a trained network's do). With the gain of 25 used by the parity tests (flows of ~1.5 px, a different
-    # random field for every pair) the clip jumps at every pair boundary; event density is the same (0.095 vs 0.099
-    # events/px/frame at 346x260) and the arithmetic work does not depend on the weights' values.
-    return {"state_dictFC": slomo_ref.make_test_weights(1234, 2, 4, head_gain=2.0),
+    # flow head gain 25 (flows of ~1.5 px, as in the parity tests and in round 1); V2E_BENCH_FLOW_GAIN overrides
+    g = float(os.environ.get("V2E_BENCH_FLOW_GAIN", "25"))
+    return {"state_dictFC": slomo_ref.make_test_weights(1234, 2, 4, head_gain=g),
             "state_dictAT": slomo_ref.make_test_weights(4321, 12, 5, head_gain=0.3)}
 
 
@@ -314,9 +312,11 @@ def main():
         pipe = V2EPipeline(sl, em)
         k = 0
 
+        period = clip_seconds * n_frames / (n_frames - 1)      # the next pass starts one frame interval after the last frame
+
         def one():
             nonlocal k
-            t0 = k * clip_seconds
+            t0 = k * period
             k += 1
             if e2e:
                 # host frames in (pinned), packed rows out through the emulator's pinned staging buffer on EVERY
@@ -435,7 +435,11 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     _a, _b = ctypes.c_longlong(0), ctypes.c_longlong(0)
     pipe.emulator._lib.v2e_emu_fused_stats(pipe.emulator._h, ctypes.byref(_a), ctypes.byref(_b))
+    _c, _d = ctypes.c_int(0), ctypes.c_int(0)
+    pipe.emulator._lib.v2e_emu_fused_last_reject(pipe.emulator._h, ctypes.byref(_c), ctypes.byref(_d))
     chunk_stats = {"multi_frame": _a.value, "rejected_and_replayed": _b.value}
+    if _b.value:
+        chunk_stats["last_rejected_at"] = {"frame_in_chunk": _c.value, "max_events_of_one_pixel": _d.value}
 
     # ---- roofline of the dominant kernel (UNet convolutions, tensor pipe) and of the pixel model (HBM) ----
     prof = {}
@@ -448,7 +452,7 @@ def main():
         k0 = args.steps + args.warmup
         torch.cuda.synchronize()
         w0 = time.perf_counter()
-        pipe.run(src_dev, clip_s, t_offset=k0 * clip_s, return_device=True)
+        pipe.run(src_dev, clip_s, t_offset=k0 * clip_s * n_interp / (n_interp - 1), return_device=True)
         torch.cuda.synchronize()
         step_ms_prof = (time.perf_counter() - w0) * 1e3
         conv_ms, conv_n, conv_fl = ctypes.c_float(0), ctypes.c_int(0), ctypes.c_double(0)
@@ -573,7 +577,7 @@ def main():
                        "events_per_px_per_frame": ev_dev / steps / world / (n_interp * H * W),
                        "l2_policy": "activations of one UNet pass (>2 GB at batch 8) exceed L2",
                        "rng": "device philox",
-                       "weights": "seeded random, reference checkpoint layout (flow head gain 2: sub-pixel flows)",
+                       "weights": "seeded random, reference checkpoint layout",
                        "pixel_model_chunks": chunk_stats,
                        "sharding": "one independent clip per GPU; NCCL gather of the event streams per step"},
             "interp_frames_per_s": world * n_interp * steps / (ms_dev * 1e-3),

@@ -62,7 +62,7 @@ def run_config5(args, rank, world, local_rank, pk):
 
     def one(timed):
         nonlocal total, chk, k
-        t0 = k * clip_s
+        t0 = k * clip_s * n_frames / (n_frames - 1)      # the next pass starts one frame interval after the last frame
         k += 1
         if world > 1:
             rows, t, nf = pipe.run_clip_sharded(src, clip_s, t_offset=t0)

@@ -164,6 +164,9 @@ int32_t *v2e_emu_max_vec_dev(V2eEmu *h);
 int v2e_emu_fused_emit(V2eEmu *h, float *events_out_dev, uint64_t capacity, uint64_t ev_base_start, void *stream);
 /* counters: chunks that went through the fast path / chunks it rejected */
 int v2e_emu_fused_stats(V2eEmu *h, long long *chunks, long long *rejected);
+/* diagnostics: the frame (index in its chunk) at which the last rejected chunk broke the assumption, and that frame's
+ * max_num_events_any_pixel */
+int v2e_emu_fused_last_reject(V2eEmu *h, int *frame, int *max_n);
 /* Measurement: K repetitions of the fast path of one chunk (update, count, plan, emit; no commit, so the state is
  * left untouched and every repetition does the same work) between one CUDA-event pair, and K repetitions of the
  * update kernel alone between another. Returns microseconds per chunk. Synchronises. */
@@ -361,6 +364,19 @@ int v2e_resize_run_strided(V2eResizer *r, const uint8_t *src_dev, uint8_t *dst_d
                            long dst_image_stride, void *stream);
 
 /* ------------------------------------------------------------------------- */
+/* Stage-1 input preparation (v2e.py:687-737): crop, cv2.resize(INTER_AREA), BGR -> luma for
+ * 8-bit frames, bit-exact with OpenCV 4.x. src_dev: [n][src_h][src_w][channels] uint8 (channels 1 = grey, 3 = BGR as
+ * cv2 delivers); crop_* as v2e's --crop (pixels removed at the left / right / top / bottom, <= 0: none);
+ * dst_dev: [n][dst_h][dst_w] uint8 luma -- what v2e.py:733-737 saves as source frames. Shrinking (or equal size)
+ * only: OpenCV treats an INTER_AREA enlargement as bilinear, which is not built (V2E_E_UNSUPPORTED). */
+/* ------------------------------------------------------------------------- */
+typedef struct V2ePrep V2ePrep;
+int v2e_prep_create(int src_w, int src_h, int channels, int crop_left, int crop_right, int crop_top, int crop_bottom,
+                    int dst_w, int dst_h, V2ePrep **out);
+int v2e_prep_destroy(V2ePrep *h);
+int v2e_prep_run(V2ePrep *h, const uint8_t *src_dev, int n_images, uint8_t *dst_dev, void *stream);
+
+/* ------------------------------------------------------------------------- */
 /* Event-sink row conversions: packed rows [t, x, y, p] float32 -> what the reference's writers
  * store. events_dev: [n][4] float32, 16-byte aligned. Enqueue only.                                             */
 /* ------------------------------------------------------------------------- */
@@ -374,6 +390,18 @@ int v2e_events_to_h5_rows(const float *events_dev, uint64_t n, uint32_t *rows_de
 int v2e_events_to_aedat2(const float *events_dev, uint64_t n, int size_x, int size_y, int x_shift, int y_shift,
                          int pol_shift, int flip_x, int flip_y, uint32_t *words_dev, uint64_t *n_on_dev,
                          void *stream);
+
+/* ------------------------------------------------------------------------- */
+/* DVS frame rendering: the histogram of EventRenderer.render_events_to_frames
+ * (v2ecore/renderer.py:392-430, v2ecore/v2e_utils.py:474-486). Frame f takes the event rows
+ * [starts_dev[f], ends_dev[f]) of events_dev ([n][4] float32 [t, x, y, p]; slices may overlap, as the reference's do):
+ * ON minus OFF per pixel, clipped to +-full_scale_count. acc_dev: [n_frames][H][W] int32 scratch;
+ * frames_f64_dev (nullable): (frame + fs) / (2 fs) float64, what the reference returns; frames_u8_dev (nullable):
+ * uint8(img * 255), what it writes to the AVI (renderer.py:345-347). max_events_per_frame sizes the grid. */
+/* ------------------------------------------------------------------------- */
+int v2e_render_frames(const float *events_dev, const int64_t *starts_dev, const int64_t *ends_dev, int n_frames,
+                      int64_t max_events_per_frame, int height, int width, int full_scale_count, int32_t *acc_dev,
+                      double *frames_f64_dev, uint8_t *frames_u8_dev, void *stream);
 
 #ifdef __cplusplus
 }

@@ -56,6 +56,7 @@ _SIGS = {
     "v2e_emu_max_vec_dev": (_vp, [_vp]),
     "v2e_emu_fused_emit": (_i, [_vp, _vp, _u64, _u64, _vp]),
     "v2e_emu_fused_stats": (_i, [_vp, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong)]),
+    "v2e_emu_fused_last_reject": (_i, [_vp, ctypes.POINTER(_i), ctypes.POINTER(_i)]),
     "v2e_emu_time_fused": (_i, [_vp, _vp, _i, _i, _vp, _d, _vp, _u64, _i, ctypes.POINTER(ctypes.c_float),
                                 ctypes.POINTER(ctypes.c_float), _vp]),
     "v2e_emu_create": (_i, [ctypes.POINTER(V2eEmuCfg), ctypes.POINTER(_vp)]),
@@ -110,6 +111,10 @@ _SIGS = {
     "v2e_resize_run_strided": (_i, [_vp, _vp, _vp, _i, ctypes.c_long, _vp]),
     "v2e_emu_set_scidvs_tau": (_i, [_vp, _vp]),
     "v2e_emu_set_pr_noise": (_i, [_vp, _vp, ctypes.POINTER(_d), _i]),
+    "v2e_prep_create": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _i, ctypes.POINTER(_vp)]),
+    "v2e_prep_destroy": (_i, [_vp]),
+    "v2e_prep_run": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "v2e_render_frames": (_i, [_vp, _vp, _vp, _i, ctypes.c_int64, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "v2e_events_to_h5_rows": (_i, [_vp, _u64, _vp, _vp]),
     "v2e_events_to_aedat2": (_i, [_vp, _u64, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "v2e_emu_profile": (_i, [_vp, _i]),

@@ -22,6 +22,8 @@ UNITS = {
     "slomo.cu": [],
     "conv_tc.cu": [],
     "sinks.cu": [],
+    "prep.cu": [],
+    "render.cu": [],
 }
 
 

@@ -1782,6 +1782,7 @@ struct V2eEmu {
         double *t_frames;       // [max_slots]
     } ls;
     long long n_fused_chunks, n_fused_rejected;
+    int last_reject_frame, last_reject_max_n;      // diagnostics: where and why the last chunk was rejected
     // pixel-sharded centre-surround model: plan of the current frame (v2e_emu_cs_begin) and the exchange buffers
     int cs_K;                   // halo rows = Euler steps per chunk (0: not sharded)
     double *cs_send, *cs_recv;  // [2][K][W]
@@ -2439,6 +2440,12 @@ extern "C" int v2e_emu_fused_stats(V2eEmu *h, long long *chunks, long long *reje
     if (rejected) *rejected = h->n_fused_rejected;
     return V2E_OK;
 }
+extern "C" int v2e_emu_fused_last_reject(V2eEmu *h, int *frame, int *max_n) {
+    if (!h) return fail(V2E_E_INVALID, "null handle");
+    if (frame) *frame = h->last_reject_frame;
+    if (max_n) *max_n = h->last_reject_max_n;
+    return V2E_OK;
+}
 extern "C" int32_t *v2e_emu_max_vec_dev(V2eEmu *h) { return h ? h->max_vec : nullptr; }
 
 __global__ void emu_gather_max_kernel(EmuDev d, int T, int32_t *max_vec) {
@@ -2607,6 +2614,8 @@ extern "C" int v2e_emu_collect(V2eEmu *h, V2eFrameInfo *info, int T, int *frames
         // frame indices, continuing at the row where the first part ends.
         const int fb = h->abort_host[1];
         h->n_fused_rejected++;
+        h->last_reject_frame = fb;
+        h->last_reject_max_n = (fb >= 0 && fb < T) ? h->ctrl_host[fb].max_n : -1;
         const int mode = h->last_fused;
         h->last_fused = 0;
         h->frame_counter = h->step_base;

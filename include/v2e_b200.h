@@ -334,6 +334,10 @@ int v2e_slomo_max_flow(V2eSlomo *h, float *max_speed_host, void *stream);
  * out_u8_dev: [B][H][W] = uint8((Ft_p + 0.428) * 255) as torchvision's ToPILImage computes it;
  * out_f32_dev: optional [B][H][W] float32 Ft_p before quantisation (parity probe), may be NULL. */
 int v2e_slomo_interp(V2eSlomo *h, double t, uint8_t *out_u8_dev, float *out_f32_dev, void *stream);
+/* fp16 range guard: *nonfinite_host = 1 if, since the last call, any fp32 network head (flows, residual flows,
+ * visibility) or blended pixel was inf / nan -- what fp16 activations beyond 65504 turn into. Resets the flag.
+ * Synchronises. The Python class raises FloatingPointError on it (no silent garbage frames). */
+int v2e_slomo_check_finite(V2eSlomo *h, int *nonfinite_host, void *stream);
 /* option 0: force the per-tap convolution kernel for every layer; option 1: do not fold the up-sampling into
  * up5.conv1; option 2: do not fuse the average pools into the epilogues of conv2 / down1.conv2 (A/B measurements
  * and bit-identity tests: the fused pool must equal the separate kernel exactly), value 0/1 */

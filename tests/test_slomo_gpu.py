@@ -394,3 +394,67 @@ def test_fused_average_pool_is_bit_identical_to_the_separate_kernel():
             outs.append((flow, ft.clone(), out.clone()))
         assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
         eng.close()
+
+
+def _scaled(sd, first, last, names=("conv1", "conv3")):
+    out = {k: v.clone() for k, v in sd.items()}
+    out[names[0] + ".weight"] *= first
+    out[names[0] + ".bias"] *= first
+    out[names[1] + ".weight"] *= last
+    return out
+
+
+def test_fp16_dynamic_range_large_activations_still_match_float32():
+    """The reference computes in float32 (TF32 multiplies on Ampere+); here operands are fp16 (same 10-bit mantissa,
+    5-bit exponent). Weights scaled so that every hidden activation is ~400x larger (thousands, where fp16's absolute
+    spacing is 2-8) with the head scaled back: LeakyReLU networks are positively homogeneous, so the float32 result
+    is the unscaled one and the fp16 path must still match it to the usual tolerance -- relative precision, not
+    absolute, is what the layers need. Biases of the hidden layers are scaled consistently by the first layer only,
+    so this is not an exact rescaling: the comparison is against the float32 reference of the SAME scaled weights."""
+    from v2e_b200.slomo import SloMoEngine
+    sd_fc, sd_at = _weights(3)
+    sd_fc, sd_at = _scaled(sd_fc, 400.0, 1 / 400.0), _scaled(sd_at, 400.0, 1 / 400.0)
+    H, W, B = 96, 128, 2
+    frames = np.stack([np.asarray(f) for f in __import__("make_golden_slomo_frames").smooth_frames(B + 1, H, W, 5)])
+    eng = SloMoEngine(sd_fc, sd_at, (W, H), B, DEV)
+    eng.set_pairs(torch.from_numpy(frames).to(DEV))
+    flow = eng.flow_out().clone().cpu()[..., :4].permute(0, 3, 1, 2)
+    I, _ = slomo_ref.load_pair_tensors(frames, (W, H))
+    ref_flow, ref_outs = slomo_ref.interp_batch(sd_fc, sd_at, I[:B], I[1:B + 1], 2)
+    rms = ref_flow.pow(2).mean().sqrt().item()
+    assert torch.isfinite(flow).all()
+    assert (flow - ref_flow).abs().max().item() < 0.03 * rms + 0.03, ((flow - ref_flow).abs().max().item(), rms)
+    out = torch.empty((B, H, W), dtype=torch.uint8, device=DEV)
+    ft = torch.empty((B, H, W), dtype=torch.float32, device=DEV)
+    for k in range(2):
+        eng.interp((k + 0.5) / 2, out, ft)
+        d = (ft.cpu() - ref_outs[k][1][:, 0]).abs()
+        assert d.max().item() < 0.02 and d.mean().item() < 0.002, (d.max().item(), d.mean().item())
+    eng.check_finite()
+    eng.close()
+
+
+def test_fp16_overflow_fails_loudly():
+    """Activations beyond fp16's 65504 become inf / nan in the heads: the drop-in must raise, not return garbage frames."""
+    from v2e_b200 import SuperSloMo
+    sd_fc, sd_at = _weights(3)
+    sd_at = _scaled(sd_at, 3.0e5, 1.0)
+    frames = np.stack([np.asarray(f) for f in __import__("make_golden_slomo_frames").smooth_frames(3, 96, 128, 5)])
+    sl = SuperSloMo(model=None, auto_upsample=False, upsampling_factor=2, batch_size=2,
+                    state_dicts={'state_dictFC': sd_fc, 'state_dictAT': sd_at})
+    with pytest.raises(FloatingPointError):
+        sl.interpolate_frames(frames)
+    sl.cleanup()
+
+
+def test_end_to_end_event_delta_of_the_fp16_slomo():
+    """SURVEY.md 8(d) parity criterion for the reduced-precision SloMo: "report max / mean abs diff of the uint8 frames
+    and the induced event-count delta". Same source frames (scripts/gradients.py's moving bump, 346x260, x10) through
+    the fp16 tensor-core SloMo and through the float32 restatement of the reference; both frame sets through the same
+    pixel model with noise off. Bars: frames within 3 DN (observed 1), events within 1 % in total and per polarity."""
+    import bench
+    d = bench.slomo_event_delta(DEV, bench.slomo_weights())
+    assert d["dn_max"] <= 3 and d["dn_mean"] < 0.3, d
+    assert d["events_fp32"] > 10000
+    assert abs(d["delta_events"]) <= 0.01 * d["events_fp32"], d
+    assert abs(d["delta_on"]) <= 0.01 * d["events_fp32"] and abs(d["delta_off"]) <= 0.01 * d["events_fp32"], d

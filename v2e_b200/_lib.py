@@ -97,6 +97,7 @@ _SIGS = {
     "v2e_slomo_max_flow": (_i, [_vp, ctypes.POINTER(ctypes.c_float), _vp]),
     "v2e_slomo_interp": (_i, [_vp, _d, _vp, _vp, _vp]),
     "v2e_slomo_set_option": (_i, [_vp, _i, _i]),
+    "v2e_slomo_check_finite": (_i, [_vp, ctypes.POINTER(_i), _vp]),
     "v2e_slomo_profile": (_i, [_vp, _i]),
     "v2e_slomo_profile_read": (_i, [_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_i),
                                     ctypes.POINTER(ctypes.c_double), _vp]),

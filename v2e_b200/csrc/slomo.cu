@@ -214,7 +214,7 @@ __global__ void pre_interp_kernel(const float *__restrict__ img, const float *__
 // slomo.py:421-437: refined flows, visibility, warps, blend, de-normalise, uint8 truncation
 __global__ void post_interp_kernel(const float *__restrict__ img, const float *__restrict__ flow,
                                    const float *__restrict__ intrp, uint8_t *__restrict__ out,
-                                   float *__restrict__ out_f32, int B, int H, int W, FlowCoef k) {
+                                   float *__restrict__ out_f32, int B, int H, int W, FlowCoef k, int *nonfinite) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const long HW = (long)H * W;
     if (i >= (long)B * HW) return;
@@ -232,6 +232,11 @@ __global__ void post_interp_kernel(const float *__restrict__ img, const float *_
     const float g1 = backwarp(I1, H, W, x, y, ft1x, ft1y);
     const float ft = (k.w0 * v0 * g0 + k.w1 * v1 * g1) / (k.w0 * v0 + k.w1 * v1);
     if (out_f32) out_f32[i] = ft;
+    // fp16 activations that overflowed (a checkpoint whose dynamic range exceeds 65504) surface here as inf / nan in
+    // the fp32 network heads or in the blended value: flag it, v2e_slomo_check_finite reports it (fail loudly)
+    if (!(isfinite(f.x) && isfinite(f.y) && isfinite(f.z) && isfinite(f.w) && isfinite(r0.x) && isfinite(r0.y) &&
+          isfinite(r0.z) && isfinite(r0.w) && isfinite(vlogit) && isfinite(ft)))
+        *nonfinite = 1;
     // revNormalize then ToPILImage: (x + 0.428).mul(255).byte() -- CPU float->uint8 conversion
     // truncates toward zero and wraps modulo 256
     const float s = (ft + kMean) * 255.0f;
@@ -369,6 +374,7 @@ struct V2eSlomo {
     float *flow_out, *intrp_out;  // [B,H,W,8] fp32
     float *img;                   // [B+1,H,W] fp32
     float *maxspeed;              // device scalar
+    int *nonfinite;               // device flag: a network head or a blended pixel was inf / nan
     int curB;
     std::vector<char> launch_mem, row_mem, up_mem;
     int n_sms, force_tap_kernel, no_fused_up, no_fused_pool;
@@ -471,6 +477,8 @@ extern "C" int v2e_slomo_create(int H, int W, int max_batch, const V2eUNetWeight
     CU(cudaMalloc((void **)&h->intrp_out, B * HW * 8 * sizeof(float)));
     CU(cudaMalloc((void **)&h->img, (B + 1) * HW * sizeof(float)));
     CU(cudaMalloc((void **)&h->maxspeed, sizeof(float)));
+    CU(cudaMalloc((void **)&h->nonfinite, sizeof(int)));
+    CU(cudaMemset(h->nonfinite, 0, sizeof(int)));
     h->launch_mem.resize(v2e_conv_launch_size());
     h->row_mem.resize(v2e_strip_launch_size());
     { int dev = 0; cudaGetDevice(&dev); h->n_sms = 148; cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, dev); }
@@ -486,7 +494,7 @@ extern "C" int v2e_slomo_destroy(V2eSlomo *h) {
     if (!h) return V2E_OK;
     for (UNet *u : {&h->flow, &h->interp})
         for (int i = 0; i < 23; i++) { if (u->w[i]) cudaFree(u->w[i]); if (u->b[i]) cudaFree(u->b[i]); if (u->w_row[i]) cudaFree(u->w_row[i]); if (u->w_fold[i]) cudaFree(u->w_fold[i]); }
-    void *ptrs[] = {h->in16, h->x0, h->s1, h->flow_out, h->intrp_out, h->img, h->maxspeed};
+    void *ptrs[] = {h->in16, h->x0, h->s1, h->flow_out, h->intrp_out, h->img, h->maxspeed, h->nonfinite};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int l = 0; l < 5; l++) {
         cudaFree(h->pool[l]); cudaFree(h->da[l]); cudaFree(h->s[l]);
@@ -642,9 +650,19 @@ extern "C" int v2e_slomo_interp(V2eSlomo *h, double t, uint8_t *out_u8_dev, floa
     pre_interp_kernel<<<cdiv(n, 256), 256, 0, st>>>(h->img, h->flow_out, h->in16, B, h->H, h->W, k);
     int rc = unet_forward(h, h->interp, h->in16, h->intrp_out, B, st);
     if (rc) return rc;
-    post_interp_kernel<<<cdiv(n, 256), 256, 0, st>>>(h->img, h->flow_out, h->intrp_out, out_u8_dev, out_f32_dev, B, h->H, h->W, k);
+    post_interp_kernel<<<cdiv(n, 256), 256, 0, st>>>(h->img, h->flow_out, h->intrp_out, out_u8_dev, out_f32_dev, B, h->H, h->W, k,
+                                                     h->nonfinite);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return v2e_set_error(V2E_E_CUDA, "v2e_slomo_interp: %s", cudaGetErrorString(e));
+    return V2E_OK;
+}
+
+extern "C" int v2e_slomo_check_finite(V2eSlomo *h, int *nonfinite_host, void *stream) {
+    if (!h || !nonfinite_host) return v2e_set_error(V2E_E_INVALID, "null argument%s", "");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaMemcpyAsync(nonfinite_host, h->nonfinite, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemsetAsync(h->nonfinite, 0, sizeof(int), st));
+    CU(cudaStreamSynchronize(st));
     return V2E_OK;
 }
 

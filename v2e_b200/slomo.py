@@ -128,6 +128,17 @@ class SloMoEngine:
             _lib.check(self.lib.v2e_resize_run_strided(self._rout, ctypes.c_void_p(self._net_out.data_ptr()),
                                                        ctypes.c_void_p(out_u8_dev.data_ptr()), b, stride, self._stream()))
 
+    def check_finite(self):
+        """Raises FloatingPointError if a network head or a blended pixel was inf / nan since the last check: the
+        convolutions run on fp16 operands (fp32 accumulation), a checkpoint whose activations exceed 65504 overflows.
+        One small D2H read (synchronises the stream)."""
+        bad = ctypes.c_int(0)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.v2e_slomo_check_finite(self._h, ctypes.byref(bad), self._stream()))
+        if bad.value:
+            raise FloatingPointError("SuperSloMo produced non-finite values: fp16 activations overflowed "
+                                     "(this checkpoint needs a wider dynamic range than the fp16 tensor-core path has)")
+
     def _view(self, ptr_fn):
         from .emulator import _DevView
         ptr = ptr_fn(self._h)
@@ -246,6 +257,7 @@ class SuperSloMo(object):
                 chunks.append(blk)
         if fixed is None:
             out = torch.cat(chunks, 0)
+        self._engine.check_finite()
         return out, np.concatenate(times), sum(ups) / len(ups)
 
     # -- reference file API ----------------------------------------------------------------------
@@ -283,6 +295,7 @@ class SuperSloMo(object):
             out_ctr += host.shape[0]
             times.append(tt)
             ups.append(U)
+        self._engine.check_finite()
         interp_times, avg = np.concatenate(times), sum(ups) / len(ups)
         logger.info('Wrote {} frames and returning {} frame times.\nAverage upsampling factor={:5.1f}'.format(
             out_ctr, len(interp_times), avg))

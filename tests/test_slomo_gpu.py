@@ -59,6 +59,8 @@ CONV_CASES = [
     (1, 16, 32, 12, 0, 32, 7, 0), (1, 8, 10, 512, 0, 512, 3, 0), (1, 16, 20, 512, 512, 512, 3, 0),
     (1, 64, 80, 32, 32, 32, 3, 0), (1, 32, 40, 64, 64, 64, 3, 0), (1, 32, 32, 32, 0, 5, 3, 1),
     (1, 32, 32, 32, 0, 4, 3, 1), (2, 64, 96, 256, 0, 128, 3, 0), (1, 5, 7, 128, 0, 256, 3, 0),
+    # grids large enough for the N = 256 tiles (256 / 512 output channels, >= one wave of 2 CTAs per SM)
+    (4, 88, 160, 128, 0, 256, 3, 0), (8, 44, 80, 256, 256, 512, 3, 0), (8, 41, 75, 512, 0, 512, 3, 0),
 ]
 
 

@@ -44,6 +44,7 @@ struct ConvParams {
     int KH, KW;
     int KC;                     // channels per K slab: 64 / 32 / 16  -> swizzle 128B / 64B / 32B
     int BN;                     // output channels per CTA (UMMA N)
+    int stages;                 // depth of the producer / issuer ring (<= kStages)
     int tiles_x, tiles_y;
     int out_cstride;            // channel stride (elements) of the fp16 NHWC output
     int out_mode;               // 0: fp16 NHWC; 1: fp32 [N,H,W,8], first co_real channels
@@ -112,7 +113,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (c < p.C1) tma_load_4d(sa, &tmA, &full_bar[stage], c, x0 + s - pw, y0 + r - ph, n);
                     else tma_load_4d(sa, &tmA2, &full_bar[stage], c - p.C1, x0 + s - pw, y0 + r - ph, n);
                     tma_load_2d(sb, &tmB, &full_bar[stage], tap * Ctot + c, n0);
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -136,7 +137,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 umma_f16_pred(tmem_acc, desc_with_lo(dhi, alo + 2u * j), desc_with_lo(dhi, blo + 2u * j), idesc,
                               (uint32_t)((it | j) != 0), leader);
             umma_commit_pred(&empty_bar[stage], leader);     // frees the smem slot once these MMAs retire
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         umma_commit_pred(&tmem_full_bar, leader);            // accumulator complete
     } else {
@@ -1105,6 +1106,19 @@ int v2e_conv_pick_kc(int C1, int C2) {
     return g % 64 == 0 ? 64 : (g % 32 == 0 ? 32 : 16);
 }
 int v2e_conv_pick_bn(int Cout_pad) { return Cout_pad >= 128 ? 128 : Cout_pad; }
+// N = 256 tiles for the 256 / 512-channel layers: an A window (the shifted 8x16 input patch, re-fetched through L2 for
+// every filter tap) then feeds twice the math, 94 instead of 125 bytes per clock and SM from L2 at full tensor rate.
+// Two ring stages of 48 KB keep two CTAs per SM (and 2 x 256 TMEM columns). Only when the grid still fills the
+// machine: at least one full wave of 2 CTAs per SM. V2E_CONV_BN256=0 disables it (A/B measurements).
+static int conv_use_bn256(int Cout_pad, long tiles) {
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("V2E_CONV_BN256"); on = e ? atoi(e) : 1; }
+    if (!on || Cout_pad % 256) return 0;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return tiles * (Cout_pad / 256) >= 2L * sms;
+}
 
 struct V2eConvLaunch {
     CUtensorMap tmA, tmA2, tmB;
@@ -1123,8 +1137,10 @@ int v2e_conv_prepare(V2eConvLaunch *L, const void *x1, int C1, const void *x2, i
     p.N = N; p.H = H; p.W = W; p.C1 = C1; p.C2 = C2; p.KH = KH; p.KW = KW;
     p.KC = v2e_conv_pick_kc(C1, C2);
     p.BN = v2e_conv_pick_bn(Cout_pad);
+    p.stages = kStages;
     p.tiles_x = (W + kTileW - 1) / kTileW;
     p.tiles_y = (H + kTileH - 1) / kTileH;
+    if (out_mode == 0 && conv_use_bn256(Cout_pad, (long)p.tiles_x * p.tiles_y * N)) { p.BN = 256; p.stages = 2; }
     p.out_cstride = out_cstride; p.out_mode = out_mode; p.co_real = co_real; p.slope = slope;
     p.bias = bias; p.out = out;
     int rc;
@@ -1134,7 +1150,7 @@ int v2e_conv_prepare(V2eConvLaunch *L, const void *x1, int C1, const void *x2, i
     if ((rc = v2e_make_wgt_tmap(&L->tmB, wgt, Cout_pad, KH * KW * (C1 + C2), p.KC, p.BN))) return rc;
     L->grid = dim3((unsigned)(p.tiles_x * p.tiles_y * N), (unsigned)(Cout_pad / p.BN), 1);
     size_t stage = (size_t)kBM * p.KC * 2 + (((size_t)p.BN * p.KC * 2 + 1023) & ~(size_t)1023);
-    L->smem = stage * kStages + 1024;
+    L->smem = stage * p.stages + 1024;
     return V2E_OK;
 }
 

@@ -1783,6 +1783,7 @@ struct V2eEmu {
     } ls;
     long long n_fused_chunks, n_fused_rejected;
     int last_reject_frame, last_reject_max_n;      // diagnostics: where and why the last chunk was rejected
+    int fused_skip, fused_penalty;                 // back-off: chunks to run frame by frame before the next attempt
     // pixel-sharded centre-surround model: plan of the current frame (v2e_emu_cs_begin) and the exchange buffers
     int cs_K;                   // halo rows = Euler steps per chunk (0: not sharded)
     double *cs_send, *cs_recv;  // [2][K][W]
@@ -2581,8 +2582,12 @@ extern "C" int v2e_emu_step(V2eEmu *h, const void *frames, int dtype, int T, con
         }
         return V2E_OK;
     }
-    const bool want_fused = h->fused_enable && T >= 2 && first == 0 && !resume_emit && !leak_randn && !shot_rand &&
-                            fused_config_ok(h, dtype);
+    bool want_fused = h->fused_enable && T >= 2 && first == 0 && !resume_emit && !leak_randn && !shot_rand &&
+                      fused_config_ok(h, dtype);
+    // back-off: input whose chunks keep being rejected early (a pixel with >= dt / refractory events in some frame)
+    // pays for the wasted multi-frame pass; after a rejection in the first half of a chunk the next 1, 2, 4, ... 64
+    // chunks go frame by frame before the multi-frame path is tried again
+    if (want_fused && h->fused_skip > 0) { h->fused_skip--; want_fused = false; }
     if (want_fused) {
         if ((rc = fused_alloc(h))) return rc;
         if (h->fused_max_T >= T) {
@@ -2616,6 +2621,10 @@ extern "C" int v2e_emu_collect(V2eEmu *h, V2eFrameInfo *info, int T, int *frames
         h->n_fused_rejected++;
         h->last_reject_frame = fb;
         h->last_reject_max_n = (fb >= 0 && fb < T) ? h->ctrl_host[fb].max_n : -1;
+        if (2 * fb < T) {
+            h->fused_penalty = h->fused_penalty ? (h->fused_penalty < 64 ? 2 * h->fused_penalty : 64) : 1;
+            h->fused_skip = h->fused_penalty;
+        }
         const int mode = h->last_fused;
         h->last_fused = 0;
         h->frame_counter = h->step_base;
@@ -2639,6 +2648,7 @@ extern "C" int v2e_emu_collect(V2eEmu *h, V2eFrameInfo *info, int T, int *frames
         CU(cudaStreamSynchronize(st));
     }
     int status = h->abort_host[0], done = status ? h->abort_host[1] : T;
+    if (!status && h->last_fused == 1 && h->fused_T == T) h->fused_penalty = 0;       // a whole chunk accepted
     uint64_t rows = 0;
     for (int f = 0; f < T; f++) {
         const FrameCtrl &c = h->ctrl_host[f];

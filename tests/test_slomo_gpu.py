@@ -61,6 +61,8 @@ CONV_CASES = [
     (1, 32, 32, 32, 0, 4, 3, 1), (2, 64, 96, 256, 0, 128, 3, 0), (1, 5, 7, 128, 0, 256, 3, 0),
     # grids large enough for the N = 256 tiles (256 / 512 output channels, >= one wave of 2 CTAs per SM)
     (4, 88, 160, 128, 0, 256, 3, 0), (8, 44, 80, 256, 256, 512, 3, 0), (8, 41, 75, 512, 0, 512, 3, 0),
+    # ... and for two pixel tiles per CTA (128 output channels; odd tile counts, concatenated input)
+    (8, 88, 160, 64, 0, 128, 3, 0), (8, 83, 150, 64, 64, 128, 3, 0), (6, 72, 160, 128, 0, 128, 3, 0),
 ]
 
 

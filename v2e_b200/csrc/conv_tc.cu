@@ -45,6 +45,7 @@ struct ConvParams {
     int KC;                     // channels per K slab: 64 / 32 / 16  -> swizzle 128B / 64B / 32B
     int BN;                     // output channels per CTA (UMMA N)
     int stages;                 // depth of the producer / issuer ring (<= kStages)
+    int MT;                     // 8x16 pixel tiles per CTA (1 or 2, stacked vertically: M = 128 or 2 x 128)
     int tiles_x, tiles_y;
     int out_cstride;            // channel stride (elements) of the fp16 NHWC output
     int out_mode;               // 0: fp16 NHWC; 1: fp32 [N,H,W,8], first co_real channels
@@ -63,19 +64,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t a_bytes = kBM * p.KC * 2;
     const uint32_t b_bytes_raw = p.BN * p.KC * 2;
     const uint32_t b_bytes = (b_bytes_raw + 1023) & ~1023u;
-    const uint32_t stage_bytes = a_bytes + b_bytes;
+    const int MT = p.MT;                                   // vertically adjacent 8x16 tiles sharing the weight slab
+    const uint32_t stage_bytes = MT * a_bytes + b_bytes;
     __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], tmem_full_bar;
     __shared__ uint32_t tmem_base_smem;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x;
     const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, n = tile / (p.tiles_x * p.tiles_y);
-    const int x0 = tx * kTileW, y0 = ty * kTileH;
+    const int x0 = tx * kTileW, y0 = ty * kTileH * MT;
     const int n0 = blockIdx.y * p.BN;
     const int Ctot = p.C1 + p.C2;
     const int slabs = Ctot / p.KC;
     const int k_iters = p.KH * p.KW * slabs;
-    const uint32_t tmem_cols = p.BN < 32 ? 32 : p.BN;
+    const uint32_t tmem_cols = MT * p.BN < 32 ? 32 : MT * p.BN;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -107,11 +109,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int r = tap / p.KW, s = tap % p.KW;
                 for (int sl = 0; sl < slabs; sl++, it++) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t *sa = smem + stage * stage_bytes, *sb = sa + a_bytes;
-                    mbar_expect_tx(&full_bar[stage], a_bytes + b_bytes_raw);
+                    uint8_t *sa = smem + stage * stage_bytes, *sb = sa + MT * a_bytes;
+                    mbar_expect_tx(&full_bar[stage], MT * a_bytes + b_bytes_raw);
                     const int c = sl * p.KC;
-                    if (c < p.C1) tma_load_4d(sa, &tmA, &full_bar[stage], c, x0 + s - pw, y0 + r - ph, n);
-                    else tma_load_4d(sa, &tmA2, &full_bar[stage], c - p.C1, x0 + s - pw, y0 + r - ph, n);
+                    for (int mt = 0; mt < MT; mt++) {
+                        if (c < p.C1) tma_load_4d(sa + mt * a_bytes, &tmA, &full_bar[stage], c, x0 + s - pw, y0 + mt * kTileH + r - ph, n);
+                        else tma_load_4d(sa + mt * a_bytes, &tmA2, &full_bar[stage], c - p.C1, x0 + s - pw, y0 + mt * kTileH + r - ph, n);
+                    }
                     tma_load_2d(sb, &tmB, &full_bar[stage], tap * Ctot + c, n0);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
@@ -132,10 +136,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(&full_bar[stage], phase);
             tcgen05_fence_after();
             const uint32_t alo = sa0 + (uint32_t)stage * stage16 + (uint32_t)(dhi & 0xFFFF0000u);
-            const uint32_t blo = alo + a16;
-            for (int j = 0; j < ksteps; j++)
-                umma_f16_pred(tmem_acc, desc_with_lo(dhi, alo + 2u * j), desc_with_lo(dhi, blo + 2u * j), idesc,
-                              (uint32_t)((it | j) != 0), leader);
+            const uint32_t blo = alo + (uint32_t)MT * a16;
+            for (int mt = 0; mt < MT; mt++)
+                for (int j = 0; j < ksteps; j++)
+                    umma_f16_pred(tmem_acc + (uint32_t)(mt * p.BN), desc_with_lo(dhi, alo + (uint32_t)mt * a16 + 2u * j),
+                                  desc_with_lo(dhi, blo + 2u * j), idesc, (uint32_t)((it | j) != 0), leader);
             umma_commit_pred(&empty_bar[stage], leader);     // frees the smem slot once these MMAs retire
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
@@ -144,33 +149,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===== epilogue: 4 warps, TMEM lane group = warp % 4 =====
         const int q = warp & 3;
         const int m = q * 32 + lane;                     // pixel row of the tile == TMEM lane
-        const int py = y0 + m / kTileW, px = x0 + m % kTileW;
-        const bool inb = py < p.H && px < p.W;
         mbar_wait(&tmem_full_bar, 0);
         tcgen05_fence_after();
-        const size_t pix = ((size_t)n * p.H + py) * p.W + px;
-        for (int c0 = 0; c0 < p.BN; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld_32x32b_x16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            tmem_ld_wait();
-            float f[16];
+        for (int mt = 0; mt < MT; mt++) {
+            const int py = y0 + mt * kTileH + m / kTileW, px = x0 + m % kTileW;
+            const bool inb = py < p.H && px < p.W;
+            const size_t pix = ((size_t)n * p.H + py) * p.W + px;
+            for (int c0 = 0; c0 < p.BN; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld_32x32b_x16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * p.BN + c0), v);
+                tmem_ld_wait();
+                float f[16];
 #pragma unroll
-            for (int j = 0; j < 16; j++) {
-                float x = __uint_as_float(v[j]) + __ldg(p.bias + n0 + c0 + j);
-                f[j] = x > 0.f ? x : x * p.slope;
-            }
-            if (inb) {
-                if (p.out_mode == 0) {
-                    __half2 h[8];
+                for (int j = 0; j < 16; j++) {
+                    float x = __uint_as_float(v[j]) + __ldg(p.bias + n0 + c0 + j);
+                    f[j] = x > 0.f ? x : x * p.slope;
+                }
+                if (inb) {
+                    if (p.out_mode == 0) {
+                        __half2 h[8];
 #pragma unroll
-                    for (int j = 0; j < 8; j++) h[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
-                    uint4 *dst = (uint4 *)((__half *)p.out + pix * p.out_cstride + n0 + c0);
-                    dst[0] = *(uint4 *)&h[0];
-                    dst[1] = *(uint4 *)&h[4];
-                } else if (c0 == 0 && n0 == 0) {
-                    float4 *dst = (float4 *)((float *)p.out + pix * 8);
-                    dst[0] = make_float4(f[0], f[1], f[2], f[3]);
-                    dst[1] = make_float4(f[4], f[5], f[6], f[7]);
+                        for (int j = 0; j < 8; j++) h[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+                        uint4 *dst = (uint4 *)((__half *)p.out + pix * p.out_cstride + n0 + c0);
+                        dst[0] = *(uint4 *)&h[0];
+                        dst[1] = *(uint4 *)&h[4];
+                    } else if (c0 == 0 && n0 == 0) {
+                        float4 *dst = (float4 *)((float *)p.out + pix * 8);
+                        dst[0] = make_float4(f[0], f[1], f[2], f[3]);
+                        dst[1] = make_float4(f[4], f[5], f[6], f[7]);
+                    }
                 }
             }
         }
@@ -1101,6 +1108,15 @@ int v2e_make_wgt_tmap(CUtensorMap *tm, const void *ptr, int Cout_pad, int Ktot, 
     return V2E_OK;
 }
 
+static int conv_use_mt2(long ctas) {
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("V2E_CONV_MT2"); on = e ? atoi(e) : 1; }
+    if (!on) return 0;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return ctas >= 2L * sms;
+}
 int v2e_conv_pick_kc(int C1, int C2) {
     int g = C2 ? (C1 < C2 ? C1 : C2) : C1;
     return g % 64 == 0 ? 64 : (g % 32 == 0 ? 32 : 16);
@@ -1138,9 +1154,16 @@ int v2e_conv_prepare(V2eConvLaunch *L, const void *x1, int C1, const void *x2, i
     p.KC = v2e_conv_pick_kc(C1, C2);
     p.BN = v2e_conv_pick_bn(Cout_pad);
     p.stages = kStages;
+    p.MT = 1;
     p.tiles_x = (W + kTileW - 1) / kTileW;
     p.tiles_y = (H + kTileH - 1) / kTileH;
     if (out_mode == 0 && conv_use_bn256(Cout_pad, (long)p.tiles_x * p.tiles_y * N)) { p.BN = 256; p.stages = 2; }
+    else if (out_mode == 0 && p.BN == 128 && p.KC == 64 &&
+             conv_use_mt2((long)p.tiles_x * ((p.tiles_y + 1) / 2) * N * (Cout_pad / 128))) {
+        // two vertically adjacent pixel tiles per CTA share every weight slab: the same 94 B/clk as the N = 256 tiles
+        p.MT = 2; p.stages = 2;
+        p.tiles_y = (p.tiles_y + 1) / 2;
+    }
     p.out_cstride = out_cstride; p.out_mode = out_mode; p.co_real = co_real; p.slope = slope;
     p.bias = bias; p.out = out;
     int rc;
@@ -1149,7 +1172,7 @@ int v2e_conv_prepare(V2eConvLaunch *L, const void *x1, int C1, const void *x2, i
     else L->tmA2 = L->tmA;
     if ((rc = v2e_make_wgt_tmap(&L->tmB, wgt, Cout_pad, KH * KW * (C1 + C2), p.KC, p.BN))) return rc;
     L->grid = dim3((unsigned)(p.tiles_x * p.tiles_y * N), (unsigned)(Cout_pad / p.BN), 1);
-    size_t stage = (size_t)kBM * p.KC * 2 + (((size_t)p.BN * p.KC * 2 + 1023) & ~(size_t)1023);
+    size_t stage = (size_t)p.MT * kBM * p.KC * 2 + (((size_t)p.BN * p.KC * 2 + 1023) & ~(size_t)1023);
     L->smem = stage * p.stages + 1024;
     return V2E_OK;
 }

@@ -75,14 +75,13 @@ __global__ void prep_pairs_kernel(const uint8_t *__restrict__ frames, float *__r
     img[i] = v;
     const int b = (int)(i / HW);
     const long px = i % HW;
-    if (b < B) {                       // frame b is I0 of pair b
-        __half *d = flow_in + ((long)b * HW + px) * 16;
-        d[0] = __float2half_rn(v);
-#pragma unroll
-        for (int c = 2; c < 16; c++) d[c] = __float2half_rn(0.f);
-    }
-    if (b > 0) {                       // frame b is I1 of pair b-1
-        flow_in[((long)(b - 1) * HW + px) * 16 + 1] = __float2half_rn(v);
+    if (b < B) {                       // frame b is I0 of pair b, frame b + 1 its I1: one 32-byte pixel record per thread
+        const float v1 = (float)frames[i + HW] / 255.0f - kMean;
+        const __half2 h01 = __floats2half2_rn(v, v1);
+        uint4 lo = make_uint4(*(const uint32_t *)&h01, 0u, 0u, 0u), hi = make_uint4(0u, 0u, 0u, 0u);
+        uint4 *d = (uint4 *)(flow_in + ((long)b * HW + px) * 16);
+        d[0] = lo;
+        d[1] = hi;
     }
 }
 

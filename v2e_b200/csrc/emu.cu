@@ -21,6 +21,7 @@
 // and linspace formulas. This TU must be compiled with -fmad=false; the only fused multiply-adds
 // are the explicit fmaf() in linspace_f32().
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -565,6 +566,67 @@ emu_csdvs_step_kernel(EmuDev d, double alpha_p, float alpha_h, int step, int i, 
     if (threadIdx.x == 0) {
         for (int w = 1; w < kThreads / 32; w++) bits = s_m[w] > bits ? s_m[w] : bits;
         atomicMax(&d.cs_max[step], bits);
+    }
+}
+
+// The same Euler steps s0 .. s1-1 in ONE cooperative launch: a grid-wide barrier between steps instead of a kernel
+// launch per step (the iteration is a chain of tiny stencil passes over an L2-resident field: launch latency, not
+// bandwidth, was what a step cost). Single GPU: the loop ends right after the first step whose max|change| <= 1e-5, as
+// the reference's while loop does (emulator.py:1105-1121), and block 0 records cs_steps_taken and the new ring position.
+// Sharded: a chunk of K steps between two halo exchanges, no early exit inside (the maxima are reduced over the ranks
+// after the chunk; emu_csdvs_advance_kernel picks the step).
+constexpr int kCsThreads = 512;
+__global__ void __launch_bounds__(kCsThreads)
+emu_csdvs_iter_kernel(EmuDev d, double alpha_p, float alpha_h, int s0, int s1, int sharded, int slot) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ unsigned long long s_m[kCsThreads / 32];
+    // uniform over the grid: read before anyone can change them (only the tail of this kernel / later kernels do)
+    if (*(volatile int32_t *)d.abort_flag) return;
+    if (sharded && *(volatile int32_t *)d.cs_done) return;
+    const int cur0 = *(volatile int32_t *)d.cs_cur;
+    const double *pp = (const double *)d.lp;
+    const int stride = gridDim.x * kCsThreads;
+    int taken = s1 - s0;
+    for (int s = s0; s < s1; s++) {
+        const int cur = (cur0 + (s - s0)) % d.cs_ring, nxt = (cur + 1) % d.cs_ring;
+        const double *h = d.cs_bufs ? d.cs_bufs + (size_t)cur * d.cs_stride : (cur ? d.surround2 : d.surround);
+        double *hn = d.cs_bufs ? d.cs_bufs + (size_t)nxt * d.cs_stride : (nxt ? d.surround2 : d.surround);
+        double a = 0.0;
+        for (int idx = blockIdx.x * kCsThreads + threadIdx.x; idx < d.n; idx += stride) {
+            const int y = idx / d.W, x = idx - y * d.W;
+            const int ym = y > 0 ? y - 1 : 0, yp = y < d.H - 1 ? y + 1 : d.H - 1;
+            const int xm = x > 0 ? x - 1 : 0, xp = x < d.W - 1 ? x + 1 : d.W - 1;
+            const double hc = h[idx];
+            const float uu = (float)h[ym * d.W + x], ll = (float)h[y * d.W + xm], cc = -4.0f * (float)hc;
+            const float rr = (float)h[y * d.W + xp], dd = (float)h[yp * d.W + x];
+            const float acc = d.cs_seq_order ? ((((uu + ll) + cc) + rr) + dd) : (uu + ll) + (cc + (rr + dd));
+            const float h_term = alpha_h * acc;
+            const double chg = alpha_p * (pp[idx] - hc) + (double)h_term;
+            hn[idx] = hc + chg;
+            if (y >= d.cs_y_lo && y < d.cs_y_hi) a = fmax(a, fabs(chg));
+        }
+        unsigned long long bits = (unsigned long long)__double_as_longlong(a);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            unsigned long long t = __shfl_xor_sync(0xffffffffu, bits, o);
+            bits = t > bits ? t : bits;
+        }
+        if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = bits;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < kCsThreads / 32; w++) bits = s_m[w] > bits ? s_m[w] : bits;
+            atomicMax(&d.cs_max[s], bits);
+        }
+        grid.sync();                            // step s complete everywhere, its maximum final
+        if (!sharded && __longlong_as_double((long long)*(volatile unsigned long long *)&d.cs_max[s]) <= 1e-5) {
+            taken = s - s0 + 1;
+            break;
+        }
+    }
+    if (!sharded && blockIdx.x == 0 && threadIdx.x == 0) {
+        d.ctrl[slot].cs_steps = s0 + taken;
+        *d.cs_cur = (cur0 + taken) % d.cs_ring;     // everyone read cs_cur before the first barrier
     }
 }
 
@@ -2155,6 +2217,34 @@ struct ProfScope {
 
 static size_t frame_elem(int dt) { return dt == V2E_U8 ? 1 : (dt == V2E_F32 ? 4 : 8); }
 
+// One cooperative launch for Euler steps [s0, s1) (emu_csdvs_iter_kernel). Returns false when the device / occupancy
+// does not allow a cooperative grid (the per-step kernels are used then).
+static bool cs_launch_iter(V2eEmu *h, double alpha_p, float alpha_h, int s0, int s1, int sharded, int slot, cudaStream_t st) {
+    static int coop = -1, blocks_per_sm = 0, sms = 148;
+    if (coop < 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, emu_csdvs_iter_kernel, kCsThreads, 0) != cudaSuccess)
+            blocks_per_sm = 0;
+        const char *e = getenv("V2E_CS_COOP");
+        if (e && atoi(e) == 0) coop = 0;
+    }
+    if (!coop || blocks_per_sm < 1) return false;
+    const EmuDev &d = h->d;
+    int grid = sms * (blocks_per_sm > 2 ? 2 : blocks_per_sm);            // few, fat blocks: a cheap grid barrier
+    const int need = (d.n + kCsThreads - 1) / kCsThreads;
+    if (grid > need) grid = need;
+    EmuDev dd = d;
+    void *args[] = {(void *)&dd, (void *)&alpha_p, (void *)&alpha_h, (void *)&s0, (void *)&s1, (void *)&sharded, (void *)&slot};
+    if (cudaLaunchCooperativeKernel((const void *)emu_csdvs_iter_kernel, dim3(grid), dim3(kCsThreads), args, 0, st) == cudaSuccess)
+        return true;
+    cudaGetLastError();         // clear; fall back to one launch per step from now on
+    coop = 0;
+    return false;
+}
+
 // Euler-step plan of one frame of the centre-surround model (emulator.py:1068-1096)
 static int cs_plan(const V2eEmu *h, const FrameParams &p, int *num_steps, double *alpha_p, float *alpha_h) {
     const double tau_p = h->cfg.cs_tau_p_s, tau_h = h->cfg.cs_tau_h_s;
@@ -2216,10 +2306,12 @@ static int enqueue_count(V2eEmu *h, const FrameParams &p, const void *frame, int
         float alpha_h = 0;
         if ((rc = cs_plan(h, p, &num_steps, &alpha_p, &alpha_h))) return rc;
         CU(cudaMemsetAsync(d.cs_max, 0, (size_t)num_steps * sizeof(unsigned long long), st));
-        const int gs = (d.n + kThreads - 1) / kThreads;
-        for (int k = 0; k < num_steps; k++)
-            emu_csdvs_step_kernel<<<gs, kThreads, 0, st>>>(d, alpha_p, alpha_h, k, k, 0);
-        emu_csdvs_finish_kernel<<<1, 1, 0, st>>>(d, num_steps, slot);
+        if (!cs_launch_iter(h, alpha_p, alpha_h, 0, num_steps, 0, slot, st)) {
+            const int gs = (d.n + kThreads - 1) / kThreads;
+            for (int k = 0; k < num_steps; k++)
+                emu_csdvs_step_kernel<<<gs, kThreads, 0, st>>>(d, alpha_p, alpha_h, k, k, 0);
+            emu_csdvs_finish_kernel<<<1, 1, 0, st>>>(d, num_steps, slot);
+        }
     }
     {
         ProfScope ps(h, slot, 0, st);
@@ -2820,9 +2912,11 @@ extern "C" int v2e_emu_cs_chunk(V2eEmu *h, int s0, int s1, void *stream) {
     if (!h || !h->cs_pending) return fail(V2E_E_STATE, "v2e_emu_cs_begin must precede v2e_emu_cs_chunk");
     if (s0 < 0 || s1 <= s0 || s1 > h->cs_num_steps || s1 - s0 > h->cs_K) return fail(V2E_E_INVALID, "bad chunk of Euler steps");
     const EmuDev &d = h->d;
-    const int gs = (d.n + kThreads - 1) / kThreads;
-    for (int s = s0; s < s1; s++)
-        emu_csdvs_step_kernel<<<gs, kThreads, 0, (cudaStream_t)stream>>>(d, h->cs_alpha_p, h->cs_alpha_h, s, s - s0, 1);
+    if (!cs_launch_iter(h, h->cs_alpha_p, h->cs_alpha_h, s0, s1, 1, 0, (cudaStream_t)stream)) {
+        const int gs = (d.n + kThreads - 1) / kThreads;
+        for (int s = s0; s < s1; s++)
+            emu_csdvs_step_kernel<<<gs, kThreads, 0, (cudaStream_t)stream>>>(d, h->cs_alpha_p, h->cs_alpha_h, s, s - s0, 1);
+    }
     CU(cudaGetLastError());
     return V2E_OK;
 }

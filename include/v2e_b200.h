@@ -215,6 +215,10 @@ int v2e_emu_cs_begin(V2eEmu *h, const void *frame_dev, int frame_dtype, double t
                      uint64_t capacity, uint64_t ev_base_start, int *num_steps, void *stream);
 int v2e_emu_cs_pack(V2eEmu *h, void *stream);
 int v2e_emu_cs_unpack(V2eEmu *h, void *stream);
+/* the same, reading the neighbours' rows where the exchange left them (e.g. inside an all-gathered buffer):
+ * rows_above_dev = the upper neighbour's bottom K rows [K][W], rows_below_dev = the lower neighbour's top K rows;
+ * NULL at the image border */
+int v2e_emu_cs_unpack_from(V2eEmu *h, const double *rows_above_dev, const double *rows_below_dev, void *stream);
 double *v2e_emu_cs_send_dev(V2eEmu *h);
 double *v2e_emu_cs_recv_dev(V2eEmu *h);
 int v2e_emu_cs_chunk(V2eEmu *h, int s0, int s1, void *stream);

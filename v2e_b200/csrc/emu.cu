@@ -652,14 +652,16 @@ __global__ void emu_csdvs_pack_kernel(EmuDev d, double *send, int K) {
         send[i] = h[(size_t)y * d.W + x];
     }
 }
-__global__ void emu_csdvs_unpack_kernel(EmuDev d, const double *recv, int K) {
+// recv_above / recv_below: [K][W] rows of the neighbour above (its bottom edge) / below (its top edge); null at the
+// image border
+__global__ void emu_csdvs_unpack_kernel(EmuDev d, const double *recv_above, const double *recv_below, int K) {
     double *h = d.cs_bufs + (size_t)(*d.cs_cur) * d.cs_stride;
     const int per = K * d.W;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * per; i += gridDim.x * blockDim.x) {
         const int side = i / per, r = (i - side * per) / d.W, x = i % d.W;
         // side 0: halo above the own rows (present iff cs_y_lo > 0), side 1: halo below
-        if (side == 0 && d.cs_y_lo >= K) h[(size_t)(d.cs_y_lo - K + r) * d.W + x] = recv[i];
-        if (side == 1 && d.cs_y_hi + K <= d.H) h[(size_t)(d.cs_y_hi + r) * d.W + x] = recv[i];
+        if (side == 0 && recv_above && d.cs_y_lo >= K) h[(size_t)(d.cs_y_lo - K + r) * d.W + x] = recv_above[i];
+        if (side == 1 && recv_below && d.cs_y_hi + K <= d.H) h[(size_t)(d.cs_y_hi + r) * d.W + x] = recv_below[i - per];
     }
 }
 
@@ -2904,7 +2906,13 @@ extern "C" int v2e_emu_cs_pack(V2eEmu *h, void *stream) {
 }
 extern "C" int v2e_emu_cs_unpack(V2eEmu *h, void *stream) {
     if (!h || !h->cs_K) return fail(V2E_E_STATE, "not a pixel-sharded centre-surround handle");
-    emu_csdvs_unpack_kernel<<<148, 256, 0, (cudaStream_t)stream>>>(h->d, h->cs_recv, h->cs_K);
+    emu_csdvs_unpack_kernel<<<148, 256, 0, (cudaStream_t)stream>>>(h->d, h->cs_recv, h->cs_recv + (size_t)h->cs_K * h->d.W, h->cs_K);
+    CU(cudaGetLastError());
+    return V2E_OK;
+}
+extern "C" int v2e_emu_cs_unpack_from(V2eEmu *h, const double *rows_above_dev, const double *rows_below_dev, void *stream) {
+    if (!h || !h->cs_K) return fail(V2E_E_STATE, "not a pixel-sharded centre-surround handle");
+    emu_csdvs_unpack_kernel<<<148, 256, 0, (cudaStream_t)stream>>>(h->d, rows_above_dev, rows_below_dev, h->cs_K);
     CU(cudaGetLastError());
     return V2E_OK;
 }

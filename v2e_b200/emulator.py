@@ -357,6 +357,7 @@ class EventEmulator(object):
             except Exception:
                 pass
             box[0] = None
+        self._cs_cache = None
 
     # ------------------------------------------------------------------------------------------
     def _stream(self):
@@ -639,7 +640,7 @@ class EventEmulator(object):
             raise ValueError("band_frame must hold rows [%d, %d) of the frame" % (y0, y1))
         return self._generate_sharded(fr, code, t_frame, full_height=int(full_height))
 
-    def _generate_sharded(self, fr_full, code, t_frame, full_height=None):
+    def _generate_sharded(self, fr_full, code, t_frame, full_height=None, return_device=False):
         import torch.distributed as dist
         rank, world, group = self.shard
         if full_height is None:
@@ -702,12 +703,16 @@ class EventEmulator(object):
             dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
             shot_pending = shot_on and replay
             _lib.check(L.v2e_emu_phase_filter(h, t_frame, tp, cap, 0 if shot_pending else 1, st))
-            max_n = ctypes.c_int32(0)
-            counts = np.zeros(2 * self.iter_cap, np.uint32)
-            _lib.check(L.v2e_emu_read_counts(h, ctypes.byref(max_n), counts.ctypes.data_as(ctypes.c_void_p),
-                                             counts.size, st))
-            m = max_n.value
-            counts = counts[:2 * m].astype(np.int64)
+            m, counts = 0, None
+            if replay or not return_device:
+                # per-(iteration, polarity) counts on the host: the replayed randperm draws and the canonical row
+                # order need them (one synchronisation); the device-RNG batch path skips this
+                max_n = ctypes.c_int32(0)
+                counts = np.zeros(2 * self.iter_cap, np.uint32)
+                _lib.check(L.v2e_emu_read_counts(h, ctypes.byref(max_n), counts.ctypes.data_as(ctypes.c_void_p),
+                                                 counts.size, st))
+                m = max_n.value
+                counts = counts[:2 * m].astype(np.int64)
             if replay:
                 # keep the seeded generator aligned with an unsharded run: the reference draws one
                 # randperm(n_i) per iteration with n_i = events of the WHOLE frame (emulator.py:868)
@@ -725,6 +730,14 @@ class EventEmulator(object):
             _lib.check(L.v2e_emu_phase_emit(h, t_frame, tp, ctypes.c_void_p(self._ev_dev.data_ptr()), cap, st))
             fi = self._collect_one(fp, code, t_frame, tp, st)
             self.last_frame_info = fi
+            if return_device and not replay:
+                self._account(fi)
+                self.t_previous = t_frame
+                if fi.n_events == 0:
+                    return None
+                evd = self._ev_dev[:int(fi.n_events)].clone()
+                evd[:, 2] += ye0
+                return evd
             ev = self._rows_to_host(int(fi.n_events))
         self._account(fi)
         self.t_previous = t_frame
@@ -736,7 +749,7 @@ class EventEmulator(object):
         finally:
             self.exact_order = saved
         ev[:, 2] += ye0
-        return ev
+        return torch.from_numpy(ev).to(self.device) if return_device else ev
 
     def _cs_iterate(self, fp, code, t_frame, tp, cap, lrp, st, W):
         """Centre-surround model over row bands (emulator.py:1061-1124; BASELINE config 5): the Euler iteration in
@@ -750,26 +763,27 @@ class EventEmulator(object):
         ns = ctypes.c_int(0)
         _lib.check(L.v2e_emu_cs_begin(h, fp, code, t_frame, tp, cap, 0, ctypes.byref(ns), st))
         ns = ns.value
-        send = torch.as_tensor(_DevView(L.v2e_emu_cs_send_dev(h), (2, K, W), "<f8", self), device=self.device)
-        recv = torch.as_tensor(_DevView(L.v2e_emu_cs_recv_dev(h), (2, K, W), "<f8", self), device=self.device)
-        mxv = torch.as_tensor(_DevView(L.v2e_emu_cs_max_dev(h), (ns,), "<i8", self), device=self.device)
-        nccl = dist.get_backend(group) == "nccl"
-        if nccl:
-            gathered = torch.empty((world, 2, K, W), dtype=torch.float64, device=self.device)
+        c = getattr(self, "_cs_cache", None)
+        if c is None:                # views of the library's exchange buffers, made once per handle
+            nccl = dist.get_backend(group) == "nccl"
+            c = self._cs_cache = dict(
+                nccl=nccl,
+                send=torch.as_tensor(_DevView(L.v2e_emu_cs_send_dev(h), (2, K, W), "<f8", self), device=self.device),
+                mxv=torch.as_tensor(_DevView(L.v2e_emu_cs_max_dev(h), (8192,), "<i8", self), device=self.device),
+                gathered=torch.empty((world, 2, K, W), dtype=torch.float64, device=self.device))
+        send, mxv, gathered = c["send"], c["mxv"], c["gathered"]
+        row_bytes = 2 * K * W * 8
+        # the upper neighbour's bottom edge / the lower neighbour's top edge, where the all-gather leaves them
+        above = ctypes.c_void_p(gathered.data_ptr() + (rank - 1) * row_bytes + K * W * 8) if rank > 0 else None
+        below = ctypes.c_void_p(gathered.data_ptr() + (rank + 1) * row_bytes) if rank < world - 1 else None
         for s0 in range(0, ns, K):
             s1 = min(ns, s0 + K)
             _lib.check(L.v2e_emu_cs_pack(h, st))
-            if nccl:
+            if c["nccl"]:
                 dist.all_gather_into_tensor(gathered, send, group=group)
-                parts = gathered
             else:
-                parts = [torch.empty_like(send) for _ in range(world)]
-                dist.all_gather(parts, send.clone(), group=group)
-            if rank > 0:
-                recv[0].copy_(parts[rank - 1][1])          # the rows above: the upper neighbour's bottom edge
-            if rank < world - 1:
-                recv[1].copy_(parts[rank + 1][0])          # the rows below: the lower neighbour's top edge
-            _lib.check(L.v2e_emu_cs_unpack(h, st))
+                dist.all_gather(list(gathered.unbind(0)), send.clone(), group=group)
+            _lib.check(L.v2e_emu_cs_unpack_from(h, above, below, st))
             _lib.check(L.v2e_emu_cs_chunk(h, s0, s1, st))
             dist.all_reduce(mxv[s0:s1], op=dist.ReduceOp.MAX, group=group)
             _lib.check(L.v2e_emu_cs_advance(h, s0, s1, st))
@@ -852,9 +866,9 @@ class EventEmulator(object):
         def frame_by_frame(a, b):
             for k in range(a, b):
                 self.frame_counter += 1
-                evk = self._generate_sharded(fr[k], code, t_frames[k], full_height=H)
+                evk = self._generate_sharded(fr[k], code, t_frames[k], full_height=H, return_device=True)
                 if evk is not None:
-                    out.append(torch.from_numpy(evk).to(self.device))
+                    out.append(evk)
                     state["total"] += len(evk)
                 offs.append(state["total"])
 

@@ -471,18 +471,34 @@ def main():
         big = max(range(23), key=lambda i: ms23[i])
         achieved = conv_fl.value / (conv_ms.value * 1e-3) / 1e12
         tr_conv = traffic.get("conv_all_layers_per_step")
-        # pixel model: the multi-frame path on this clip's interpolated frames (K repetitions between one event pair)
-        interp, times, _ = pipe.slomo.interpolate_frames(src_dev)
-        f = clip_s / (np.max(times) - np.min(times))
-        t_next = float(em.t_previous) + 1.0 / (SRC_FPS * U)
-        tvec = t_next + f * (times - times[0])
-        T = interp.shape[0]
-        ts = (ctypes.c_double * T)(*[float(x) for x in tvec])
+        # pixel model alone: the multi-frame path on a clean 1280x720 clip (the headline texture translating 1 px per
+        # frame, CLI defaults, device RNG), K repetitions of one 80-frame chunk between one event pair. Measured on its
+        # own clip because the headline's interpolated frames -- synthesised by a RANDOM-weight network -- flicker: in
+        # every chunk some pixel makes >= 7 events in one frame, the refractory filter engages (emulator.py:830) and
+        # the chunk is replayed frame by frame (config.pixel_model_chunks); a trained network's frames do not do that.
+        T = 80
+        clean = torch.from_numpy(source_clip(H, W, T + 1, seed=11, px_per_frame=1)).to(dev)      # loops: frame T == frame 0
+        emc = EventEmulator(device=devname, rng_mode="device", seed=77, max_frames_per_step=T, **CLI_DEFAULTS)
+        emc.event_rows_hint = 48 * 1024 * 1024
+        emc.generate_events_batch(clean, np.arange(T + 1) / (SRC_FPS * U), return_device=True)
+        rows_c, _ = emc.generate_events_batch(clean[1:], (T + 1 + np.arange(T)) / (SRC_FPS * U), return_device=True)
+        ca, cb = ctypes.c_longlong(0), ctypes.c_longlong(0)
+        emc._lib.v2e_emu_fused_stats(emc._h, ctypes.byref(ca), ctypes.byref(cb))
+        ts = (ctypes.c_double * T)(*[(2 * T + 1 + k) / (SRC_FPS * U) for k in range(T)])
         uc, uu = ctypes.c_float(0), ctypes.c_float(0)
-        _lib.check(em._lib.v2e_emu_time_fused(em._h, ctypes.c_void_p(interp.data_ptr()), 0, T, ts,
-                                              float(em.t_previous), ctypes.c_void_p(em._ev_dev.data_ptr()),
-                                              em._ev_dev.shape[0], 10, ctypes.byref(uc), ctypes.byref(uu), em._stream()))
-        ev_per_frame = ev_dev / args.steps / world / n_interp
+        _lib.check(emc._lib.v2e_emu_time_fused(emc._h, ctypes.c_void_p(clean[1:].data_ptr()), 0, T, ts,
+                                               float(emc.t_previous), ctypes.c_void_p(emc._ev_dev.data_ptr()),
+                                               emc._ev_dev.shape[0], 10, ctypes.byref(uc), ctypes.byref(uu), emc._stream()))
+        ev_clean = rows_c.shape[0] / T
+        emc.cleanup()
+        # what the headline step itself ran: per-kernel brackets of the frame-by-frame kernels (or of the chunk)
+        em = pipe.emulator
+        _lib.check(em._lib.v2e_emu_profile(em._h, 1))
+        pipe.run(src_dev, clip_s, t_offset=(k0 + 1) * clip_s * n_interp / (n_interp - 1), return_device=True)
+        ms4, n4 = (ctypes.c_float * 4)(), (ctypes.c_int * 4)()
+        _lib.check(em._lib.v2e_emu_profile_read4(em._h, ms4, n4, em._stream()))
+        _lib.check(em._lib.v2e_emu_profile(em._h, 0))
+        ev_per_frame = ev_clean
         us_frame = uc.value / T
         bytes_frame = H * W * 53.0 + 16.0 * ev_per_frame                    # T = 1 form, per frame
         bytes_launch = H * W * (T * 1.0 + 52.0) + 16.0 * ev_per_frame * T   # one launch over T frames
@@ -513,10 +529,18 @@ def main():
                                   "note": "per-pixel state stays in registers across the chunk, so the launch moves "
                                           "H*W*(T+52)+16N bytes and is instruction-issue bound, not HBM bound"},
                 "timing": "v2e_emu_time_fused: 10 repetitions of the chunk (update, count, plan, emit; no commit, state "
-                          "untouched) between one CUDA-event pair on the launching stream"},
+                          "untouched) between one CUDA-event pair on the launching stream",
+                "clip": "1280x720 smooth texture translating 1 px per frame, %.3f events/px/frame; chunks accepted %d, "
+                        "rejected %d" % (ev_clean / (H * W), ca.value - cb.value, cb.value),
+                # the headline step's own pixel-model launches (CUDA-event brackets, one profiled step)
+                "headline_step_kernels": {"update_ms": ms4[0], "update_launches": n4[0], "filter_or_count_ms": ms4[1],
+                                          "filter_or_count_launches": n4[1], "emit_ms": ms4[2], "emit_launches": n4[2],
+                                          "note": "80 launches each = frame-by-frame kernels (chunk rejected and "
+                                                  "replayed); 1-2 launches = the multi-frame kernels"}},
         }
         # the bit-exact mode (host-replayed torch draws, one frame per call) on the same frames
         em_r = EventEmulator(device=devname, rng_mode="replay", seed=5, **CLI_DEFAULTS)
+        interp, _, _ = pipe.slomo.interpolate_frames(src_dev)
         fr_host = interp[:24].cpu().numpy()
         em_r.generate_events(fr_host[0], 0.0)
         em_r.generate_events(fr_host[1], 1 / 300.0)

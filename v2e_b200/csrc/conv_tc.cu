@@ -30,6 +30,7 @@
 #include <stdlib.h>
 
 #include "../../include/v2e_b200.h"
+#include "common.cuh"
 #include "tc_common.cuh"
 
 namespace {
@@ -1178,11 +1179,8 @@ int v2e_conv_prepare(V2eConvLaunch *L, const void *x1, int C1, const void *x2, i
 }
 
 int v2e_conv_launch(const V2eConvLaunch *L, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
-    }
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     conv_tc_kernel<<<L->grid, kConvThreads, L->smem, st>>>(L->tmA, L->tmA2, L->tmB, L->p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return v2e_set_error(V2E_E_CUDA, "conv_tc_kernel launch: %s", cudaGetErrorString(e));
@@ -1424,15 +1422,10 @@ int v2e_strip_launch(const V2eStripLaunch *L0, cudaStream_t st) {
 #endif
 #define STRIP_CASE(KW_, KC_)                                                                                  \
     if (L->p.KW == KW_ && L->p.KC == KC_) {                                                                    \
-        static bool attr_set = false;                                                                           \
-        if (!attr_set) {                                                                                        \
+        static PerDeviceOnce attr_once;                                                                         \
+        if (attr_once.first()) {                                                                                \
             cudaFuncSetAttribute(conv_strip_kernel<KW_, KC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); \
-            attr_set = true;                                                                                    \
-        }                                                                                                       \
-        static bool attr2_set = false;                                                                          \
-        if (!attr2_set) {                                                                                       \
             cudaFuncSetAttribute(conv_strip2_kernel<KW_, KC_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); \
-            attr2_set = true;                                                                                   \
         }                                                                                                       \
         if (L->p.variant == 1 && L->p.pool_out)                                                                 \
             return v2e_set_error(V2E_E_UNSUPPORTED, "strip2: no pooled variant for this filter width / slab%s", ""); \
@@ -1446,11 +1439,9 @@ int v2e_strip_launch(const V2eStripLaunch *L0, cudaStream_t st) {
     // the two layers that are followed by the pool of a down block at full / half resolution (conv2, down1.conv2)
 #define STRIP_POOL_CASE(KW_, KC_)                                                                              \
     if (L->p.variant == 1 && L->p.pool_out && L->p.KW == KW_ && L->p.KC == KC_) {                              \
-        static bool attrp_set = false;                                                                          \
-        if (!attrp_set) {                                                                                       \
+        static PerDeviceOnce attrp_once;                                                                        \
+        if (attrp_once.first())                                                                                 \
             cudaFuncSetAttribute(conv_strip2_kernel<KW_, KC_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); \
-            attrp_set = true;                                                                                   \
-        }                                                                                                       \
         conv_strip2_kernel<KW_, KC_, true><<<L->grid, kStrip2Threads, L->smem, st>>>(L->tmA, L->tmA2, L->tmB, L->p); \
         launched = true;                                                                                        \
     }
@@ -1590,22 +1581,16 @@ int v2e_conv_up2_prepare(V2eUpLaunch *L, const void *x_low, int C, const void *w
 }
 
 int v2e_conv_up2_launch(const V2eUpLaunch *L, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(conv_strip2up_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-        attr_set = true;
-    }
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) cudaFuncSetAttribute(conv_strip2up_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     conv_strip2up_kernel<<<L->grid, kStrip2Threads, L->smem, st>>>(L->tmA, L->tmB, L->p);
     // the 2-pixel frame, where clamping / zero padding break the shift invariance the folding relies on
     const StripParams &p = L->p;
     static int skip_frame = -1;                                   // measurement only: time the main kernel alone
     if (skip_frame < 0) skip_frame = getenv("V2E_UP2_NO_FRAME") ? 1 : 0;
     if (skip_frame) return V2E_OK;
-    static bool battr = false;
-    if (!battr) {
-        cudaFuncSetAttribute(conv_up2_border_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 9 * 64 * 2);
-        battr = true;
-    }
+    static PerDeviceOnce battr_once;
+    if (battr_once.first()) cudaFuncSetAttribute(conv_up2_border_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 9 * 64 * 2);
     conv_up2_border_kernel<<<L->grid * 4, 128, 32 * 9 * 64 * 2, st>>>(L->low, L->w_plain, p.bias, (__half *)p.out, p.N, p.H, p.W,
                                                                        p.out_cstride, p.slope);
     cudaError_t e = cudaGetLastError();

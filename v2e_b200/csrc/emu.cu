@@ -2168,13 +2168,12 @@ static int launch_update_r(V2eEmu *h, const FrameParams &p, const void *frame, i
     const size_t sm = (size_t)StageLayout<S>::block_bytes;
     {
         // opt in to > 48 KB of dynamic shared memory once per instantiation
-        static bool done = false;
-        if (!done) {
+        static PerDeviceOnce once;
+        if (once.first()) {
             CU(cudaFuncSetAttribute(emu_update_kernel<double, V2E_U8, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StageLayout<double>::block_bytes));
             CU(cudaFuncSetAttribute(emu_update_kernel<S, V2E_U8, RNG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
             CU(cudaFuncSetAttribute(emu_update_kernel<S, V2E_F32, RNG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
             CU(cudaFuncSetAttribute(emu_update_kernel<S, V2E_F64, RNG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            done = true;
         }
     }
     if (sizeof(S) == 8 && RNG == 1 && dt == V2E_U8 && d.per_pixel_thres && d.leak_on && d.lowpass_on && d.shot_on &&

@@ -400,11 +400,19 @@ def test_fused_multi_frame_path_equals_frame_by_frame_kernels(ci, shape):
     assert (rejected > 0) == expect_reject, (chunks, rejected)
 
 
-def test_fused_path_grows_the_event_buffer_without_loss():
-    kw = dict(cutoff_hz=300, leak_rate_hz=0.01, shot_noise_rate_hz=0.001, refractory_period_s=0.0005)
+@pytest.mark.parametrize("rejecting", [False, True])
+def test_fused_path_grows_the_event_buffer_without_loss(rejecting):
+    """V2E_E_CAPACITY inside a multi-frame segment (records kept, planned again into the larger buffer) and, with
+    chunks that are rejected and re-scheduled (multi-frame runs between the frames where the refractory filter
+    engages), inside any segment of the schedule: no row lost or duplicated, state identical."""
+    if rejecting:
+        kw = dict(cutoff_hz=200, leak_rate_hz=0.1, refractory_period_s=0.004, pos_thres=0.05, neg_thres=0.05,
+                  sigma_thres=0.01, shot_noise_rate_hz=2)
+    else:
+        kw = dict(cutoff_hz=300, leak_rate_hz=0.01, shot_noise_rate_hz=0.001, refractory_period_s=0.0005)
     H, W, T = 64, 96, 17
-    fr = smooth_frames(H, W, T, seed=3)
-    ts = [k / 300. for k in range(T)]
+    fr = texture_frames(H, W, T, seed=3, speed=0.5) if rejecting else smooth_frames(H, W, T, seed=3)
+    ts = [k / 100. for k in range(T)] if rejecting else [k / 300. for k in range(T)]
     a = _emulator(seed=2, rng_mode="device", max_frames_per_step=8, **kw)
     ra, oa = a.generate_events_batch(fr, ts)
     b = _emulator(seed=2, rng_mode="device", max_frames_per_step=8, **kw)
@@ -414,7 +422,7 @@ def test_fused_path_grows_the_event_buffer_without_loss():
     for i in range(T):
         assert_events_equal(ra[oa[i]:oa[i + 1]], rb[ob[i]:ob[i + 1]], exact_order=False, ctx="frame %d" % i)
     assert torch.equal(a.base_log_frame, b.base_log_frame)
-    assert _fused_stats(b)[1] == 0
+    assert (_fused_stats(b)[1] > 0) == rejecting
 
 
 def test_full_size_replay_mode_bit_exact_1280x720():

@@ -27,6 +27,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <vector>
 
 #include "../../include/v2e_b200.h"
 #include "common.cuh"
@@ -369,6 +370,7 @@ __device__ void plan_frame(const EmuDev &d, const FrameParams &p, int slot) {
                 if (atomicCAS(d.abort_flag, 0, V2E_E_CAPACITY) == 0) d.abort_flag[1] = slot;
             } else {
                 d.ctrl[slot + 1].ev_base = base + total;
+                *d.chain_base = base + total;
                 c->planned = 1;
             }
             __threadfence();
@@ -424,6 +426,7 @@ __device__ void plan_frame(const EmuDev &d, const FrameParams &p, int slot) {
             if (atomicCAS(d.abort_flag, 0, V2E_E_CAPACITY) == 0) d.abort_flag[1] = slot;
         } else {
             d.ctrl[slot + 1].ev_base = base + total;
+            *d.chain_base = base + total;
             c->planned = 1;
         }
         __threadfence();
@@ -1636,7 +1639,7 @@ emu_fused_count_kernel(EmuDev d, int T, int groups, const uint16_t *__restrict__
 // plan of all T frames: one block. max_vec (nullable): the frame maxima reduced over the ranks of a pixel-sharded clip.
 __global__ void __launch_bounds__(kThreads)
 emu_fused_plan_kernel(EmuDev d, const FrameParams *__restrict__ fp, int T, uint64_t ev_base_start, uint64_t capacity,
-                      const int32_t *__restrict__ max_vec) {
+                      const int32_t *__restrict__ max_vec, int slot0, int chain) {
     extern __shared__ uint32_t s_tot[];          // [T] rows of each frame
     __shared__ int s_bad;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1681,20 +1684,22 @@ emu_fused_plan_kernel(EmuDev d, const FrameParams *__restrict__ fp, int T, uint6
         }
     }
     __syncthreads();
-    if (tid == 0) {
-        uint64_t base = ev_base_start;
+    if (tid == 0 && !*(volatile int32_t *)d.abort_flag) {
+        // d is shifted to the segment's first frame (slot0 of the step); a segment after the first continues at the
+        // row the previous segment / frame of the step ended at
+        uint64_t base = chain ? (uint64_t)*d.chain_base : ev_base_start;
         for (int f = 0; f < T; f++) {
             d.ctrl[f].ev_base = base;
             base += s_tot[f];
         }
         d.ctrl[T].ev_base = base;
-        *d.chain_base = base;
         if (s_bad != 0x7fffffff) {
-            if (atomicCAS(d.abort_flag, 0, kFusedFallback) == 0) d.abort_flag[1] = s_bad;
+            if (atomicCAS(d.abort_flag, 0, kFusedFallback) == 0) d.abort_flag[1] = slot0 + s_bad;
         } else if (base > capacity) {
-            if (atomicCAS(d.abort_flag, 0, V2E_E_CAPACITY) == 0) d.abort_flag[1] = 0;
+            if (atomicCAS(d.abort_flag, 0, V2E_E_CAPACITY) == 0) d.abort_flag[1] = slot0;
         } else {
             for (int f = 0; f < T; f++) d.ctrl[f].planned = 1;
+            *d.chain_base = base;
         }
         __threadfence();
     }
@@ -1840,7 +1845,10 @@ struct V2eEmu {
     FrameParams *fp_dev;        // [max_slots]
     int32_t *max_vec;           // [max_slots] frame maxima, contiguous (all-reduced over ranks when sharded)
     int last_fused;             // the last step went through the fused path: 1 = v2e_emu_step, 2 = phase functions
-    int fused_T;                // frames of that step the fused kernels covered (the rest went frame by frame)
+    int fused_T;                // (phase functions) frames of that step the fused kernels covered
+    // schedule of the last v2e_emu_step: segments of frames [a, b), kind 0 = multi-frame kernels, 1 = frame by frame
+    struct Seg { int kind, a, b; } *sched;
+    int n_seg;
     struct {                    // arguments of that step, for the frame-by-frame replay of a rejected chunk
         const void *frames; int dtype, T; double t_previous; float *events; uint64_t capacity, ev_base_start;
         double *t_frames;       // [max_slots]
@@ -1970,6 +1978,7 @@ extern "C" int v2e_emu_create(const V2eEmuCfg *cfg, V2eEmu **out) {
     h->min_thres = 0.01;
     h->fused_enable = 1;
     h->ls.t_frames = new double[cfg->max_frames_per_step]();
+    h->sched = new V2eEmu::Seg[(size_t)cfg->max_frames_per_step + 2]();
     d.px_off = cfg->rng_pixel_offset;
     d.units = (d.n + kUnitPx - 1) / kUnitPx;
     // state arrays are staged in whole 128-pixel units by the update kernel's bulk copies
@@ -2068,6 +2077,7 @@ extern "C" int v2e_emu_destroy(V2eEmu *h) {
     EmuDev &d = h->d;
     delete[] h->pr_vrms;
     delete[] h->ls.t_frames;
+    delete[] h->sched;
     void *cs_ptrs[] = {d.cs_bufs, d.cs_done, h->cs_send, h->cs_recv};
     for (void *p : cs_ptrs) if (p) cudaFree(p);
     void *fused_ptrs[] = {h->lp_alt, h->base_alt, h->rec_list, h->rec_cnt, h->blk_cnt, h->ff_dev, h->fp_dev, h->max_vec};
@@ -2405,8 +2415,8 @@ static int fused_cfg() {
     return cfg;
 }
 template <typename S, bool FAST, int WARPS, int MINB>
-static void launch_fused_update_cfg(V2eEmu *h, const uint8_t *frames, int T, size_t sm, cudaStream_t st) {
-    const EmuDev &d = h->d;
+static void launch_fused_update_cfg(V2eEmu *h, const EmuDev &d, const FusedFrame *ff, const uint8_t *frames, int T, size_t sm,
+                                    cudaStream_t st) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -2414,26 +2424,26 @@ static void launch_fused_update_cfg(V2eEmu *h, const uint8_t *frames, int T, siz
     const int min_units = 2 * WARPS;                       // small frames: at least two units per warp
     if (blocks > (d.units + min_units - 1) / min_units) blocks = (d.units + min_units - 1) / min_units;
     if (blocks < 1) blocks = 1;
-    emu_fused_update_kernel<S, FAST, WARPS, MINB><<<blocks, WARPS * 32, sm, st>>>(d, h->ff_dev, frames, T, (S *)h->lp_alt,
+    emu_fused_update_kernel<S, FAST, WARPS, MINB><<<blocks, WARPS * 32, sm, st>>>(d, ff, frames, T, (S *)h->lp_alt,
                                                                                    (S *)h->base_alt, h->rec_list, h->rec_cnt);
 }
 template <typename S, bool FAST>
-static void launch_fused_update_f(V2eEmu *h, const uint8_t *frames, int T, size_t sm, cudaStream_t st) {
+static void launch_fused_update_f(V2eEmu *h, const EmuDev &d, const FusedFrame *ff, const uint8_t *frames, int T, size_t sm,
+                                  cudaStream_t st) {
     switch (fused_cfg()) {
-        case 1: launch_fused_update_cfg<S, FAST, 4, 5>(h, frames, T, sm, st); break;
-        case 2: launch_fused_update_cfg<S, FAST, 4, 7>(h, frames, T, sm, st); break;
-        case 3: launch_fused_update_cfg<S, FAST, 8, 2>(h, frames, T, sm, st); break;
-        default: launch_fused_update_cfg<S, FAST, 8, 3>(h, frames, T, sm, st); break;
+        case 0: launch_fused_update_cfg<S, FAST, 8, 3>(h, d, ff, frames, T, sm, st); break;
+        case 2: launch_fused_update_cfg<S, FAST, 4, 7>(h, d, ff, frames, T, sm, st); break;
+        case 3: launch_fused_update_cfg<S, FAST, 8, 2>(h, d, ff, frames, T, sm, st); break;
+        default: launch_fused_update_cfg<S, FAST, 4, 5>(h, d, ff, frames, T, sm, st); break;
     }
 }
 template <typename S>
-static int launch_fused_update(V2eEmu *h, const uint8_t *frames, int T, cudaStream_t st) {
-    const EmuDev &d = h->d;
+static int launch_fused_update(V2eEmu *h, const EmuDev &d, const FusedFrame *ff, const uint8_t *frames, int T, cudaStream_t st) {
     const size_t sm = (size_t)T * sizeof(FusedFrame);
     const bool fast = sizeof(S) == 8 && d.rng_mode == 1 && d.per_pixel_thres && d.leak_on && d.shot_on;
     if (sm > 40 * 1024) return fail(V2E_E_INVALID, "fused path: too many frames per step");
-    if (fast) launch_fused_update_f<S, true>(h, frames, T, sm, st);
-    else launch_fused_update_f<S, false>(h, frames, T, sm, st);
+    if (fast) launch_fused_update_f<S, true>(h, d, ff, frames, T, sm, st);
+    else launch_fused_update_f<S, false>(h, d, ff, frames, T, sm, st);
     return V2E_OK;
 }
 
@@ -2466,13 +2476,26 @@ static int fused_upload_params(V2eEmu *h, int T, const double *t_frames, double 
     return V2E_OK;
 }
 
-static int enqueue_fused_count(V2eEmu *h, const void *frames, int T, cudaStream_t st) {
-    const EmuDev &d = h->d;
+// the handle's device view shifted to frame slot `a` of the step: the multi-frame kernels index frames from 0
+static EmuDev shifted_dev(const EmuDev &d, int a) {
+    EmuDev s = d;
+    s.ctrl = d.ctrl + a;
+    s.hist_pre = d.hist_pre + (size_t)a * d.seg_stride;
+    s.hist_post = d.hist_post + (size_t)a * d.seg_stride;
+    s.segoff = d.segoff + (size_t)a * d.seg_stride;
+    s.cursor = d.cursor + (size_t)a * d.seg_stride;
+    return s;
+}
+
+// frames [a, a + T) of `frames` (the step's frame 0 at `frames`)
+static int enqueue_fused_count(V2eEmu *h, const void *frames, int T, cudaStream_t st, int a = 0) {
+    const EmuDev d = shifted_dev(h->d, a);
+    const uint8_t *fr = (const uint8_t *)frames + (size_t)a * d.n;
     int rc;
     {
         ProfScope ps(h, 0, 0, st);
-        rc = d.state_f64 ? launch_fused_update<double>(h, (const uint8_t *)frames, T, st)
-                         : launch_fused_update<float>(h, (const uint8_t *)frames, T, st);
+        rc = d.state_f64 ? launch_fused_update<double>(h, d, h->ff_dev + a, fr, T, st)
+                         : launch_fused_update<float>(h, d, h->ff_dev + a, fr, T, st);
     }
     if (rc) return rc;
     {
@@ -2483,15 +2506,16 @@ static int enqueue_fused_count(V2eEmu *h, const void *frames, int T, cudaStream_
 }
 
 static int enqueue_fused_emit(V2eEmu *h, int T, float *events, uint64_t capacity, uint64_t ev_base_start,
-                              const int32_t *max_vec, bool commit, cudaStream_t st) {
-    const EmuDev &d = h->d;
+                              const int32_t *max_vec, bool commit, cudaStream_t st, int a = 0, int chain = 0) {
+    const EmuDev d = shifted_dev(h->d, a);
     {
         ProfScope ps(h, 1, 1, st);       // slot 1: v2e_emu_profile_read sums count + plan under "filter"
-        emu_fused_plan_kernel<<<1, kThreads, (size_t)T * sizeof(uint32_t), st>>>(d, h->fp_dev, T, ev_base_start, capacity, max_vec);
+        emu_fused_plan_kernel<<<1, kThreads, (size_t)T * sizeof(uint32_t), st>>>(d, h->fp_dev + a, T, ev_base_start, capacity,
+                                                                                 max_vec, a, chain);
     }
     {
         ProfScope ps(h, 0, 2, st);
-        emu_fused_emit_kernel<<<T * fused_groups(d), kThreads, 0, st>>>(d, h->fp_dev, T, fused_groups(d), h->rec_list,
+        emu_fused_emit_kernel<<<T * fused_groups(d), kThreads, 0, st>>>(d, h->fp_dev + a, T, fused_groups(d), h->rec_list,
                                                                          h->rec_cnt, h->blk_cnt, (float4 *)events);
     }
     if (commit) {
@@ -2509,17 +2533,35 @@ static void remember_step(V2eEmu *h, const void *frames, int dtype, int T, const
     if (t_frames != h->ls.t_frames) memcpy(h->ls.t_frames, t_frames, sizeof(double) * (size_t)T);
 }
 
-// multi-frame kernels over the first Tf frames of the remembered step (h->ls), Philox frame indices from step_base
-static int fused_run(V2eEmu *h, int Tf, cudaStream_t st) {
+static int step_classic(V2eEmu *h, const void *frames, int dtype, int T, const double *t_frames, double t_previous,
+                        const float *leak_randn, const float *shot_rand, float *events, uint64_t capacity,
+                        uint64_t ev_base_start, int first, int resume_emit, void *stream, int last = -1);
+
+// Runs segments [from, n_seg) of the handle's schedule over the remembered step (h->ls); Philox frame indices are
+// step_base + frame. The first segment of the step starts at ls.ev_base_start, every other one where the previous
+// segment / frame ended (chain_base, device side). A capacity abort or a rejection anywhere is sticky: every later
+// kernel leaves at once; v2e_emu_collect sorts it out.
+static int run_schedule(V2eEmu *h, int from, cudaStream_t st) {
     int rc;
-    if ((rc = reset_slots(h, 0, Tf, st))) return rc;
-    if (h->profile) { memset(h->prof_used, 0, (size_t)h->d.max_slots * kProfKinds); h->prof_frames = Tf; }
-    if ((rc = fused_upload_params(h, Tf, h->ls.t_frames, h->ls.t_previous, h->step_base, h->ls.capacity, st))) return rc;
-    if ((rc = enqueue_fused_count(h, h->ls.frames, Tf, st))) return rc;
-    if ((rc = enqueue_fused_emit(h, Tf, h->ls.events, h->ls.capacity, h->ls.ev_base_start, nullptr, true, st))) return rc;
+    for (int i = from; i < h->n_seg; i++) {
+        const V2eEmu::Seg g = h->sched[i];
+        const bool step_start = g.a == 0;
+        if (g.kind == 0) {
+            const int Tf = g.b - g.a;
+            if ((rc = reset_slots(h, g.a, Tf, st, false))) return rc;
+            if ((rc = enqueue_fused_count(h, h->ls.frames, Tf, st, g.a))) return rc;
+            if ((rc = enqueue_fused_emit(h, Tf, h->ls.events, h->ls.capacity, h->ls.ev_base_start, nullptr, true, st, g.a,
+                                         step_start ? 0 : 1))) return rc;
+        } else {
+            h->frame_counter = h->step_base;
+            if ((rc = step_classic(h, h->ls.frames, h->ls.dtype, h->ls.T, h->ls.t_frames, h->ls.t_previous, nullptr, nullptr,
+                                   h->ls.events, h->ls.capacity, step_start ? h->ls.ev_base_start : kChainBase, g.a, 0,
+                                   (void *)st, g.b))) return rc;
+        }
+    }
     CU(cudaGetLastError());
-    h->last_fused = 1;
-    h->fused_T = Tf;
+    h->frame_counter = h->step_base + (uint32_t)h->ls.T;
+    h->last_T = h->ls.T;
     return V2E_OK;
 }
 
@@ -2590,10 +2632,11 @@ extern "C" int v2e_emu_fused_emit(V2eEmu *h, float *events, uint64_t capacity, u
     return V2E_OK;
 }
 
+// frames [first, last) of the step (last < 0: to the end)
 static int step_classic(V2eEmu *h, const void *frames, int dtype, int T, const double *t_frames,
                             double t_previous, const float *leak_randn, const float *shot_rand,
                             float *events, uint64_t capacity, uint64_t ev_base_start, int first,
-                            int resume_emit, void *stream) {
+                            int resume_emit, void *stream, int last) {
     if (!h || !frames || !t_frames || (!events && capacity)) return fail(V2E_E_INVALID, "null argument");
     if (!h->first_done) return fail(V2E_E_STATE, "v2e_emu_first_frame must run before v2e_emu_step");
     if (T < 1 || T > h->d.max_slots || first < 0 || first >= T) return fail(V2E_E_INVALID, "bad T / first");
@@ -2601,25 +2644,27 @@ static int step_classic(V2eEmu *h, const void *frames, int dtype, int T, const d
     cudaStream_t st = (cudaStream_t)stream;
     const EmuDev &d = h->d;
     const size_t fbytes = (size_t)d.n * frame_elem(dtype);
+    if (last < 0 || last > T) last = T;
+    if (first >= last) return fail(V2E_E_INVALID, "bad frame range");
     int rc;
     if (resume_emit) {
         // frame `first` was counted but not emitted (capacity abort): clear the abort and the slots
         // after it, keep slot `first`'s histograms, re-plan it against the new capacity.
-        if (first + 1 < T && (rc = reset_slots(h, first + 1, T - first - 1, st))) return rc;
+        if (first + 1 < last && (rc = reset_slots(h, first + 1, last - first - 1, st))) return rc;
         CU(cudaMemsetAsync(d.abort_flag, 0, 2 * sizeof(int32_t), st));
     } else {
-        // continuing after a multi-frame chunk of the same step: its capacity abort (if any) must stay sticky
-        if ((rc = reset_slots(h, first, T - first, st, ev_base_start != kChainBase))) return rc;
+        // continuing after a multi-frame segment of the same step: its capacity abort (if any) must stay sticky
+        if ((rc = reset_slots(h, first, last - first, st, ev_base_start != kChainBase))) return rc;
     }
     if (resume_emit && h->pr_T == 0) h->pr_T = h->pr_T_last;
-    if (h->profile) { memset(h->prof_used, 0, (size_t)d.max_slots * kProfKinds); h->prof_frames = T - first; }
+    if (h->profile && first == 0) { memset(h->prof_used, 0, (size_t)d.max_slots * kProfKinds); h->prof_frames = T - first; }
     if (!resume_emit) {
         h->step_base = h->frame_counter;
         h->frame_counter += (uint32_t)T;
     }
     if (ev_base_start == kChainBase) emu_chain_step_kernel<<<1, 1, 0, st>>>(d, first);
     else emu_begin_step_kernel<<<1, 1, 0, st>>>(d, first, ev_base_start);
-    for (int f = first; f < T; f++) {
+    for (int f = first; f < last; f++) {
         double tp = f == 0 ? t_previous : t_frames[f - 1];
         if (t_frames[f] < tp) return fail(V2E_E_INVALID, "frame times must be non-decreasing");
         FrameParams p = make_params(h, t_frames[f], tp, h->step_base + (uint32_t)f, capacity);
@@ -2660,39 +2705,49 @@ extern "C" int v2e_emu_step(V2eEmu *h, const void *frames, int dtype, int T, con
     cudaStream_t st = (cudaStream_t)stream;
     const EmuDev &d = h->d;
     int rc;
-    if (resume_emit && h->last_fused == 1 && first == 0) {
-        // capacity abort inside the multi-frame part of the step: its records are still there; plan again into the
-        // larger buffer, then the frames that follow it (none of them ran: the abort is sticky)
+    if (resume_emit && h->last_fused == 1 && h->n_seg > 0) {
+        // capacity abort at frame `first` of a scheduled step (the abort is sticky: nothing after it ran). The segment
+        // that holds `first` is finished into the larger buffer -- a multi-frame segment still has its records and is
+        // planned again, a frame-by-frame segment resumes at its counted-but-not-emitted frame -- then the rest of the
+        // schedule runs.
+        int i = 0;
+        while (i < h->n_seg && !(h->sched[i].a <= first && first < h->sched[i].b)) i++;
+        if (i == h->n_seg || (h->sched[i].kind == 0 && h->sched[i].a != first))
+            return fail(V2E_E_STATE, "resume_emit: frame is not where the scheduled step stopped");
+        remember_step(h, frames, dtype, T, t_frames, t_previous, events, capacity, h->ls.ev_base_start);
         CU(cudaMemsetAsync(d.abort_flag, 0, 2 * sizeof(int32_t), st));
-        CU(cudaMemsetAsync(d.cursor, 0, (size_t)h->fused_T * d.seg_stride * 4, st));
-        remember_step(h, frames, dtype, T, t_frames, t_previous, events, capacity, ev_base_start);
-        if ((rc = enqueue_fused_emit(h, h->fused_T, events, capacity, ev_base_start, nullptr, true, st))) return rc;
-        CU(cudaGetLastError());
-        if (h->fused_T < T) {
+        const V2eEmu::Seg g = h->sched[i];
+        if (g.kind == 0) {
+            CU(cudaMemsetAsync(d.cursor + (size_t)g.a * d.seg_stride, 0, (size_t)(g.b - g.a) * d.seg_stride * 4, st));
+            if ((rc = enqueue_fused_emit(h, g.b - g.a, events, capacity, ev_base_start, nullptr, true, st, g.a, 0))) return rc;
+        } else {
             h->frame_counter = h->step_base;
-            return step_classic(h, frames, dtype, T, t_frames, t_previous, nullptr, nullptr, events, capacity,
-                                kChainBase, h->fused_T, 0, stream);
+            if ((rc = step_classic(h, frames, dtype, T, t_frames, t_previous, nullptr, nullptr, events, capacity, ev_base_start,
+                                   first, 1, stream, g.b))) return rc;
         }
-        return V2E_OK;
+        return run_schedule(h, i + 1, st);
     }
     bool want_fused = h->fused_enable && T >= 2 && first == 0 && !resume_emit && !leak_randn && !shot_rand &&
                       fused_config_ok(h, dtype);
-    // back-off: input whose chunks keep being rejected early (a pixel with >= dt / refractory events in some frame)
-    // pays for the wasted multi-frame pass; after a rejection in the first half of a chunk the next 1, 2, 4, ... 64
-    // chunks go frame by frame before the multi-frame path is tried again
+    // back-off: input whose chunks keep breaking the assumption in many frames pays for the wasted speculative pass;
+    // after such a chunk the next 1, 2, 4, ... 64 chunks go frame by frame before the multi-frame path is tried again
     if (want_fused && h->fused_skip > 0) { h->fused_skip--; want_fused = false; }
     if (want_fused) {
         if ((rc = fused_alloc(h))) return rc;
         if (h->fused_max_T >= T) {
             h->step_base = h->frame_counter;
             remember_step(h, frames, dtype, T, t_frames, t_previous, events, capacity, ev_base_start);
-            if ((rc = fused_run(h, T, st))) return rc;
-            h->frame_counter = h->step_base + (uint32_t)T;
-            h->last_T = T;
+            if (h->profile) { memset(h->prof_used, 0, (size_t)d.max_slots * kProfKinds); h->prof_frames = T; }
+            if ((rc = fused_upload_params(h, T, t_frames, t_previous, h->step_base, capacity, st))) return rc;
+            CU(cudaMemsetAsync(d.abort_flag, 0, 2 * sizeof(int32_t), st));
+            h->sched[0] = {0, 0, T};
+            h->n_seg = 1;
+            h->last_fused = 1;
             h->n_fused_chunks++;
-            return V2E_OK;
+            return run_schedule(h, 0, st);
         }
     }
+    h->n_seg = 0;
     h->last_fused = 0;
     return step_classic(h, frames, dtype, T, t_frames, t_previous, leak_randn, shot_rand, events, capacity,
                         ev_base_start, first, resume_emit, stream);
@@ -2705,43 +2760,70 @@ extern "C" int v2e_emu_collect(V2eEmu *h, V2eFrameInfo *info, int T, int *frames
     CU(cudaMemcpyAsync(h->ctrl_host, h->d.ctrl, (size_t)(T + 1) * sizeof(FrameCtrl), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(h->abort_host, h->d.abort_flag, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    if (h->abort_host[0] == kFusedFallback) {
-        // the multi-frame chunk was rejected on the device at frame fb (refractory filter active, or more than
-        // kFusedMaxN events of one pixel): nothing was emitted or committed. The frames before fb go through the
-        // multi-frame kernels again (accepted by construction), the rest frame by frame -- same frames, same Philox
-        // frame indices, continuing at the row where the first part ends.
+    for (int round = 0; h->abort_host[0] == kFusedFallback; round++) {
+        // A multi-frame segment was rejected on the device at frame fb (refractory filter active there, or more than
+        // kFusedMaxN events of one pixel): nothing of it was emitted or committed, nothing after it ran.
         const int fb = h->abort_host[1];
         h->n_fused_rejected++;
         h->last_reject_frame = fb;
         h->last_reject_max_n = (fb >= 0 && fb < T) ? h->ctrl_host[fb].max_n : -1;
-        if (2 * fb < T) {
-            h->fused_penalty = h->fused_penalty ? (h->fused_penalty < 64 ? 2 * h->fused_penalty : 64) : 1;
-            h->fused_skip = h->fused_penalty;
-        }
-        const int mode = h->last_fused;
-        h->last_fused = 0;
-        h->frame_counter = h->step_base;
-        if (mode == 2) {
+        if (h->last_fused == 2) {                 // phase functions: the caller replays (identically on every rank)
+            h->last_fused = 0;
+            h->frame_counter = h->step_base;
             if (frames_done) *frames_done = fb;
             return fail(V2E_E_FALLBACK, "fused chunk rejected: replay it frame by frame");
         }
-        int rc;
-        if (fb >= 2) {
-            if ((rc = fused_run(h, fb, st))) return rc;
-            h->frame_counter = h->step_base;
-            rc = step_classic(h, h->ls.frames, h->ls.dtype, h->ls.T, h->ls.t_frames, h->ls.t_previous, nullptr, nullptr,
-                              h->ls.events, h->ls.capacity, kChainBase, fb, 0, stream);
-        } else {
-            rc = step_classic(h, h->ls.frames, h->ls.dtype, h->ls.T, h->ls.t_frames, h->ls.t_previous, nullptr, nullptr,
-                              h->ls.events, h->ls.capacity, h->ls.ev_base_start, 0, 0, stream);
+        // Re-schedule the segment: its count pass left every frame's maximum (exact up to fb, a prediction after it --
+        // the state was speculative). Frames that break the assumption go frame by frame, the runs between them
+        // through the multi-frame kernels again (each run still verifies itself: a wrong prediction costs another
+        // round, never a wrong row). Same frames, same Philox frame indices, rows chained on the device.
+        int i = 0;
+        while (i < h->n_seg && !(h->sched[i].kind == 0 && h->sched[i].a <= fb && fb < h->sched[i].b)) i++;
+        if (i == h->n_seg || round > T) return fail(V2E_E_STATE, "rejected frame outside the schedule");
+        const V2eEmu::Seg g = h->sched[i];
+        std::vector<V2eEmu::Seg> neu;
+        int n_bad = 0;
+        for (int f = g.a; f < g.b;) {
+            auto bad = [&](int q) {
+                const int m = h->ctrl_host[q].max_n;
+                const double dt = h->ls.t_frames[q] - (q == 0 ? h->ls.t_previous : h->ls.t_frames[q - 1]);
+                return q == fb || m > kFusedMaxN || m > h->d.iter_cap || (h->d.refr_on && m > 0 && h->d.refr_d > dt / (double)m);
+            };
+            int e = f;
+            if (bad(f)) { while (e < g.b && bad(e)) { e++; n_bad++; } neu.push_back({1, f, e}); }
+            else {
+                while (e < g.b && !bad(e)) e++;
+                if (e - f >= 2) neu.push_back({0, f, e});
+                else if (!neu.empty() && neu.back().kind == 1) neu.back().b = e;     // a lone good frame joins its neighbours
+                else neu.push_back({1, f, e});
+            }
+            f = e;
         }
+        // merge adjacent frame-by-frame segments
+        std::vector<V2eEmu::Seg> merged;
+        for (const auto &q : neu) {
+            if (!merged.empty() && merged.back().kind == 1 && q.kind == 1) merged.back().b = q.b;
+            else merged.push_back(q);
+        }
+        if ((size_t)h->n_seg - 1 + merged.size() > (size_t)h->d.max_slots + 2) return fail(V2E_E_STATE, "schedule overflow");
+        std::vector<V2eEmu::Seg> all(h->sched, h->sched + i);
+        all.insert(all.end(), merged.begin(), merged.end());
+        all.insert(all.end(), h->sched + i + 1, h->sched + h->n_seg);
+        for (size_t k = 0; k < all.size(); k++) h->sched[k] = all[k];
+        h->n_seg = (int)all.size();
+        if (4 * n_bad > g.b - g.a) {              // the assumption fails in many frames of this input: back off
+            h->fused_penalty = h->fused_penalty ? (h->fused_penalty < 64 ? 2 * h->fused_penalty : 64) : 1;
+            h->fused_skip = h->fused_penalty;
+        }
+        CU(cudaMemsetAsync(h->d.abort_flag, 0, 2 * sizeof(int32_t), st));
+        int rc = run_schedule(h, i, st);
         if (rc) return rc;
         CU(cudaMemcpyAsync(h->ctrl_host, h->d.ctrl, (size_t)(T + 1) * sizeof(FrameCtrl), cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(h->abort_host, h->d.abort_flag, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
     }
     int status = h->abort_host[0], done = status ? h->abort_host[1] : T;
-    if (!status && h->last_fused == 1 && h->fused_T == T) h->fused_penalty = 0;       // a whole chunk accepted
+    if (!status && h->last_fused == 1 && h->n_seg == 1) h->fused_penalty = 0;       // a whole chunk accepted
     uint64_t rows = 0;
     for (int f = 0; f < T; f++) {
         const FrameCtrl &c = h->ctrl_host[f];
@@ -2788,8 +2870,8 @@ extern "C" int v2e_emu_time_fused(V2eEmu *h, const void *frames, int dtype, int 
     if (!rc) rc = reset_slots(h, 0, T, st);
     cudaEventRecord(e[2], st);
     for (int k = 0; k < K && !rc; k++)
-        rc = h->d.state_f64 ? launch_fused_update<double>(h, (const uint8_t *)frames, T, st)
-                            : launch_fused_update<float>(h, (const uint8_t *)frames, T, st);
+        rc = h->d.state_f64 ? launch_fused_update<double>(h, h->d, h->ff_dev, (const uint8_t *)frames, T, st)
+                            : launch_fused_update<float>(h, h->d, h->ff_dev, (const uint8_t *)frames, T, st);
     cudaEventRecord(e[3], st);
     h->profile = prof;
     if (!rc) rc = reset_slots(h, 0, T, st);

@@ -405,6 +405,8 @@ def main():
                                (NS3 - 1) / SRC_FPS, 7)
         a, b = ctypes.c_longlong(0), ctypes.c_longlong(0)
         p.emulator._lib.v2e_emu_fused_stats(p.emulator._h, ctypes.byref(a), ctypes.byref(b))
+        e, f = ctypes.c_longlong(0), ctypes.c_longlong(0)
+        p.emulator._lib.v2e_emu_fused_frames(p.emulator._h, ctypes.byref(e), ctypes.byref(f))
         close(p)
         fl = 2.0 * Hd * Wd * (330016 + 314048 / U3)
         return {"workload": "1280x720_random_4x4_block_texture_%dsrc_frames_slomo_x%d_b%d_emulator_noisy" % (NS3, U3, args.batch),
@@ -412,7 +414,8 @@ def main():
                 "interp_frames_per_s": steps * nf / (ms * 1e-3),
                 "slomo_tflops": steps * nf * fl / (ms * 1e-3) / 1e12,
                 "events_per_px_per_frame": cnt / steps / (nf * H * W),
-                "pixel_model_chunks": {"multi_frame": a.value, "replayed_frame_by_frame": b.value},
+                "pixel_model_chunks": {"chunks_through_multi_frame_path": a.value, "re_scheduling_rounds": b.value,
+                                       "frames_in_multi_frame_segments": e.value, "frames_frame_by_frame": f.value},
                 "params": C3_PARAMS}
 
     if args.workload == "c3":
@@ -437,7 +440,10 @@ def main():
     pipe.emulator._lib.v2e_emu_fused_stats(pipe.emulator._h, ctypes.byref(_a), ctypes.byref(_b))
     _c, _d = ctypes.c_int(0), ctypes.c_int(0)
     pipe.emulator._lib.v2e_emu_fused_last_reject(pipe.emulator._h, ctypes.byref(_c), ctypes.byref(_d))
-    chunk_stats = {"multi_frame": _a.value, "rejected_and_replayed": _b.value}
+    _e, _f = ctypes.c_longlong(0), ctypes.c_longlong(0)
+    pipe.emulator._lib.v2e_emu_fused_frames(pipe.emulator._h, ctypes.byref(_e), ctypes.byref(_f))
+    chunk_stats = {"chunks_through_multi_frame_path": _a.value, "re_scheduling_rounds": _b.value,
+                   "frames_in_multi_frame_segments": _e.value, "frames_frame_by_frame": _f.value}
     if _b.value:
         chunk_stats["last_rejected_at"] = {"frame_in_chunk": _c.value, "max_events_of_one_pixel": _d.value}
 
@@ -474,8 +480,9 @@ def main():
         # pixel model alone: the multi-frame path on a clean 1280x720 clip (the headline texture translating 1 px per
         # frame, CLI defaults, device RNG), K repetitions of one 80-frame chunk between one event pair. Measured on its
         # own clip because the headline's interpolated frames -- synthesised by a RANDOM-weight network -- flicker: in
-        # every chunk some pixel makes >= 7 events in one frame, the refractory filter engages (emulator.py:830) and
-        # the chunk is replayed frame by frame (config.pixel_model_chunks); a trained network's frames do not do that.
+        # a few frames of every chunk some pixel makes >= 7 events, the refractory filter engages there
+        # (emulator.py:830), and the chunk is re-scheduled: those frames frame by frame, the runs between them through
+        # the multi-frame kernels (config.pixel_model_chunks says how many of each).
         T = 80
         clean = torch.from_numpy(source_clip(H, W, T + 1, seed=11, px_per_frame=1)).to(dev)      # loops: frame T == frame 0
         emc = EventEmulator(device=devname, rng_mode="device", seed=77, max_frames_per_step=T, **CLI_DEFAULTS)
@@ -535,8 +542,9 @@ def main():
                 # the headline step's own pixel-model launches (CUDA-event brackets, one profiled step)
                 "headline_step_kernels": {"update_ms": ms4[0], "update_launches": n4[0], "filter_or_count_ms": ms4[1],
                                           "filter_or_count_launches": n4[1], "emit_ms": ms4[2], "emit_launches": n4[2],
-                                          "note": "80 launches each = frame-by-frame kernels (chunk rejected and "
-                                                  "replayed); 1-2 launches = the multi-frame kernels"}},
+                                          "note": "launch counts of one profiled headline step: frame-by-frame kernels for the "
+                                                  "frames that break the assumption, multi-frame kernels for the runs between "
+                                                  "them (config.pixel_model_chunks)"}},
         }
         # the bit-exact mode (host-replayed torch draws, one frame per call) on the same frames
         em_r = EventEmulator(device=devname, rng_mode="replay", seed=5, **CLI_DEFAULTS)

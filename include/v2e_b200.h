@@ -164,6 +164,9 @@ int32_t *v2e_emu_max_vec_dev(V2eEmu *h);
 int v2e_emu_fused_emit(V2eEmu *h, float *events_out_dev, uint64_t capacity, uint64_t ev_base_start, void *stream);
 /* counters: chunks that went through the fast path / chunks it rejected */
 int v2e_emu_fused_stats(V2eEmu *h, long long *chunks, long long *rejected);
+/* frames of the steps that took the fast path: how many went through multi-frame segments and how many (those
+ * breaking the assumption, and lone frames between them) through the frame-by-frame kernels */
+int v2e_emu_fused_frames(V2eEmu *h, long long *frames_multi, long long *frames_single);
 /* diagnostics: the frame (index in its chunk) at which the last rejected chunk broke the assumption, and that frame's
  * max_num_events_any_pixel */
 int v2e_emu_fused_last_reject(V2eEmu *h, int *frame, int *max_n);

@@ -1855,6 +1855,7 @@ struct V2eEmu {
     } ls;
     long long n_fused_chunks, n_fused_rejected;
     int last_reject_frame, last_reject_max_n;      // diagnostics: where and why the last chunk was rejected
+    long long n_frames_multi, n_frames_single;     // frames of scheduled steps that ended up in multi-frame / single-frame segments
     int fused_skip, fused_penalty;                 // back-off: chunks to run frame by frame before the next attempt
     // pixel-sharded centre-surround model: plan of the current frame (v2e_emu_cs_begin) and the exchange buffers
     int cs_K;                   // halo rows = Euler steps per chunk (0: not sharded)
@@ -2576,6 +2577,12 @@ extern "C" int v2e_emu_fused_stats(V2eEmu *h, long long *chunks, long long *reje
     if (rejected) *rejected = h->n_fused_rejected;
     return V2E_OK;
 }
+extern "C" int v2e_emu_fused_frames(V2eEmu *h, long long *frames_multi, long long *frames_single) {
+    if (!h) return fail(V2E_E_INVALID, "null handle");
+    if (frames_multi) *frames_multi = h->n_frames_multi;
+    if (frames_single) *frames_single = h->n_frames_single;
+    return V2E_OK;
+}
 extern "C" int v2e_emu_fused_last_reject(V2eEmu *h, int *frame, int *max_n) {
     if (!h) return fail(V2E_E_INVALID, "null handle");
     if (frame) *frame = h->last_reject_frame;
@@ -2824,6 +2831,12 @@ extern "C" int v2e_emu_collect(V2eEmu *h, V2eFrameInfo *info, int T, int *frames
     }
     int status = h->abort_host[0], done = status ? h->abort_host[1] : T;
     if (!status && h->last_fused == 1 && h->n_seg == 1) h->fused_penalty = 0;       // a whole chunk accepted
+    if (!status && h->last_fused == 1 && h->n_seg > 0) {
+        for (int k = 0; k < h->n_seg; k++)
+            (h->sched[k].kind == 0 ? h->n_frames_multi : h->n_frames_single) += h->sched[k].b - h->sched[k].a;
+        h->n_seg = 0;                                  // counted once
+        h->last_fused = 0;
+    }
     uint64_t rows = 0;
     for (int f = 0; f < T; f++) {
         const FrameCtrl &c = h->ctrl_host[f];

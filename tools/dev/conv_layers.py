@@ -1,7 +1,7 @@
 """Per-layer timing of the UNet convolutions at 1280x704, batch B (standalone conv ABI, random data)."""
 import ctypes, sys
 import numpy as np, torch
-sys.path.insert(0, '.'); sys.path.insert(0, 'scratch')
+sys.path.insert(0, '.'); sys.path.insert(0, 'tools/dev')
 from test_conv import L, pad16, cout_pad, dev
 USE_ROW = (len(sys.argv) > 2 and sys.argv[2] == 'row')
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8

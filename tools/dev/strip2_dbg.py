@@ -1,6 +1,6 @@
 """STRIP2_DEBUG build only: issuer wait breakdown per strip2 layer."""
 import ctypes, sys, torch
-sys.path.insert(0, '.'); sys.path.insert(0, 'scratch')
+sys.path.insert(0, '.'); sys.path.insert(0, 'tools/dev')
 from test_conv import L, pad16, cout_pad, dev
 B, H, W = 8, 704, 1280
 layers = [("conv1", 12, 0, 32, 7, 0), ("conv2", 32, 0, 32, 7, 0), ("down1.c1", 32, 0, 64, 5, 1), ("down1.c2", 64, 0, 64, 5, 1),

@@ -1,7 +1,7 @@
 """GPU harness: halo-resident row conv kernel vs torch; probes the descriptor base-offset policy."""
 import ctypes, sys
 import numpy as np, torch
-sys.path.insert(0, '.'); sys.path.insert(0, 'scratch')
+sys.path.insert(0, '.'); sys.path.insert(0, 'tools/dev')
 from test_conv import L, pad16, cout_pad, to_nhwc16, dev
 
 def pack_w_row(w, C1, C2, KC):

@@ -1,6 +1,6 @@
 """Timing of the fused up-sampling convolution (up5.conv1 shape: 64 -> 32 at 1280x704, batch 8)."""
 import ctypes, sys, numpy as np, torch
-sys.path.insert(0, '.'); sys.path.insert(0, 'scratch')
+sys.path.insert(0, '.'); sys.path.insert(0, 'tools/dev')
 from test_conv import L, pad16, cout_pad, dev
 B, H, W, C, Co = 8, 704, 1280, 64, 32
 a = torch.randn((B, H // 2, W // 2, C), device=dev).half()

@@ -47,6 +47,7 @@ struct ConvParams {
     int BN;                     // output channels per CTA (UMMA N)
     int stages;                 // depth of the producer / issuer ring (<= kStages)
     int MT;                     // 8x16 pixel tiles per CTA (1 or 2, stacked vertically: M = 128 or 2 x 128)
+    int co_fast;                // grid order: 1 = output-channel blocks in gridDim.x
     int tiles_x, tiles_y;
     int out_cstride;            // channel stride (elements) of the fp16 NHWC output
     int out_mode;               // 0: fp16 NHWC; 1: fp32 [N,H,W,8], first co_real channels
@@ -71,10 +72,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __shared__ uint32_t tmem_base_smem;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x;
+    // output-channel block fastest (gridDim.x when p.co_fast): the CTAs that share an input window run together, so
+    // the window comes from DRAM once and from L2 for its siblings
+    const int tile = p.co_fast ? blockIdx.y : blockIdx.x;
     const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, n = tile / (p.tiles_x * p.tiles_y);
     const int x0 = tx * kTileW, y0 = ty * kTileH * MT;
-    const int n0 = blockIdx.y * p.BN;
+    const int n0 = (p.co_fast ? blockIdx.x : blockIdx.y) * p.BN;
     const int Ctot = p.C1 + p.C2;
     const int slabs = Ctot / p.KC;
     const int k_iters = p.KH * p.KW * slabs;
@@ -971,7 +974,10 @@ conv_strip2up_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 // 1.4 % of the layer's pixels; the partial sums are ~0.2 in magnitude, fp16 rounding of them stays below
 // 1e-3 absolute), widened to float32 for the cross-lane reduction: a halving butterfly after which lane co holds
 // output channel co.
-__global__ void __launch_bounds__(128, 4)
+// latency-bound (a warp's pixel is a serial chain of gathers, half2 FMAs and shuffles); block shape by template so
+// that occupancy against registers can be measured (V2E_BORDER_CFG: 0 = 4 warps x 4 blocks/SM, 1 = 4 x 5, 2 = 8 x 3)
+template <int kBorderThreads, int kBorderBlocks>
+__global__ void __launch_bounds__(kBorderThreads, kBorderBlocks)
 conv_up2_border_kernel(const __half *__restrict__ L, const __half *__restrict__ wgt, const float *__restrict__ bias,
                        __half *__restrict__ out, int N, int H, int W, int out_cstride, float slope) {
     constexpr int C = 64, BN = 32;
@@ -1172,7 +1178,13 @@ int v2e_conv_prepare(V2eConvLaunch *L, const void *x1, int C1, const void *x2, i
     if (C2) { if ((rc = v2e_make_act_tmap(&L->tmA2, x2, N, H, W, C2, p.KC))) return rc; }
     else L->tmA2 = L->tmA;
     if ((rc = v2e_make_wgt_tmap(&L->tmB, wgt, Cout_pad, KH * KW * (C1 + C2), p.KC, p.BN))) return rc;
-    L->grid = dim3((unsigned)(p.tiles_x * p.tiles_y * N), (unsigned)(Cout_pad / p.BN), 1);
+    {
+        static int co_fast = -1;
+        if (co_fast < 0) { const char *e = getenv("V2E_CONV_CO_FAST"); co_fast = e ? atoi(e) : 1; }
+        const unsigned tiles = (unsigned)(p.tiles_x * p.tiles_y * N), cob = (unsigned)(Cout_pad / p.BN);
+        p.co_fast = (co_fast && cob > 1 && tiles <= 65535u) ? 1 : 0;
+        L->grid = p.co_fast ? dim3(cob, tiles, 1) : dim3(tiles, cob, 1);
+    }
     size_t stage = (size_t)p.MT * kBM * p.KC * 2 + (((size_t)p.BN * p.KC * 2 + 1023) & ~(size_t)1023);
     L->smem = stage * p.stages + 1024;
     return V2E_OK;
@@ -1590,9 +1602,20 @@ int v2e_conv_up2_launch(const V2eUpLaunch *L, cudaStream_t st) {
     if (skip_frame < 0) skip_frame = getenv("V2E_UP2_NO_FRAME") ? 1 : 0;
     if (skip_frame) return V2E_OK;
     static PerDeviceOnce battr_once;
-    if (battr_once.first()) cudaFuncSetAttribute(conv_up2_border_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 9 * 64 * 2);
-    conv_up2_border_kernel<<<L->grid * 4, 128, 32 * 9 * 64 * 2, st>>>(L->low, L->w_plain, p.bias, (__half *)p.out, p.N, p.H, p.W,
-                                                                       p.out_cstride, p.slope);
+    if (battr_once.first()) {
+        cudaFuncSetAttribute(conv_up2_border_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 9 * 64 * 2);
+        cudaFuncSetAttribute(conv_up2_border_kernel<128, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 9 * 64 * 2);
+        cudaFuncSetAttribute(conv_up2_border_kernel<256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 9 * 64 * 2);
+    }
+    static int bcfg = -1;
+    if (bcfg < 0) { const char *e = getenv("V2E_BORDER_CFG"); bcfg = e ? atoi(e) : 0; }
+    const size_t bsm = 32 * 9 * 64 * 2;
+    if (bcfg == 1)
+        conv_up2_border_kernel<128, 5><<<L->grid * 5, 128, bsm, st>>>(L->low, L->w_plain, p.bias, (__half *)p.out, p.N, p.H, p.W, p.out_cstride, p.slope);
+    else if (bcfg == 2)
+        conv_up2_border_kernel<256, 3><<<L->grid * 3, 256, bsm, st>>>(L->low, L->w_plain, p.bias, (__half *)p.out, p.N, p.H, p.W, p.out_cstride, p.slope);
+    else
+        conv_up2_border_kernel<128, 4><<<L->grid * 4, 128, bsm, st>>>(L->low, L->w_plain, p.bias, (__half *)p.out, p.N, p.H, p.W, p.out_cstride, p.slope);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return v2e_set_error(V2E_E_CUDA, "conv_strip2up_kernel launch: %s", cudaGetErrorString(e));
     return V2E_OK;

@@ -116,6 +116,27 @@ def block_texture_clip(H, W, n_src, seed=0, block=4, shift=(8, 4)):
                      for k in range(n_src)])
 
 
+def unet_activation_bytes(in_ch, out_ch, H, W, B):
+    """Algorithmic DRAM bytes of one UNet pass: every layer's input + output activations once (fp16 NHWC, channels
+    padded to 16; the up blocks' first convolution charged with the LOW-resolution tensor it is a function of; fp32
+    heads), weights excluded (19.8 M parameters, L2-resident)."""
+    pad16 = lambda c: (c + 15) // 16 * 16
+    ch = [32, 64, 128, 256, 512, 512]
+    layers = [(in_ch, 32, 0), (32, 32, 0)]
+    for d in range(5):
+        layers += [(ch[d], ch[d + 1], d + 1), (ch[d + 1], ch[d + 1], d + 1)]
+    uo, ui = [512, 256, 128, 64, 32], [512, 512, 256, 128, 64]
+    for k in range(5):
+        layers += [(ui[k], uo[k], 4 - k), (2 * uo[k], uo[k], 4 - k)]
+    layers += [(32, out_ch, 0)]
+    tot = 0.0
+    for i, (ci, co, lvl) in enumerate(layers):
+        inb = pad16(ci) * 2 / (4 if i in (12, 14, 16, 18, 20) else 1)
+        outb = 32 if i == len(layers) - 1 else pad16(co) * 2
+        tot += B * (H >> lvl) * (W >> lvl) * (inb + outb)
+    return tot
+
+
 def slomo_weights():
     """Seeded variance-preserving weights in the reference's checkpoint layout ('state_dictFC' /
     'state_dictAT'); the real SuperSloMo39.ckpt is not available offline (README.md:95-96)."""
@@ -477,6 +498,7 @@ def main():
         big = max(range(23), key=lambda i: ms23[i])
         achieved = conv_fl.value / (conv_ms.value * 1e-3) / 1e12
         tr_conv = traffic.get("conv_all_layers_per_step")
+        n_batches_p = -(-(NS - 1) // args.batch)
         # pixel model alone: the multi-frame path on a clean 1280x720 clip (the headline texture translating 1 px per
         # frame, CLI defaults, device RNG), K repetitions of one 80-frame chunk between one event pair. Measured on its
         # own clip because the headline's interpolated frames -- synthesised by a RANDOM-weight network -- flicker: in
@@ -514,6 +536,8 @@ def main():
                          "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                          "frac": achieved / pk["bf16_tflops_sustained"], "traffic": tr_conv,
                          "peak_source": pk["source"] + " (sustained 16-bit dense; burst %.1f)" % pk["bf16_tflops"],
+                         "algorithmic_bytes": n_batches_p * (unet_activation_bytes(2, 4, Hd, Wd, args.batch) +
+                                                             U * unet_activation_bytes(12, 5, Hd, Wd, args.batch)),
                          "flops_per_step": conv_fl.value, "conv_ms_per_step": conv_ms.value,
                          "launches_per_step": conv_n.value, "share_of_step": conv_ms.value / step_ms_prof,
                          "largest_layer": {"layer": names[big], "ms_per_launch": ms23[big] / n23[big],

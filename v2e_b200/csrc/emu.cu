@@ -1585,6 +1585,34 @@ emu_fused_update_kernel(EmuDev d, const FusedFrame *__restrict__ ff, const uint8
     }
 }
 
+// the records of up to 8 consecutive units of one frame as one list: off[k] = first list position of unit k
+struct FusedWarpList {
+    uint32_t off[9];
+    uint32_t total;
+    // unit of list position i and that unit's first position (selects: no dynamically indexed array)
+    __device__ __forceinline__ int unit_of(uint32_t i, uint32_t &first) const {
+        int k = 0;
+        first = off[0];
+#pragma unroll
+        for (int m = 1; m < 8; m++)
+            if (i >= off[m]) { k = m; first = off[m]; }
+        return k;
+    }
+};
+__device__ __forceinline__ void fused_warp_list(FusedWarpList &wl, const uint32_t *cnt, int nu, int lane) {
+    uint32_t c = lane < nu ? cnt[lane] : 0u;
+    uint32_t incl = c;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const uint32_t excl = incl - c;
+#pragma unroll
+    for (int m = 0; m < 8; m++) wl.off[m] = __shfl_sync(0xffffffffu, excl, m);
+    wl.off[8] = wl.total = __shfl_sync(0xffffffffu, incl, 7);
+}
+
 // pass 2: histogram per (iteration, polarity) and maximum per frame from the records. Block = (frame, group of
 // kFusedGroup units). The block's own per-segment counts are kept for the emit kernel (blk_cnt).
 __global__ void __launch_bounds__(kThreads)
@@ -1601,11 +1629,20 @@ emu_fused_count_kernel(EmuDev d, int T, int groups, const uint16_t *__restrict__
     uint32_t *hist = d.hist_pre + (size_t)f * d.seg_stride;
     const int ue = min(d.units, (g + 1) * kFusedGroup);
     int local_max = 0;
-    for (int u = g * kFusedGroup + warp; u < ue; u += kWarps) {
-        const uint32_t n = rec_cnt[(size_t)f * d.units + u];
-        const uint16_t *seg = rec_list + ((size_t)f * d.units + u) * kUnitPx;
-        for (uint32_t b0 = 0; b0 < n; b0 += 32) {
-            const uint32_t r = b0 + lane < n ? (uint32_t)seg[b0 + lane] : 0u;
+    // a warp takes 8 consecutive units and walks their records as ONE list (a unit holds ~13 records at 0.1
+    // events/px/frame: unit by unit two thirds of the lanes would idle)
+    for (int ub = g * kFusedGroup + warp * 8; ub < ue; ub += kWarps * 8) {
+        const int nu = min(8, ue - ub);
+        FusedWarpList wl;
+        fused_warp_list(wl, rec_cnt + (size_t)f * d.units + ub, nu, lane);
+        for (uint32_t i0 = 0; i0 < wl.total; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            uint32_t r = 0u;
+            if (i < wl.total) {
+                uint32_t first;
+                const int k = wl.unit_of(i, first);
+                r = (uint32_t)rec_list[((size_t)f * d.units + ub + k) * kUnitPx + (i - first)];
+            }
             const int mag = (int)(r >> 10), neg = (int)((r >> 7) & 1u), flags = (int)((r >> 8) & 3u);
             local_max = max(local_max, mag);
             const int magc = min(mag, d.iter_cap);
@@ -1736,13 +1773,21 @@ emu_fused_emit_kernel(EmuDev d, const FrameParams *__restrict__ fp, int T, int g
         return segoff[seg] + atomicAdd(&cursor[seg], count);
     };
     const int ue = min(d.units, (g + 1) * kFusedGroup);
-    for (int u = g * kFusedGroup + warp; u < ue; u += kWarps) {
-        const uint32_t n = rec_cnt[(size_t)f * d.units + u];
-        const uint16_t *seg = rec_list + ((size_t)f * d.units + u) * kUnitPx;
-        for (uint32_t b0 = 0; b0 < n; b0 += 32) {
-            const uint32_t r = b0 + lane < n ? (uint32_t)seg[b0 + lane] : 0u;
+    for (int ub = g * kFusedGroup + warp * 8; ub < ue; ub += kWarps * 8) {
+        const int nu = min(8, ue - ub);
+        FusedWarpList wl;
+        fused_warp_list(wl, rec_cnt + (size_t)f * d.units + ub, nu, lane);
+        for (uint32_t i0 = 0; i0 < wl.total; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            uint32_t r = 0u;
+            int k = 0;
+            if (i < wl.total) {
+                uint32_t first;
+                k = wl.unit_of(i, first);
+                r = (uint32_t)rec_list[((size_t)f * d.units + ub + k) * kUnitPx + (i - first)];
+            }
             const int mag = (int)(r >> 10), neg = (int)((r >> 7) & 1u), flags = (int)((r >> 8) & 3u);
-            const int idx = u * kUnitPx + (int)(r & 127u);
+            const int idx = (ub + k) * kUnitPx + (int)(r & 127u);
             const float fx = (float)(idx % d.W), fy = (float)(idx / d.W);
             const float pv = neg ? -1.0f : 1.0f;
             const int wmax = __reduce_max_sync(0xffffffffu, mag);

@@ -48,6 +48,7 @@ struct ConvParams {
     int stages;                 // depth of the producer / issuer ring (<= kStages)
     int MT;                     // 8x16 pixel tiles per CTA (1 or 2, stacked vertically: M = 128 or 2 x 128)
     int co_fast;                // grid order: 1 = output-channel blocks in gridDim.x
+    int cl;                     // 1: clusters of 2 CTAs along the tile axis, weight slabs multicast
     int tiles_x, tiles_y;
     int out_cstride;            // channel stride (elements) of the fp16 NHWC output
     int out_mode;               // 0: fp16 NHWC; 1: fp32 [N,H,W,8], first co_real channels
@@ -59,7 +60,7 @@ struct ConvParams {
 
 __global__ void __launch_bounds__(kConvThreads)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-               const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBh, const ConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: stages of [A 128 x KC fp16][B BN x KC fp16], 1024-byte aligned
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -83,8 +84,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int k_iters = p.KH * p.KW * slabs;
     const uint32_t tmem_cols = MT * p.BN < 32 ? 32 : MT * p.BN;
 
+    // p.cl: clusters of two CTAs with the same output-channel block and neighbouring pixel tiles share every weight
+    // slab: each CTA loads half of it and multicasts it to both (tmBh: box of BN / 2 rows). A stage may be refilled
+    // only when BOTH issuers have released it, so the empty barriers count two arrivals, delivered by multicast commits.
+    const uint32_t crank = p.cl ? cluster_ctarank() : 0u;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < kStages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], p.cl ? 2 : 1); }
         mbar_init(&tmem_full_bar, 1);
         fence_barrier_init();
     }
@@ -92,6 +97,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         prefetch_tmap(&tmA);
         if (p.C2) prefetch_tmap(&tmA2);
         prefetch_tmap(&tmB);
+        if (p.cl) prefetch_tmap(&tmBh);
     }
     if (warp == 1) {
         tmem_alloc(&tmem_base_smem, tmem_cols);
@@ -99,6 +105,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     tcgen05_fence_before();
     __syncthreads();
+    if (p.cl) cluster_sync_all();            // the peer's barriers exist before anything is multicast into this CTA
     tcgen05_fence_after();
     const uint32_t tmem_acc = tmem_base_smem;
 
@@ -120,7 +127,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (c < p.C1) tma_load_4d(sa + mt * a_bytes, &tmA, &full_bar[stage], c, x0 + s - pw, y0 + mt * kTileH + r - ph, n);
                         else tma_load_4d(sa + mt * a_bytes, &tmA2, &full_bar[stage], c - p.C1, x0 + s - pw, y0 + mt * kTileH + r - ph, n);
                     }
-                    tma_load_2d(sb, &tmB, &full_bar[stage], tap * Ctot + c, n0);
+                    if (p.cl) {
+                        const uint32_t hb = b_bytes_raw / 2;
+                        tma_load_2d_multicast(sb + crank * hb, &tmBh, &full_bar[stage], tap * Ctot + c, n0 + (int)crank * (p.BN / 2),
+                                              (uint16_t)3);
+                    } else {
+                        tma_load_2d(sb, &tmB, &full_bar[stage], tap * Ctot + c, n0);
+                    }
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -145,7 +158,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int j = 0; j < ksteps; j++)
                     umma_f16_pred(tmem_acc + (uint32_t)(mt * p.BN), desc_with_lo(dhi, alo + (uint32_t)mt * a16 + 2u * j),
                                   desc_with_lo(dhi, blo + 2u * j), idesc, (uint32_t)((it | j) != 0), leader);
-            umma_commit_pred(&empty_bar[stage], leader);     // frees the smem slot once these MMAs retire
+            if (p.cl) umma_commit_mc_pred(&empty_bar[stage], (uint16_t)3, leader);      // ... in both CTAs of the cluster
+            else umma_commit_pred(&empty_bar[stage], leader);     // frees the smem slot once these MMAs retire
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         umma_commit_pred(&tmem_full_bar, leader);            // accumulator complete
@@ -157,7 +171,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tcgen05_fence_after();
         for (int mt = 0; mt < MT; mt++) {
             const int py = y0 + mt * kTileH + m / kTileW, px = x0 + m % kTileW;
-            const bool inb = py < p.H && px < p.W;
+            const bool inb = py < p.H && px < p.W && n < p.N;      // n >= N: the padding tile of an odd cluster grid
             const size_t pix = ((size_t)n * p.H + py) * p.W + px;
             for (int c0 = 0; c0 < p.BN; c0 += 16) {
                 uint32_t v[16];
@@ -192,6 +206,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tcgen05_fence_after();
         tmem_dealloc(tmem_acc, tmem_cols);
     }
+    if (p.cl) cluster_sync_all();            // nobody leaves while the peer may still arrive on its barriers
 }
 
 
@@ -1144,7 +1159,7 @@ static int conv_use_bn256(int Cout_pad, long tiles) {
 }
 
 struct V2eConvLaunch {
-    CUtensorMap tmA, tmA2, tmB;
+    CUtensorMap tmA, tmA2, tmB, tmBh;
     ConvParams p;
     dim3 grid;
     size_t smem;
@@ -1183,7 +1198,14 @@ int v2e_conv_prepare(V2eConvLaunch *L, const void *x1, int C1, const void *x2, i
         if (co_fast < 0) { const char *e = getenv("V2E_CONV_CO_FAST"); co_fast = e ? atoi(e) : 1; }
         const unsigned tiles = (unsigned)(p.tiles_x * p.tiles_y * N), cob = (unsigned)(Cout_pad / p.BN);
         p.co_fast = (co_fast && cob > 1 && tiles <= 65535u) ? 1 : 0;
-        L->grid = p.co_fast ? dim3(cob, tiles, 1) : dim3(tiles, cob, 1);
+        // clusters of two along the tile axis (weight-slab multicast): V2E_CONV_CLUSTER=1
+        static int cl = -1;
+        if (cl < 0) { const char *e = getenv("V2E_CONV_CLUSTER"); cl = e ? atoi(e) : 0; }
+        p.cl = (cl && p.BN >= 32 && (tiles + 1) / 2 * 2 <= 65534u && tiles >= 64) ? 1 : 0;
+        const unsigned tiles_l = p.cl ? (tiles + 1) / 2 * 2 : tiles;
+        L->grid = p.co_fast ? dim3(cob, tiles_l, 1) : dim3(tiles_l, cob, 1);
+        L->tmBh = L->tmB;
+        if (p.cl && (rc = v2e_make_wgt_tmap(&L->tmBh, wgt, Cout_pad, KH * KW * (C1 + C2), p.KC, p.BN / 2))) return rc;
     }
     size_t stage = (size_t)p.MT * kBM * p.KC * 2 + (((size_t)p.BN * p.KC * 2 + 1023) & ~(size_t)1023);
     L->smem = stage * p.stages + 1024;
@@ -1193,8 +1215,26 @@ int v2e_conv_prepare(V2eConvLaunch *L, const void *x1, int C1, const void *x2, i
 int v2e_conv_launch(const V2eConvLaunch *L, cudaStream_t st) {
     static PerDeviceOnce attr_once;
     if (attr_once.first()) cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    conv_tc_kernel<<<L->grid, kConvThreads, L->smem, st>>>(L->tmA, L->tmA2, L->tmB, L->p);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e;
+    if (L->p.cl) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = L->grid;
+        cfg.blockDim = dim3(kConvThreads);
+        cfg.dynamicSmemBytes = L->smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = L->p.co_fast ? 1 : 2;
+        attr.val.clusterDim.y = L->p.co_fast ? 2 : 1;
+        attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, conv_tc_kernel, L->tmA, L->tmA2, L->tmB, L->tmBh, L->p);
+    } else {
+        conv_tc_kernel<<<L->grid, kConvThreads, L->smem, st>>>(L->tmA, L->tmA2, L->tmB, L->tmBh, L->p);
+        e = cudaGetLastError();
+    }
     if (e != cudaSuccess) return v2e_set_error(V2E_E_CUDA, "conv_tc_kernel launch: %s", cudaGetErrorString(e));
     return V2E_OK;
 }

@@ -46,6 +46,22 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tm, ui
         ::"r"(smem_u32(dst)), "l"((uint64_t)tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
 
+// ---- thread-block clusters: TMA multicast and cross-CTA barrier arrival ----------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// the box lands at the same CTA-relative offset in every CTA of `mask`, and completes `bar` (same offset) in each
+__device__ __forceinline__ void tma_load_2d_multicast(void *dst, const CUtensorMap *tm, uint64_t *bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+
 // ---- tcgen05 -------------------------------------------------------------------------------------
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -88,6 +104,13 @@ __device__ __forceinline__ void umma_commit_pred(uint64_t *bar, uint32_t leader)
         "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
         "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
         ::"r"(smem_u32(bar)), "r"(leader) : "memory");
+}
+// arrives on `bar` (same CTA-relative offset) in every CTA of `mask` once this thread's MMAs have retired
+__device__ __forceinline__ void umma_commit_mc_pred(uint64_t *bar, uint16_t mask, uint32_t leader) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+        ::"r"(smem_u32(bar)), "h"(mask), "r"(leader) : "memory");
 }
 __device__ __forceinline__ uint64_t desc_with_lo(uint64_t hi_part, uint32_t lo) {
     return (hi_part & 0xFFFFFFFF00000000ull) | (uint64_t)lo;

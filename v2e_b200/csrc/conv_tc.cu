@@ -36,7 +36,7 @@
 namespace {
 
 constexpr int kTileH = 8, kTileW = 16, kBM = kTileH * kTileW;   // 128 pixels = UMMA M
-constexpr int kStages = 3;
+constexpr int kStages = 4;      // barrier slots; ConvParams::stages is the depth actually used (2-4)
 constexpr int kConvThreads = 192;
 
 struct ConvParams {
@@ -1175,7 +1175,7 @@ int v2e_conv_prepare(V2eConvLaunch *L, const void *x1, int C1, const void *x2, i
     p.N = N; p.H = H; p.W = W; p.C1 = C1; p.C2 = C2; p.KH = KH; p.KW = KW;
     p.KC = v2e_conv_pick_kc(C1, C2);
     p.BN = v2e_conv_pick_bn(Cout_pad);
-    p.stages = kStages;
+    p.stages = 3;
     p.MT = 1;
     p.tiles_x = (W + kTileW - 1) / kTileW;
     p.tiles_y = (H + kTileH - 1) / kTileH;
@@ -1185,6 +1185,12 @@ int v2e_conv_prepare(V2eConvLaunch *L, const void *x1, int C1, const void *x2, i
         // two vertically adjacent pixel tiles per CTA share every weight slab: the same 94 B/clk as the N = 256 tiles
         p.MT = 2; p.stages = 2;
         p.tiles_y = (p.tiles_y + 1) / 2;
+    }
+    {
+        // experiment (V2E_CONV_KC32=1): the 48 KB stages of the two variants above as four 24 KB stages of 32 channels
+        static int kc32 = -1;
+        if (kc32 < 0) { const char *e = getenv("V2E_CONV_KC32"); kc32 = e ? atoi(e) : 0; }
+        if (kc32 && p.stages == 2 && p.KC == 64) { p.KC = 32; p.stages = 4; }
     }
     p.out_cstride = out_cstride; p.out_mode = out_mode; p.co_real = co_real; p.slope = slope;
     p.bias = bias; p.out = out;

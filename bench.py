@@ -199,13 +199,36 @@ class ClockSampler:
 REF_SAMPLE = dict(n_src=3, batch=1)      # 2 frame pairs in 2 batches (the reference needs >= 2 batches, slomo.py:323)
 
 
+def port_sample(frames, U, params):
+    """Fallback of the CPU arm where the vendored reference (oracle/_ref) is missing: the oracle PORT of the same
+    sample (float32 torch restatement of SuperSloMo + scalar C pixel model), kind "port"."""
+    import torch
+    import slomo_ref
+    from emu_oracle import OracleEmulator
+    wts = slomo_weights()
+    t0 = time.perf_counter()
+    out, times, _ = slomo_ref.interpolate_frames(frames, wts["state_dictFC"], wts["state_dictAT"], U, batch_size=1)
+    t_slomo = time.perf_counter() - t0
+    em = OracleEmulator(seed=1, **params)
+    dt = 1.0 / (SRC_FPS * U)
+    t1 = time.perf_counter()
+    for i in range(out.shape[0]):
+        em.generate_events(out[i], i * dt)
+    t_emu = time.perf_counter() - t1
+    return dict(events=em.num_events_total, interp_frames=int(out.shape[0]), seconds=t_slomo + t_emu, slomo_s=t_slomo,
+                emu_s=t_emu, threads=torch.get_num_threads(), kind="port", slomo_device="cpu")
+
+
 def reference_sample(H, W, U, params, device="cpu", seed=0):
     """3 source frames of the headline clip -> SuperSloMo.interpolate (x U, its .npy / .png folders) -> read_image
     -> EventEmulator.generate_events: the GPU arm's per-frame work (flow net amortised over U frames), 2U frames."""
     import ref_run
+    import ref_shim
     if os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "v2ecore")):
         os.environ.setdefault("V2E_REFERENCE_ROOT", os.path.join(ROOT, "oracle", "_ref"))
     frames = source_clip(H, W, 9, seed=seed)[:REF_SAMPLE["n_src"]]
+    if not (os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "v2ecore")) or ref_shim.reference_available()):
+        return port_sample(frames, U, params)          # oracle/_ref was not built (python oracle/make_ref.py)
     return ref_run.run_reference(frames, SRC_FPS, U, REF_SAMPLE["batch"], params, slomo_weights(), seed=1,
                                  device=device)
 

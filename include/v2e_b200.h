@@ -410,6 +410,13 @@ int v2e_events_to_aedat2(const float *events_dev, uint64_t n, int size_x, int si
  * frames_f64_dev (nullable): (frame + fs) / (2 fs) float64, what the reference returns; frames_u8_dev (nullable):
  * uint8(img * 255), what it writes to the AVI (renderer.py:345-347). max_events_per_frame sizes the grid. */
 /* ------------------------------------------------------------------------- */
+/* ExposureMode.AREA_COUNT (renderer.py:246-261): frame slices of one packet -- a frame ends when a cell of
+ * area_dimension x area_dimension pixels has collected area_count events. counts_dev: [cells_w][cells_h] int32,
+ * persistent between packets (zero it once). Sequential by definition: one thread walks the packet.
+ * *n_frames_dev = finished frames (their slices in starts_dev / ends_dev), or -1 if more than max_frames. */
+int v2e_render_area_scan(const float *events_dev, int64_t n, int area_dimension, int area_count, int cells_w, int cells_h,
+                         int32_t *counts_dev, int64_t *starts_dev, int64_t *ends_dev, int max_frames,
+                         int32_t *n_frames_dev, void *stream);
 int v2e_render_frames(const float *events_dev, const int64_t *starts_dev, const int64_t *ends_dev, int n_frames,
                       int64_t max_events_per_frame, int height, int width, int full_scale_count, int32_t *acc_dev,
                       double *frames_f64_dev, uint8_t *frames_u8_dev, void *stream);

@@ -37,30 +37,27 @@ def test_cuda_renderer_matches_reference_fixtures():
     from v2e_b200.renderer import EventRenderer, ExposureMode
     done = 0
     for name, mode, value, H, W, fs, area, pk in _golden():
-        if mode == 3:
-            with pytest.raises(NotImplementedError):
-                EventRenderer(full_scale_count=fs, exposure_mode=ExposureMode(mode), exposure_value=value, area_dimension=area)
-            continue
-        r = EventRenderer(full_scale_count=fs, exposure_mode=ExposureMode(mode), exposure_value=value)
+        r = EventRenderer(full_scale_count=fs, exposure_mode=ExposureMode(mode), exposure_value=value, area_dimension=area)
         for ev, want in pk:
             got = r.render_events_to_frames(ev, H, W, return_frames=True)
             got = np.zeros((0, H, W)) if got is None else got
             assert got.dtype == np.float64 and got.shape == want.shape and np.array_equal(got, want), name
         done += 1
-    assert done == 4
+    assert done == 5
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", [1, 2, 4])
+@pytest.mark.parametrize("mode", [1, 2, 3, 4])
 def test_cuda_renderer_matches_oracle_on_a_dense_stream(mode):
     """346x260, ~200 k events per packet from the pixel model's own output format (CUDA tensor in, device frames out)."""
     import torch
     from v2e_b200.renderer import EventRenderer, ExposureMode
     H, W = 260, 346
     rng = np.random.default_rng(5)
-    value = {1: 0.002, 2: 30000, 4: 0}[mode]
-    o = RenderOracle(3, mode, value)
-    r = EventRenderer(full_scale_count=3, exposure_mode=ExposureMode(mode), exposure_value=value)
+    value = {1: 0.002, 2: 30000, 3: 400, 4: 0}[mode]
+    area = 16 if mode == 3 else None
+    o = RenderOracle(3, mode, value, area)
+    r = EventRenderer(full_scale_count=3, exposure_mode=ExposureMode(mode), exposure_value=value, area_dimension=area)
     t = 0.0
     for _ in range(3):
         n = 40000

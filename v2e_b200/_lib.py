@@ -117,6 +117,7 @@ _SIGS = {
     "v2e_prep_create": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _i, ctypes.POINTER(_vp)]),
     "v2e_prep_destroy": (_i, [_vp]),
     "v2e_prep_run": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "v2e_render_area_scan": (_i, [_vp, ctypes.c_int64, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp]),
     "v2e_render_frames": (_i, [_vp, _vp, _vp, _i, ctypes.c_int64, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "v2e_events_to_h5_rows": (_i, [_vp, _u64, _vp, _vp]),
     "v2e_events_to_aedat2": (_i, [_vp, _u64, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),

@@ -46,7 +46,56 @@ render_finish_kernel(const int32_t *__restrict__ acc, size_t n, int fs, double *
     if (u8) u8[i] = (uint8_t)(x * 255.0);                                   // (img * 255).astype(np.uint8)
 }
 
+// ExposureMode.AREA_COUNT (renderer.py:246-261, 287-291): a frame ends when any area_dimension x area_dimension
+// cell has collected area_count events. Inherently sequential (every event depends on the counters the previous ones
+// left, and the counters are cleared when a frame ends), so ONE thread walks the packet; the counters persist between
+// packets like the reference's self.area_counts. Writes the slices of the finished frames with the reference's
+// end-of-packet rule (end >= n - 1 -> stop; the last event of a packet is never rendered).
+__global__ void render_area_scan_kernel(const float4 *__restrict__ ev, int64_t n, int area_dim, int area_count, int nw, int nh,
+                                        int32_t *__restrict__ counts, int64_t *__restrict__ starts, int64_t *__restrict__ ends,
+                                        int max_frames, int32_t *__restrict__ n_frames) {
+    if (blockIdx.x || threadIdx.x) return;
+    int k = 0;
+    int64_t idx = 0;
+    bool overflow = false;
+    while (true) {
+        int64_t e = idx;
+        for (e = idx; e < n; e++) {
+            const float4 r = ev[e];
+            const int x = (int)floorf(r.y / (float)area_dim), y = (int)floorf(r.z / (float)area_dim);
+            if (x < 0 || x >= nw || y < 0 || y >= nh) continue;         // cannot happen for in-frame events
+            const int c = 1 + counts[x * nh + y];
+            counts[x * nh + y] = c;
+            if (c >= area_count) {
+                for (int i = 0; i < nw * nh; i++) counts[i] = 0;
+                break;
+            }
+        }
+        int64_t end = e < n ? e : n - 1;                                // numba leaves the loop variable at the last index
+        if (idx >= n) end = idx;                                        // empty range: ev_idx = start
+        if (end >= n - 1) break;                                        // the rest stays in the (dropped) current frame
+        if (k >= max_frames) { overflow = true; break; }
+        starts[k] = idx;
+        ends[k] = end;
+        k++;
+        idx = end;
+    }
+    *n_frames = overflow ? -1 : k;
+}
+
 }  // namespace
+
+extern "C" int v2e_render_area_scan(const float *events_dev, int64_t n, int area_dimension, int area_count, int cells_w,
+                                    int cells_h, int32_t *counts_dev, int64_t *starts_dev, int64_t *ends_dev,
+                                    int max_frames, int32_t *n_frames_dev, void *stream) {
+    if (!events_dev || !counts_dev || !starts_dev || !ends_dev || !n_frames_dev || n < 1 || area_dimension < 1 ||
+        area_count < 1 || cells_w < 1 || cells_h < 1 || max_frames < 1)
+        return v2e_set_error(V2E_E_INVALID, "bad area-scan arguments%s", "");
+    render_area_scan_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const float4 *)events_dev, n, area_dimension, area_count, cells_w,
+                                                                 cells_h, counts_dev, starts_dev, ends_dev, max_frames, n_frames_dev);
+    CU(cudaGetLastError());
+    return V2E_OK;
+}
 
 extern "C" int v2e_render_frames(const float *events_dev, const int64_t *starts_dev, const int64_t *ends_dev, int n_frames,
                                  int64_t max_events_per_frame, int height, int width, int full_scale_count,

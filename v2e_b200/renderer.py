@@ -6,7 +6,7 @@ frame being filled is dropped at the start of every call (renderer.py:270), the 
 rendered (:300-303), DURATION boundaries are searchsorted(left / right) over the whole packet so an event exactly on a
 boundary lands in both frames. Host code here decides which rows belong to which frame (exposure bookkeeping); the
 scatter-add, clip and normalisation run on the device. AREA_COUNT exposure is a sequential data-dependent scan
-(renderer.py:246-261) and is not built (raises). Writing the AVI (`dvs_vid`) is the reference's job: it is delegated
+(renderer.py:246-261): one device thread walks the packet (v2e_render_area_scan). Writing the AVI (`dvs_vid`) is the reference's job: it is delegated
 to v2ecore.v2e_utils.video_writer when that imports, otherwise ignored with a warning.
 """
 import ctypes
@@ -50,8 +50,9 @@ class EventRenderer(object):
         elif mode == ExposureMode.COUNT:
             self.event_count = int(self.exposure_value)
         elif mode == ExposureMode.AREA_COUNT:
-            raise NotImplementedError("ExposureMode.AREA_COUNT is a sequential scan over the events "
-                                      "(renderer.py:246-261); not built on the GPU")
+            self.area_count = int(self.exposure_value)
+            if not area_dimension:
+                raise ValueError("ExposureMode.AREA_COUNT needs area_dimension")
         self.video_output_file_name = dvs_vid
         self.video_output_file = None
         self.frame_times_output_file = None
@@ -132,6 +133,29 @@ class EventRenderer(object):
             k += 1
         return starts, ends, tmid
 
+    def _area_slices(self, ev, height, width):
+        """ExposureMode.AREA_COUNT (renderer.py:213-217, 246-261, 287-291): a frame ends when a cell of
+        area_dimension^2 pixels has collected area_count events; the cell counters persist between packets."""
+        n = ev.shape[0]
+        if self.area_counts is None:
+            self._cells = (1 + width // self.area_dimension, 1 + height // self.area_dimension)
+            self.area_counts = torch.zeros(self._cells, dtype=torch.int32, device=self.device)
+        cap = n // max(self.area_count, 1) + 2
+        st_t = torch.empty((cap,), dtype=torch.int64, device=self.device)
+        en_t = torch.empty((cap,), dtype=torch.int64, device=self.device)
+        nf = torch.zeros((1,), dtype=torch.int32, device=self.device)
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        with torch.cuda.device(self.device):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            _lib.check(self._lib.v2e_render_area_scan(p(ev), n, int(self.area_dimension), int(self.area_count),
+                                                      self._cells[0], self._cells[1], p(self.area_counts), p(st_t), p(en_t),
+                                                      cap, p(nf), stream))
+        k = int(nf.item())
+        if k < 0:
+            raise RuntimeError("area-count scan: more frames than its slice table holds")
+        starts, ends = st_t[:k].tolist(), en_t[:k].tolist()
+        return starts, ends, list(zip(starts, ends)), st_t[:k].contiguous(), en_t[:k].contiguous()
+
     def render_events_to_frames(self, event_arr, height, width, return_frames=False, return_device=False):
         """renderer.py:161: float64 frames [k, height, width] in 0..1 for the frames this packet finished, or None."""
         self.width, self.height = width, height
@@ -144,12 +168,17 @@ class EventRenderer(object):
         else:
             ev = event_arr.to(self.device, torch.float32).contiguous()
         self.currentFrame = None                          # renderer.py:270
-        starts, ends, tinfo = self._slices(ev[:, 0].contiguous())
+        if self.exposure_mode == ExposureMode.AREA_COUNT:
+            starts, ends, tinfo, st_t, en_t = self._area_slices(ev, height, width)
+        else:
+            starts, ends, tinfo = self._slices(ev[:, 0].contiguous())
+            st_t = en_t = None
         k = len(starts)
         if k == 0:
             return None
-        st_t = torch.tensor(starts, dtype=torch.int64, device=self.device)
-        en_t = torch.tensor(ends, dtype=torch.int64, device=self.device)
+        if st_t is None:
+            st_t = torch.tensor(starts, dtype=torch.int64, device=self.device)
+            en_t = torch.tensor(ends, dtype=torch.int64, device=self.device)
         acc = torch.empty((k, height, width), dtype=torch.int32, device=self.device)
         want_u8 = self.video_output_file is not None
         img = torch.empty((k, height, width), dtype=torch.float64, device=self.device) if (return_frames or return_device) else None
@@ -168,7 +197,7 @@ class EventRenderer(object):
                 self.video_output_file.write(cv2.cvtColor(host[f], cv2.COLOR_GRAY2BGR))
                 if self.exposure_mode == ExposureMode.SOURCE:
                     t = ts_host[0]
-                elif self.exposure_mode == ExposureMode.COUNT:
+                elif self.exposure_mode in (ExposureMode.COUNT, ExposureMode.AREA_COUNT):
                     t = (ts_host[starts[f]] + ts_host[ends[f]]) / 2
                 else:
                     t = tinfo[f]
